@@ -1,0 +1,184 @@
+// common.cuh -- shared declarations of the fos_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/fos_b200.h"
+
+namespace fos {
+
+// ---------------------------------------------------------------------------------------
+// errors: C++ exceptions inside the library, converted to int32 codes at the C boundary
+// ---------------------------------------------------------------------------------------
+struct Error : std::runtime_error {
+    int32_t code;
+    Error(int32_t c, const std::string &what) : std::runtime_error(what), code(c) {}
+};
+
+#define FOS_CUDA(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess) {                                                                         \
+            throw ::fos::Error(FOS_ERR_CUDA, std::string(#expr) + " failed: " + cudaGetErrorString(_e) + \
+                                                 " (" __FILE__ ":" + std::to_string(__LINE__) + ")");    \
+        }                                                                                                \
+    } while (0)
+
+#define FOS_REQUIRE(cond, msg)                                                   \
+    do {                                                                         \
+        if (!(cond)) throw ::fos::Error(FOS_ERR_INVALID, std::string(msg));      \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------
+// sizes
+// ---------------------------------------------------------------------------------------
+constexpr int64_t PAD = 16;  // every segment of a device vector is padded to 16 doubles (128 B)
+inline int64_t ru(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+constexpr int MAX_PARTIALS = 1024;  // upper bound on the grid of any reduction kernel
+constexpr int RED_SLOTS = 8;        // quantities reduced at once by one kernel
+
+// ---------------------------------------------------------------------------------------
+// device control block: every scalar of the CG recurrence and of the algorithms lives on
+// the device, so a whole batch of CG iterations is enqueued without host round trips.
+// ---------------------------------------------------------------------------------------
+struct Ctrl {
+    // conjugate gradients (utilities/conjugategradients.jl:31-55)
+    double rn;      // r.r
+    double alpha;   // rn / <Ap,p>
+    double beta;    // rn / rnold
+    double rnorm;   // ||r|| of the last update
+    double tol;     // absolute tolerance of this solve
+    int32_t iter;   // loop-body count (what conjugategradient! returns)
+    int32_t max_iters;
+    int32_t done;   // 1 -> every remaining CG kernel of the batch returns immediately
+    int32_t warn_maxit;
+    // GAPA (solvers/gapa.jl)
+    double alpha12;
+    // status check (HSDEStatus.jl / FeasibilityStatus.jl)
+    int32_t status;
+    int32_t nrec;       // records written so far in this run
+    double feas_err;
+    // GAPP line search
+    double ls_normbest;
+    double ls_alphabest;
+    // scratch for scalar hand-off between kernels
+    double scal[8];
+};
+
+// deterministic two-level reduction workspace
+struct RedBuf {
+    double *partials;       // [RED_SLOTS][MAX_PARTIALS]
+    unsigned int *counter;  // last-block ticket, self-resetting
+};
+
+// ---------------------------------------------------------------------------------------
+// Result view of one dual mat-vec: per-band row partials and per-slot column partials.
+//   (A X)[v][i]   = sum_{b < nb}  rowpart[b*rp_sb + v*rp_sv + i]
+//   (A' W)[v][j]  = sum_{s in [slot_base[band], slot_base[band+1])} colpart[s*cp_ss + v*cp_sv + (j & bw_mask)]
+//                   with band = j >> bw_shift
+// A complete (already reduced) result is the special case nb = 1, one band, one slot.
+// ---------------------------------------------------------------------------------------
+struct MVView {
+    const double *rowpart;
+    int32_t nb;
+    int64_t rp_sb, rp_sv;
+    const double *colpart;
+    const int32_t *slot_base;
+    int32_t bw_shift;
+    int64_t bw_mask;
+    int64_t cp_ss, cp_sv;
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ double mv_ax(const MVView &V, int v, int64_t i)
+{
+    double s = 0.0;
+    const double *p = V.rowpart + v * V.rp_sv + i;
+    for (int b = 0; b < V.nb; b++) s += p[b * V.rp_sb];
+    return s;
+}
+__device__ __forceinline__ double mv_atw(const MVView &V, int v, int64_t j)
+{
+    int64_t band = j >> V.bw_shift;
+    int64_t jj = j & V.bw_mask;
+    int s0 = V.slot_base[band], s1 = V.slot_base[band + 1];
+    double s = 0.0;
+    const double *p = V.colpart + v * V.cp_sv + jj;
+    for (int t = s0; t < s1; t++) s += p[t * V.cp_ss];
+    return s;
+}
+
+// no-contraction arithmetic: the reference's broadcasts round every operation separately
+__device__ __forceinline__ double mul_(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double add_(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double sub_(double a, double b) { return __dsub_rn(a, b); }
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Block-level deterministic reduction of NQ quantities followed by the "last block finishes"
+// pattern.  Returns true in every thread of the last block to arrive; in that block tot[q]
+// (thread 0 only) holds the grid-wide sums.  The summation tree has a fixed shape for a given
+// grid, so results are bitwise reproducible run to run (no floating-point atomics).
+template <int NQ, int BLOCK>
+__device__ __forceinline__ bool grid_reduce(const double (&val)[NQ], double (&tot)[NQ], const RedBuf &rb)
+{
+    __shared__ double s_w[NQ][BLOCK / 32];
+    __shared__ bool s_last;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < NQ; q++) {
+        double v = warp_sum(val[q]);
+        if (lane == 0) s_w[q][w] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+            double s = 0.0;
+            for (int k = 0; k < BLOCK / 32; k++) s += s_w[q][k];
+            rb.partials[q * MAX_PARTIALS + blockIdx.x] = s;
+        }
+        __threadfence();
+        unsigned int t = atomicAdd(rb.counter, 1u);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return false;
+    __threadfence();
+#pragma unroll
+    for (int q = 0; q < NQ; q++) {
+        const volatile double *p = rb.partials + q * MAX_PARTIALS;
+        double acc = 0.0;
+        for (unsigned int k = threadIdx.x; k < gridDim.x; k += BLOCK) acc += p[k];
+        acc = warp_sum(acc);
+        if (lane == 0) s_w[q][w] = acc;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+            double s = 0.0;
+            for (int k = 0; k < BLOCK / 32; k++) s += s_w[q][k];
+            tot[q] = s;
+        }
+        *rb.counter = 0u;  // self-reset for the next kernel on the stream
+    }
+    return true;
+}
+#endif  // __CUDACC__
+
+}  // namespace fos

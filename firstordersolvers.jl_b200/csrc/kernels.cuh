@@ -1,0 +1,719 @@
+// kernels.cuh -- K2 (Q / KKT epilogues fused with the CG dot products), K3 (CG vector
+// updates with fused reductions), K4 (cone projections fused with the relaxation /
+// averaging steps of GAP, GAPA, FISTA, Dykstra, GAPP) and K6 (residual check).
+//
+// All vectors use the padded device layout (see solver.cuh): every segment starts on a
+// 128-byte boundary and its padding holds zeros, so each kernel is a flat loop.
+// Arithmetic that the reference performs as separate broadcast operations is done with
+// non-contracting intrinsics (mul_/add_/sub_) in the same order.
+#pragma once
+#include "common.cuh"
+
+namespace fos {
+
+constexpr int VBLOCK = 256;  // block size of every vector kernel
+
+struct Lay {
+    int32_t form;  // 0 = HSDE conic (operator Q, l x l), 1 = plain matrix operator (am x an), 2 = symmetric n x n
+    int64_t n, m;  // A is m x n
+    int64_t n_pad, m_pad;
+    int64_t LP;  // HSDE: padded half length n_pad + m_pad + PAD.  plain: unused (0)
+    int64_t NP;  // padded iterate length
+    // HSDE offsets inside a half: x at 0, y at n_pad, tau at n_pad + m_pad
+};
+
+enum { K2_OUT = 0, K2_AP = 1, K2_RESID = 2 };
+
+#ifdef __CUDACC__
+
+__device__ __forceinline__ bool cg_skip(const Ctrl *ctrl) { return ctrl->done != 0; }
+
+// =======================================================================================
+// K2, HSDE operator:  out = [I Q'; Q -I] * in     (affinepluslinear.jl:37-49 on top of
+// HSDEAffine.jl:41-65).  V holds A*[in1.x in2.x] (v = 0,1) and A'*[in1.y in2.y].
+//   K2_OUT   : out written.
+//   K2_AP    : in = p, out = Ap, fused <Ap,p>; last block: alpha = rn / <Ap,p>   (cg :38-39)
+//   K2_RESID : in = x0, r = rhs - out, p = r, fused <r,r>; last block: rn, iter = 1 (cg :32-36)
+// =======================================================================================
+template <int MODE>
+__global__ void __launch_bounds__(VBLOCK)
+k2_kkt_hsde(Lay L, MVView V, const double *__restrict__ in, const double *__restrict__ c,
+            const double *__restrict__ b, double *__restrict__ out, const double *__restrict__ rhs,
+            double *__restrict__ r, double *__restrict__ p, Ctrl *ctrl, RedBuf rb, int predicated)
+{
+    if (predicated && cg_skip(ctrl)) return;
+    const int64_t LP = L.LP, oy = L.n_pad, ot = L.n_pad + L.m_pad;
+    const double tau1 = in[ot], tau2 = in[LP + ot];
+    double q[5] = {0, 0, 0, 0, 0};  // c.X1, b.W1, c.X2, b.W2, fused dot
+    for (int64_t e = (int64_t)blockIdx.x * VBLOCK + threadIdx.x; e < ot; e += (int64_t)gridDim.x * VBLOCK) {
+        double o1 = 0.0, o2 = 0.0;
+        const double i1 = in[e], i2 = in[LP + e];
+        if (e < oy) {
+            if (e < L.n) {
+                const double cj = c[e];
+                // (Q B).x = A'B.y + B.tau*c   (HSDEAffine.jl:51,54)
+                const double q1 = add_(mv_atw(V, 0, e), mul_(tau1, cj));
+                const double q2 = add_(mv_atw(V, 1, e), mul_(tau2, cj));
+                o1 = add_(-q2, i1);  // Q'in2 + in1  (transpose = negate, HSDEAffine.jl:61-65)
+                o2 = sub_(q1, i2);   // Q in1 - in2
+                q[0] = fma(cj, i1, q[0]);
+                q[2] = fma(cj, i2, q[2]);
+            }
+        } else {
+            const int64_t i = e - oy;
+            if (i < L.m) {
+                const double bi = b[i];
+                // (Q B).y = -(A B.x - B.tau*b)   (HSDEAffine.jl:52,55,56)
+                const double q1 = -sub_(mv_ax(V, 0, i), mul_(tau1, bi));
+                const double q2 = -sub_(mv_ax(V, 1, i), mul_(tau2, bi));
+                o1 = add_(-q2, i1);
+                o2 = sub_(q1, i2);
+                q[1] = fma(bi, i1, q[1]);
+                q[3] = fma(bi, i2, q[3]);
+            }
+        }
+        if (MODE == K2_OUT) {
+            out[e] = o1;
+            out[LP + e] = o2;
+        } else if (MODE == K2_AP) {
+            out[e] = o1;
+            out[LP + e] = o2;
+            q[4] = fma(o1, i1, q[4]);
+            q[4] = fma(o2, i2, q[4]);
+        } else {
+            const double r1 = sub_(rhs[e], o1), r2 = sub_(rhs[LP + e], o2);
+            r[e] = r1;
+            r[LP + e] = r2;
+            p[e] = r1;
+            p[LP + e] = r2;
+            q[4] = fma(r1, r1, q[4]);
+            q[4] = fma(r2, r2, q[4]);
+        }
+    }
+    double tot[5];
+    if (grid_reduce<5, VBLOCK>(q, tot, rb) && threadIdx.x == 0) {
+        // (Q B).tau = -c.B.x - b.B.y   (HSDEAffine.jl:57)
+        const double q1t = sub_(-tot[0], tot[1]);
+        const double q2t = sub_(-tot[2], tot[3]);
+        const double o1 = add_(-q2t, tau1);
+        const double o2 = sub_(q1t, tau2);
+        if (MODE == K2_OUT) {
+            out[ot] = o1;
+            out[LP + ot] = o2;
+        } else if (MODE == K2_AP) {
+            out[ot] = o1;
+            out[LP + ot] = o2;
+            const double pAp = tot[4] + o1 * tau1 + o2 * tau2;
+            ctrl->alpha = ctrl->rn / pAp;
+        } else {
+            const double r1 = sub_(rhs[ot], o1), r2 = sub_(rhs[LP + ot], o2);
+            r[ot] = r1;
+            r[LP + ot] = r2;
+            p[ot] = r1;
+            p[LP + ot] = r2;
+            ctrl->rn = tot[4] + r1 * r1 + r2 * r2;
+            ctrl->iter = 1;
+        }
+    }
+}
+
+// K2, plain operator:  out = [I A'; A -I] * in   with V = (A*in1, A'*in2), one right-hand side.
+template <int MODE>
+__global__ void __launch_bounds__(VBLOCK)
+k2_kkt_plain(Lay L, MVView V, const double *__restrict__ in, double *__restrict__ out,
+             const double *__restrict__ rhs, double *__restrict__ r, double *__restrict__ p, Ctrl *ctrl, RedBuf rb,
+             int predicated)
+{
+    if (predicated && cg_skip(ctrl)) return;
+    double q[1] = {0};
+    for (int64_t e = (int64_t)blockIdx.x * VBLOCK + threadIdx.x; e < L.NP; e += (int64_t)gridDim.x * VBLOCK) {
+        double o = 0.0;
+        const double ie = in[e];
+        if (e < L.n_pad) {
+            if (e < L.n) o = add_(mv_atw(V, 0, e), ie);  // affinepluslinear.jl:45-46
+        } else {
+            const int64_t i = e - L.n_pad;
+            if (i < L.m) o = sub_(mv_ax(V, 0, i), ie);  // :47-48
+        }
+        if (MODE == K2_OUT) {
+            out[e] = o;
+        } else if (MODE == K2_AP) {
+            out[e] = o;
+            q[0] = fma(o, ie, q[0]);
+        } else {
+            const double re = sub_(rhs[e], o);
+            r[e] = re;
+            p[e] = re;
+            q[0] = fma(re, re, q[0]);
+        }
+    }
+    double tot[1];
+    if (grid_reduce<1, VBLOCK>(q, tot, rb) && threadIdx.x == 0) {
+        if (MODE == K2_AP) ctrl->alpha = ctrl->rn / tot[0];
+        else if (MODE == K2_RESID) {
+            ctrl->rn = tot[0];
+            ctrl->iter = 1;
+        }
+    }
+}
+
+// K2, symmetric matrix operator (form 2): out = A*in.  Serves conjugategradient! on a plain SPD
+// matrix (test/conjugateGradient.jl) through fos_cg_dense.
+template <int MODE>
+__global__ void __launch_bounds__(VBLOCK)
+k2_spd(Lay L, MVView V, const double *__restrict__ in, double *__restrict__ out, const double *__restrict__ rhs,
+       double *__restrict__ r, double *__restrict__ p, Ctrl *ctrl, RedBuf rb, int predicated)
+{
+    if (predicated && cg_skip(ctrl)) return;
+    double q[1] = {0};
+    for (int64_t e = (int64_t)blockIdx.x * VBLOCK + threadIdx.x; e < L.NP; e += (int64_t)gridDim.x * VBLOCK) {
+        const double o = e < L.n ? mv_ax(V, 0, e) : 0.0;
+        if (MODE == K2_OUT) {
+            out[e] = o;
+        } else if (MODE == K2_AP) {
+            out[e] = o;
+            q[0] = fma(o, in[e], q[0]);
+        } else {
+            const double re = sub_(rhs[e], o);
+            r[e] = re;
+            p[e] = re;
+            q[0] = fma(re, re, q[0]);
+        }
+    }
+    double tot[1];
+    if (grid_reduce<1, VBLOCK>(q, tot, rb) && threadIdx.x == 0) {
+        if (MODE == K2_AP) ctrl->alpha = ctrl->rn / tot[0];
+        else if (MODE == K2_RESID) {
+            ctrl->rn = tot[0];
+            ctrl->iter = 1;
+        }
+    }
+}
+
+// Y = Q*B or Q'*B (HSDEAffine.jl:41-65) from V = (A*B.x, A'*B.y); unit-level entry point.
+static __global__ void __launch_bounds__(VBLOCK)
+k2_q_hsde(Lay L, MVView V, const double *__restrict__ B, const double *__restrict__ c, const double *__restrict__ b,
+          double *__restrict__ Y, int transpose, RedBuf rb)
+{
+    const int64_t oy = L.n_pad, ot = L.n_pad + L.m_pad;
+    const double tau = B[ot];
+    double q[2] = {0, 0};
+    for (int64_t e = (int64_t)blockIdx.x * VBLOCK + threadIdx.x; e < ot; e += (int64_t)gridDim.x * VBLOCK) {
+        double o = 0.0;
+        if (e < oy) {
+            if (e < L.n) {
+                o = add_(mv_atw(V, 0, e), mul_(tau, c[e]));
+                q[0] = fma(c[e], B[e], q[0]);
+            }
+        } else {
+            const int64_t i = e - oy;
+            if (i < L.m) {
+                o = -sub_(mv_ax(V, 0, i), mul_(tau, b[i]));
+                q[1] = fma(b[i], B[e], q[1]);
+            }
+        }
+        Y[e] = transpose ? -o : o;
+    }
+    double tot[2];
+    if (grid_reduce<2, VBLOCK>(q, tot, rb) && threadIdx.x == 0) {
+        const double o = sub_(-tot[0], tot[1]);
+        Y[ot] = transpose ? -o : o;
+    }
+}
+
+// rhs of the affine projection (affinepluslinear.jl:94-95):  rhs1 = beta*Op'x2 + x1 - q.
+// HSDE (beta = 1, q = 0, b = 0; HSDE.jl:22): V = (A*x2.x, A'*x2.y), x2 = (r, s, kappa).
+static __global__ void __launch_bounds__(VBLOCK)
+k2_rhs_hsde(Lay L, MVView V, const double *__restrict__ xin, const double *__restrict__ c,
+            const double *__restrict__ b, double *__restrict__ rhs, RedBuf rb)
+{
+    const int64_t LP = L.LP, oy = L.n_pad, ot = L.n_pad + L.m_pad;
+    const double kap = xin[LP + ot];
+    double q[2] = {0, 0};
+    for (int64_t e = (int64_t)blockIdx.x * VBLOCK + threadIdx.x; e < ot; e += (int64_t)gridDim.x * VBLOCK) {
+        double o = 0.0;
+        const double x2 = xin[LP + e];
+        if (e < oy) {
+            if (e < L.n) {
+                const double t = -add_(mv_atw(V, 0, e), mul_(kap, c[e]));  // (Q'x2).x
+                o = add_(t, xin[e]);
+                q[0] = fma(c[e], x2, q[0]);
+            }
+        } else {
+            const int64_t i = e - oy;
+            if (i < L.m) {
+                const double t = sub_(mv_ax(V, 0, i), mul_(kap, b[i]));  // (Q'x2).y = -(Q x2).y
+                o = add_(t, xin[e]);
+                q[1] = fma(b[i], x2, q[1]);
+            }
+        }
+        rhs[e] = o;
+    }
+    double tot[2];
+    if (grid_reduce<2, VBLOCK>(q, tot, rb) && threadIdx.x == 0) {
+        const double t = -sub_(-tot[0], tot[1]);
+        rhs[ot] = add_(t, xin[ot]);
+    }
+}
+
+// plain operator: rhs1 = beta*A'x2 + x1 - q ; rhs2 keeps b (pre-stored, affinepluslinear.jl:76-77)
+static __global__ void __launch_bounds__(VBLOCK)
+k2_rhs_plain(Lay L, MVView V, const double *__restrict__ xin, const double *__restrict__ qv, double beta,
+             double *__restrict__ rhs)
+{
+    for (int64_t e = (int64_t)blockIdx.x * VBLOCK + threadIdx.x; e < L.n; e += (int64_t)gridDim.x * VBLOCK)
+        rhs[e] = sub_(add_(mul_(beta, mv_atw(V, 0, e)), xin[e]), qv[e]);
+}
+
+// =======================================================================================
+// K3: CG updates (conjugategradients.jl:40-51)
+// =======================================================================================
+// x += alpha p ; r -= alpha Ap ; ||r|| ; stop test ; beta
+static __global__ void __launch_bounds__(VBLOCK)
+k3_cg_update(int64_t NP, double *__restrict__ x, double *__restrict__ r, const double *__restrict__ p,
+             const double *__restrict__ Ap, Ctrl *ctrl, RedBuf rb)
+{
+    if (cg_skip(ctrl)) return;
+    const double alpha = ctrl->alpha;
+    double q[1] = {0};
+    for (int64_t e = (int64_t)blockIdx.x * VBLOCK + threadIdx.x; e < NP; e += (int64_t)gridDim.x * VBLOCK) {
+        x[e] = add_(x[e], mul_(alpha, p[e]));               // :40
+        const double re = sub_(r[e], mul_(alpha, Ap[e]));   // :41
+        r[e] = re;
+        q[0] = fma(re, re, q[0]);
+    }
+    double tot[1];
+    if (grid_reduce<1, VBLOCK>(q, tot, rb) && threadIdx.x == 0) {
+        const double rr = tot[0];
+        const double rnorm = sqrt(rr);
+        ctrl->rnorm = rnorm;
+        if (rnorm <= ctrl->tol || ctrl->iter >= ctrl->max_iters) {  // :42
+            ctrl->done = 1;
+            if (ctrl->iter >= ctrl->max_iters) ctrl->warn_maxit = 1;  // :53
+        } else {
+            const double rnold = ctrl->rn;  // :45
+            ctrl->rn = rr;                  // :46
+            ctrl->beta = rr / rnold;        // :47
+            ctrl->iter += 1;                // :51
+        }
+    }
+}
+// p = beta p + r   (:49-50, two roundings)
+static __global__ void __launch_bounds__(VBLOCK)
+k3_cg_dir(int64_t NP, double *__restrict__ p, const double *__restrict__ r, const Ctrl *ctrl)
+{
+    if (cg_skip(ctrl)) return;
+    const double beta = ctrl->beta;
+    for (int64_t e = (int64_t)blockIdx.x * VBLOCK + threadIdx.x; e < NP; e += (int64_t)gridDim.x * VBLOCK)
+        p[e] = add_(mul_(beta, p[e]), r[e]);
+}
+
+static __global__ void k_cg_begin(Ctrl *ctrl, double tol, int max_iters)
+{
+    ctrl->tol = tol;
+    ctrl->max_iters = max_iters;
+    ctrl->done = 0;
+    ctrl->iter = 0;
+}
+
+// =======================================================================================
+// generic vector helpers
+// =======================================================================================
+// out = a*X + b*Y with three roundings (the reference's  y .= a.*y .+ (1-a).*x  form).
+// part2_scale multiplies X on entries >= part2_off first (the y2 .*= beta of affinepluslinear.jl:124).
+// use_a12: take a from ctrl->alpha12 and b = 1 - a (GAPA).
+static __global__ void __launch_bounds__(VBLOCK)
+k_relax(int64_t NP, double *__restrict__ out, double a, const double *__restrict__ X, double bcoef,
+        const double *__restrict__ Y, int64_t part2_off, double part2_scale, const Ctrl *ctrl, int use_a12)
+{
+    if (use_a12) {
+        a = ctrl->alpha12;
+        bcoef = 1.0 - a;
+    }
+    for (int64_t e = (int64_t)blockIdx.x * VBLOCK + threadIdx.x; e < NP; e += (int64_t)gridDim.x * VBLOCK) {
+        double xe = X[e];
+        if (part2_scale != 1.0 && e >= part2_off) xe = mul_(xe, part2_scale);
+        out[e] = add_(mul_(a, xe), mul_(bcoef, Y[e]));
+    }
+}
+// out = X (with the part-2 scaling)
+static __global__ void __launch_bounds__(VBLOCK)
+k_copy_scaled(int64_t NP, double *__restrict__ out, const double *__restrict__ X, int64_t part2_off,
+              double part2_scale)
+{
+    for (int64_t e = (int64_t)blockIdx.x * VBLOCK + threadIdx.x; e < NP; e += (int64_t)gridDim.x * VBLOCK) {
+        double xe = X[e];
+        if (part2_scale != 1.0 && e >= part2_off) xe = mul_(xe, part2_scale);
+        out[e] = xe;
+    }
+}
+// out = X + a*Y
+static __global__ void __launch_bounds__(VBLOCK)
+k_add_scaled(int64_t NP, double *out, const double *X, double a, const double *Y, const Ctrl *ctrl, int a_from_ls)
+{
+    if (a_from_ls) a = ctrl->ls_alphabest;
+    for (int64_t e = (int64_t)blockIdx.x * VBLOCK + threadIdx.x; e < NP; e += (int64_t)gridDim.x * VBLOCK)
+        out[e] = add_(X[e], mul_(a, Y[e]));
+}
+// out = X - Y
+static __global__ void __launch_bounds__(VBLOCK)
+k_sub(int64_t NP, double *out, const double *X, const double *Y)
+{
+    for (int64_t e = (int64_t)blockIdx.x * VBLOCK + threadIdx.x; e < NP; e += (int64_t)gridDim.x * VBLOCK)
+        out[e] = sub_(X[e], Y[e]);
+}
+// Dykstra (dykstra.jl:29-31):  w = x + p  (input of P1)
+// and after P1:  p = (x + p) - y   ;   w2 = y + q  (input of P2)
+static __global__ void __launch_bounds__(VBLOCK)
+k_dykstra_mid(int64_t NP, const double *__restrict__ w, const double *__restrict__ y, double *__restrict__ p,
+              const double *__restrict__ q, double *__restrict__ w2)
+{
+    for (int64_t e = (int64_t)blockIdx.x * VBLOCK + threadIdx.x; e < NP; e += (int64_t)gridDim.x * VBLOCK) {
+        p[e] = sub_(w[e], y[e]);
+        w2[e] = add_(y[e], q[e]);
+    }
+}
+
+// =======================================================================================
+// K4: cone projections (cones.jl) fused with the algorithm's relaxation / averaging
+// =======================================================================================
+enum : uint8_t {
+    OP_ZERO = 0,      // Zero cone, dual of Free, padding
+    OP_COPY = 1,      // Free cone, dual of Zero
+    OP_MAX0 = 2,      // NonNeg (self-dual), tau, kappa
+    OP_MIN0 = 3,      // NonPos (self-dual per cones.jl:102)
+    OP_SOC_HEAD = 4,
+    OP_SOC_TAIL = 5,
+    OP_SOCD_HEAD = 6,  // dual via Moreau, cones.jl:80-85
+    OP_SOCD_TAIL = 7,
+    OP_PRE = 8         // projected value already in proj[] (PSD cones, K5)
+};
+
+struct SocCone {
+    int64_t head;   // padded index of t
+    int64_t len;    // total length including t
+    int32_t chunk0; // first norm chunk
+    int32_t nchunk;
+    int32_t dual;
+    int32_t pad_;
+};
+struct SocScale {  // result of the norm pass for one cone
+    int32_t mode;  // primal: 0 -> 0, 1 -> copy, 2 -> scale.  dual: 0 -> copy x, 1 -> 0, 2 -> scale
+    int32_t pad_;
+    double rho;    // 0.5*(1 + t/nx) of the (possibly negated) input
+    double nx;
+};
+constexpr int SOC_CHUNK = 2048;
+
+// pass 1: one block per chunk of a SOC tail, squared-norm partial; the last block folds the
+// chunk partials per cone (in chunk order) and classifies each cone.
+static __global__ void __launch_bounds__(VBLOCK)
+k4_soc_norms(const double *__restrict__ in, const SocCone *__restrict__ cones, int ncones,
+             const int32_t *__restrict__ chunk_cone, double *__restrict__ chunk_sum, SocScale *__restrict__ scale,
+             unsigned int *counter)
+{
+    __shared__ double s_w[VBLOCK / 32];
+    __shared__ bool s_last;
+    const int ch = blockIdx.x;
+    const SocCone C = cones[chunk_cone[ch]];
+    const int64_t k0 = (int64_t)(ch - C.chunk0) * SOC_CHUNK;  // offset inside the tail
+    const int64_t tail = C.len - 1;
+    const int64_t k1 = k0 + SOC_CHUNK < tail ? k0 + SOC_CHUNK : tail;
+    double acc = 0.0;
+    for (int64_t k = k0 + threadIdx.x; k < k1; k += VBLOCK) {
+        const double w = in[C.head + 1 + k];
+        acc = fma(w, w, acc);
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int k = 0; k < VBLOCK / 32; k++) s += s_w[k];
+        chunk_sum[ch] = s;
+        __threadfence();
+        s_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int cidx = threadIdx.x; cidx < ncones; cidx += VBLOCK) {
+        const SocCone K = cones[cidx];
+        double s = 0.0;
+        const volatile double *cs = chunk_sum;
+        for (int k = 0; k < K.nchunk; k++) s += cs[K.chunk0 + k];
+        const double nx = sqrt(s);
+        double t = in[K.head];
+        if (K.dual) t = -t;
+        SocScale R;
+        R.pad_ = 0;
+        R.nx = nx;
+        R.rho = 0.0;
+        if (t <= -nx) R.mode = 0;
+        else if (t >= nx) R.mode = 1;
+        else {
+            R.mode = 2;
+            R.rho = 0.5 * (1.0 + t / nx);
+        }
+        scale[cidx] = R;
+    }
+    if (threadIdx.x == 0) *counter = 0u;
+}
+
+__device__ __forceinline__ double cone_project(uint8_t op, double x, const double *__restrict__ proj, int64_t e,
+                                               const int32_t *__restrict__ cone_of, const SocScale *__restrict__ scale)
+{
+    switch (op) {
+    case OP_ZERO: return 0.0;
+    case OP_COPY: return x;
+    case OP_MAX0: return x > 0.0 ? x : 0.0;   // max(x,0); NaN -> 0 like Julia's max? (NaN stays NaN in Julia)
+    case OP_MIN0: return x < 0.0 ? x : 0.0;
+    case OP_PRE: return proj[e];
+    default: break;
+    }
+    const SocScale S = scale[cone_of[e]];
+    if (op == OP_SOC_HEAD) return S.mode == 0 ? 0.0 : (S.mode == 1 ? x : mul_(S.rho, S.nx));
+    if (op == OP_SOC_TAIL) return S.mode == 0 ? 0.0 : (S.mode == 1 ? x : mul_(S.rho, x));
+    // dual: y = x + P(-x)
+    if (op == OP_SOCD_HEAD) {
+        const double pj = S.mode == 0 ? 0.0 : (S.mode == 1 ? -x : mul_(S.rho, S.nx));
+        return add_(x, pj);
+    }
+    const double pj = S.mode == 0 ? 0.0 : (S.mode == 1 ? -x : mul_(S.rho, -x));
+    return add_(x, pj);
+}
+
+enum { EPI_NONE = 0, EPI_GAP = 1, EPI_GAPA = 2, EPI_FISTA = 3, EPI_DYKSTRA = 4, EPI_GAPP_PROJ = 5, EPI_LS = 6 };
+
+struct EpiArgs {
+    double a2, om_a2;  // alpha2, 1 - alpha2
+    double a, om_a;    // alpha, 1 - alpha
+    double coef;       // FISTA (told-1)/t
+    double betaA;      // GAPA beta
+    double *tmp2;      // relaxed S2 output
+    double *x;         // iterate (updated in place)
+    double *aux1;      // FISTA: xold (out) ; Dykstra: q (in/out)
+    double *aux2;      // FISTA: y (out)    ; Dykstra: y (in)
+    double ls_alpha;   // EPI_LS: the step length tested
+};
+
+// proj = P_S2(in);  then the algorithm-specific epilogue:
+//   EPI_GAP   (gap.jl:58,78)        tmp2 = a2*proj + (1-a2)*in ; x = a*tmp2 + (1-a)*x
+//   EPI_GAPA  (gapa.jl:77,96-103)   same with a2 = alpha12, plus the angle estimate -> new alpha12
+//   EPI_FISTA (fista.jl:39-46)      xold = x ; x = proj ; y = x + coef*(x - xold)
+//   EPI_DYKSTRA (dykstra.jl:32-35)  x = proj ; q = in - x        (in = y + q)
+//   EPI_GAPP_PROJ (gapproj.jl:61-62) tmp2 = a2*proj + (1-a2)*in ; x = tmp2
+//   EPI_LS    (gapproj.jl:49-55)    ||proj - in|| ; last block keeps the strictly smallest
+template <int EPI>
+__global__ void __launch_bounds__(VBLOCK)
+k4_cone_apply(int64_t NP, const double *__restrict__ in, double *__restrict__ proj, const uint8_t *__restrict__ ops,
+              const int32_t *__restrict__ cone_of, const SocScale *__restrict__ scale, EpiArgs E, Ctrl *ctrl,
+              RedBuf rb)
+{
+    double a2 = E.a2, om_a2 = E.om_a2;
+    if (EPI == EPI_GAPA) {
+        a2 = ctrl->alpha12;
+        om_a2 = 1.0 - a2;
+    }
+    double q[3] = {0, 0, 0};
+    for (int64_t e = (int64_t)blockIdx.x * VBLOCK + threadIdx.x; e < NP; e += (int64_t)gridDim.x * VBLOCK) {
+        const double t1 = in[e];
+        const double pj = cone_project(ops[e], t1, proj, e, cone_of, scale);
+        proj[e] = pj;
+        if (EPI == EPI_GAP || EPI == EPI_GAPA) {
+            const double t2 = add_(mul_(a2, pj), mul_(om_a2, t1));
+            E.tmp2[e] = t2;
+            const double xo = E.x[e];
+            if (EPI == EPI_GAPA) {  // normedScalar(tmp2,tmp1,tmp1,x)  gapa.jl:36-47
+                const double d1 = sub_(t2, t1), d2 = sub_(t1, xo);
+                q[0] = fma(d1, d2, q[0]);
+                q[1] = fma(d1, d1, q[1]);
+                q[2] = fma(d2, d2, q[2]);
+            }
+            E.x[e] = add_(mul_(E.a, t2), mul_(E.om_a, xo));
+        } else if (EPI == EPI_GAPP_PROJ) {
+            const double t2 = add_(mul_(a2, pj), mul_(om_a2, t1));
+            E.tmp2[e] = t2;
+            E.x[e] = t2;
+        } else if (EPI == EPI_FISTA) {
+            const double xo = E.x[e];
+            E.aux1[e] = xo;
+            E.x[e] = pj;
+            E.aux2[e] = add_(pj, mul_(E.coef, sub_(pj, xo)));
+        } else if (EPI == EPI_DYKSTRA) {
+            E.x[e] = pj;
+            E.aux1[e] = sub_(t1, pj);
+        } else if (EPI == EPI_LS) {
+            const double d = sub_(pj, t1);
+            q[0] = fma(d, d, q[0]);
+        }
+    }
+    if (EPI == EPI_GAPA) {
+        double tot[3];
+        if (grid_reduce<3, VBLOCK>(q, tot, rb) && threadIdx.x == 0) {
+            double scl = fabs(tot[0]) / sqrt(tot[1] * tot[2]);  // normedScalar, gapa.jl:47
+            if (isnan(scl)) scl = 0.0;                          // clamp keeps NaN, :97 maps it to 0
+            else scl = scl < 0.0 ? 0.0 : (scl > 1.0 ? 1.0 : scl);  // clamp(scl, 0, 1)  :96
+            const double s = sqrt(1.0 - scl * scl);
+            const double aopt = 2.0 / (1.0 + s);
+            ctrl->alpha12 = (1.0 - E.betaA) * aopt + E.betaA * 2.0;
+        }
+    } else if (EPI == EPI_LS) {
+        double tot[3];
+        if (grid_reduce<3, VBLOCK>(q, tot, rb) && threadIdx.x == 0) {
+            const double nt = sqrt(tot[0]);
+            if (nt < ctrl->ls_normbest) {  // gapproj.jl:52-55
+                ctrl->ls_normbest = nt;
+                ctrl->ls_alphabest = E.ls_alpha;
+            }
+        }
+    }
+}
+
+static __global__ void k_ls_begin(Ctrl *ctrl)
+{
+    ctrl->ls_normbest = INFINITY;
+    ctrl->ls_alphabest = -1.0;
+}
+
+// =======================================================================================
+// K6: status checks
+// =======================================================================================
+// HSDE (HSDEStatus.jl:27-71).  V = (A*z.x, A'*z.y), one right-hand side.
+static __global__ void __launch_bounds__(VBLOCK)
+k6_check_hsde(Lay L, MVView V, const double *__restrict__ z, const double *__restrict__ c,
+              const double *__restrict__ b, double nb, double ncn, double eps, int64_t iter_i, int cgiter_host,
+              Ctrl *ctrl, double *__restrict__ recs, int rec_cap, RedBuf rb)
+{
+    const int64_t LP = L.LP, oy = L.n_pad, ot = L.n_pad + L.m_pad;
+    const double tau = z[ot], kap = z[LP + ot];
+    double q[6] = {0, 0, 0, 0, 0, 0};  // P, D, ctx, bty, U, I
+    for (int64_t e = (int64_t)blockIdx.x * VBLOCK + threadIdx.x; e < ot; e += (int64_t)gridDim.x * VBLOCK) {
+        if (e < oy) {
+            if (e < L.n) {
+                const double aty = mv_atw(V, 0, e);
+                const double x = z[e], r = z[LP + e], cj = c[e];
+                const double dv = sub_(add_(aty / tau, cj), r / tau);  // :35
+                q[1] = fma(dv, dv, q[1]);
+                q[2] = fma(cj, x, q[2]);   // :36
+                q[5] = fma(aty, aty, q[5]);  // :61
+            }
+        } else {
+            const int64_t i = e - oy;
+            if (i < L.m) {
+                const double ax = mv_ax(V, 0, i);
+                const double y = z[e], s = z[LP + e], bi = b[i];
+                const double pv = sub_(add_(ax / tau, s / tau), bi);  // :34
+                q[0] = fma(pv, pv, q[0]);
+                q[3] = fma(bi, y, q[3]);   // :37
+                const double uv = add_(ax, s);  // :59
+                q[4] = fma(uv, uv, q[4]);
+            }
+        }
+    }
+    double tot[6];
+    if (grid_reduce<6, VBLOCK>(q, tot, rb) && threadIdx.x == 0) {
+        const double p = sqrt(tot[0]) / fabs(1.0 + nb);
+        const double d = sqrt(tot[1]) / fabs(1.0 + ncn);
+        const double ctx = tot[2], bty = tot[3];
+        const double g = fabs(ctx / tau + bty / tau) / (1.0 + fabs(ctx / tau) + fabs(bty / tau));  // :38
+        int status = FOS_STATUS_CONTINUE;
+        if (p <= eps * (1.0 + nb) && d <= eps * (1.0 + ncn) &&
+            g <= eps * (1.0 + fabs(ctx / tau) + fabs(bty / tau)))  // :54
+            status = FOS_STATUS_OPTIMAL;
+        else if (sqrt(tot[4]) <= eps * (-ctx / ncn))  // :59
+            status = FOS_STATUS_UNBOUNDED;
+        else if (sqrt(tot[5]) <= eps * (-bty / nb))  // :61
+            status = FOS_STATUS_INFEASIBLE;
+        const int k = ctrl->nrec;
+        if (k < rec_cap) {
+            double *R = recs + (size_t)k * FOS_REC_LEN;
+            R[0] = (double)iter_i; R[1] = p; R[2] = d; R[3] = g; R[4] = ctx; R[5] = bty; R[6] = kap; R[7] = tau;
+            R[8] = cgiter_host >= 0 ? (double)cgiter_host : (double)ctrl->iter;
+            R[9] = (double)status;
+        }
+        ctrl->nrec = k + 1;
+        ctrl->status = status;
+    }
+}
+
+// Feasibility form (FeasibilityStatus.jl:32-72): err = ||prev - z||, prev = z every iteration
+static __global__ void __launch_bounds__(VBLOCK)
+k6_check_feas(int64_t NP, const double *__restrict__ z, double *__restrict__ prev, int do_check, double eps,
+              int64_t iter_i, Ctrl *ctrl, double *__restrict__ recs, int rec_cap, RedBuf rb)
+{
+    double q[1] = {0};
+    for (int64_t e = (int64_t)blockIdx.x * VBLOCK + threadIdx.x; e < NP; e += (int64_t)gridDim.x * VBLOCK) {
+        const double ze = z[e];
+        const double d = sub_(prev[e], ze);
+        q[0] = fma(d, d, q[0]);
+        prev[e] = ze;
+    }
+    if (!do_check) return;
+    double tot[1];
+    if (grid_reduce<1, VBLOCK>(q, tot, rb) && threadIdx.x == 0) {
+        // prev starts as NaN (Feasibility.jl:79, begin_solve): the first error is NaN and never <= eps
+        const double err = sqrt(tot[0]);
+        const int status = (err <= eps) ? FOS_STATUS_OPTIMAL : FOS_STATUS_CONTINUE;
+        const int k = ctrl->nrec;
+        if (k < rec_cap) {
+            double *R = recs + (size_t)k * FOS_REC_LEN;
+            R[0] = (double)iter_i; R[1] = err;
+            for (int t = 2; t < 8; t++) R[t] = 0.0;
+            R[8] = (double)ctrl->iter;
+            R[9] = (double)status;
+        }
+        ctrl->nrec = k + 1;
+        ctrl->status = status;
+    }
+}
+
+// =======================================================================================
+// pack / unpack between the reference's contiguous vector and the padded device layout
+// =======================================================================================
+struct SegMap {
+    int32_t nseg;
+    int64_t len[6], src[6], dst[6];  // logical offset, padded offset
+};
+static __global__ void __launch_bounds__(VBLOCK)
+k_pack(SegMap M, const double *__restrict__ logical, double *__restrict__ padded, int64_t NP)
+{
+    for (int64_t e = (int64_t)blockIdx.x * VBLOCK + threadIdx.x; e < NP; e += (int64_t)gridDim.x * VBLOCK) {
+        double v = 0.0;
+        for (int s = 0; s < M.nseg; s++) {
+            const int64_t k = e - M.dst[s];
+            if (k >= 0 && k < M.len[s]) v = logical[M.src[s] + k];
+        }
+        padded[e] = v;
+    }
+}
+static __global__ void __launch_bounds__(VBLOCK)
+k_unpack(SegMap M, const double *__restrict__ padded, double *__restrict__ logical, int64_t N)
+{
+    for (int64_t e = (int64_t)blockIdx.x * VBLOCK + threadIdx.x; e < N; e += (int64_t)gridDim.x * VBLOCK) {
+        for (int s = 0; s < M.nseg; s++) {
+            const int64_t k = e - M.src[s];
+            if (k >= 0 && k < M.len[s]) logical[e] = padded[M.dst[s] + k];
+        }
+    }
+}
+
+// multi-GPU: fold the local partials into the exchange buffer [NV][n_pad] | [NV][m_pad]
+template <int NV>
+__global__ void __launch_bounds__(VBLOCK)
+k1_finalize_local(MVView V, int64_t n, int64_t n_pad, int64_t m_local, int64_t row_begin, int64_t m_pad,
+                  double *__restrict__ xbuf, const int32_t *skip_flag)
+{
+    if (skip_flag != nullptr && *skip_flag != 0) return;
+    const int64_t total = n + m_local;
+    for (int64_t e = (int64_t)blockIdx.x * VBLOCK + threadIdx.x; e < total; e += (int64_t)gridDim.x * VBLOCK) {
+#pragma unroll
+        for (int v = 0; v < NV; v++) {
+            if (e < n) xbuf[(size_t)v * n_pad + e] = mv_atw(V, v, e);
+            else xbuf[(size_t)NV * n_pad + (size_t)v * m_pad + row_begin + (e - n)] = mv_ax(V, v, e - n);
+        }
+    }
+}
+#endif  // __CUDACC__
+
+}  // namespace fos

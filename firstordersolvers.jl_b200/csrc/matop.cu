@@ -1,0 +1,278 @@
+// matop.cu -- device storage of A and the launch logic of the fused dual mat-vec (K1).
+#include <dlfcn.h>
+
+#include <algorithm>
+
+#include "solver.cuh"
+
+namespace fos {
+
+// ---------------------------------------------------------------------------------------
+// TMA descriptor through the driver entry point (no link-time dependency on libcuda)
+// ---------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn()
+{
+    static PFN_encodeTiled fn = nullptr;
+    if (fn) return fn;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    FOS_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+    if (qres != cudaDriverEntryPointSuccess || !p)
+        throw Error(FOS_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    fn = (PFN_encodeTiled)p;
+    return fn;
+}
+
+static void make_tmap(CUtensorMap *map, const double *A, int64_t rows, int64_t cols, int64_t lda)
+{
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)lda * 8};
+    cuuint32_t box[2] = {(cuuint32_t)K1_BOXC, (cuuint32_t)K1_TR};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = get_encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)A, dims, strides, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        throw Error(FOS_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+}
+
+static size_t k1_smem_bytes(int NV)
+{
+    return (size_t)K1_STAGES * K1_TILE_BYTES + (size_t)K1_STAGES * NV * K1_TR * 8 +
+           (size_t)2 * K1_CONSUMER_WARPS * NV * K1_TR * 8 + 2 * K1_STAGES * 8 + 64;
+}
+
+void MatOp::init_dense(int64_t m_, int64_t n_, const double *Asrc, int64_t lda_src, int location, int64_t row_begin_,
+                       int64_t row_count, int grid_ctas, cudaStream_t st)
+{
+    (void)st;
+    kind = 1;
+    m = m_;
+    n = n_;
+    n_pad = ru(n, PAD);
+    m_pad = ru(m, PAD);
+    row_begin = row_begin_;
+    m_local = row_count;
+    m_pad_local = ru(std::max<int64_t>(m_local, 1), PAD);
+    FOS_REQUIRE(row_begin >= 0 && row_begin + m_local <= m, "row shard out of range");
+    FOS_REQUIRE(row_begin % PAD == 0, "row_begin must be a multiple of 16");
+    FOS_REQUIRE(lda_src >= n, "lda < n");
+    const bool adoptable =
+        location == FOS_MEM_DEVICE && (lda_src % 2 == 0) && ((reinterpret_cast<uintptr_t>(Asrc) & 15) == 0);
+    if (adoptable) {
+        A = Asrc;  // borrowed: the caller keeps the tensor alive for the lifetime of the problem
+        lda = lda_src;
+    } else {
+        lda = ru(n, PAD);
+        A_own.alloc((size_t)std::max<int64_t>(m_local, 1) * lda, false);
+        FOS_CUDA(cudaMemset(A_own.p, 0, (size_t)std::max<int64_t>(m_local, 1) * lda * 8));
+        if (m_local > 0)
+            FOS_CUDA(cudaMemcpy2D(A_own.p, (size_t)lda * 8, Asrc, (size_t)lda_src * 8, (size_t)n * 8, (size_t)m_local,
+                                  location == FOS_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+        A = A_own.p;
+    }
+    make_tmap(&tmap, A, std::max<int64_t>(m_local, 1), n, lda);
+    int G = grid_ctas > 0 ? grid_ctas : num_sms;
+    plan = k1_make_plan(std::max<int64_t>(m_local, 1), n, G);
+    d_unit_begin.upload(plan.cta_unit_begin);
+    d_slot_base.upload(plan.band_slot_base);
+    d_first_cta.upload(plan.band_first_cta);
+    rowpart.alloc((size_t)plan.NB * 2 * m_pad_local);
+    colpart.alloc((size_t)std::max(plan.nslots, 1) * 2 * K1_BW);
+    // plain path / exchange buffers
+    full_ax.alloc((size_t)2 * m_pad);
+    full_atw.alloc((size_t)2 * n_pad);
+    nchunk = (int)((std::max<int64_t>(m_local, 1) + K1S_ROWCHUNK - 1) / K1S_ROWCHUNK);
+    scratch.alloc((size_t)nchunk * 2 * n_pad);
+    d_one_band.upload(std::vector<int32_t>{0, 1});
+    FOS_CUDA(cudaFuncSetAttribute(k1_dual_matvec_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)k1_smem_bytes(1)));
+    FOS_CUDA(cudaFuncSetAttribute(k1_dual_matvec_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)k1_smem_bytes(2)));
+    if (nranks > 1) xbuf.alloc((size_t)2 * (n_pad + m_pad));
+}
+
+void MatOp::init_sparse(int64_t m_, int64_t n_, const int64_t *colptr, const int64_t *rowval, const double *nzval,
+                        int64_t base, cudaStream_t st)
+{
+    (void)st;
+    kind = 2;
+    m = m_;
+    n = n_;
+    n_pad = ru(n, PAD);
+    m_pad = ru(m, PAD);
+    row_begin = 0;
+    m_local = m;
+    m_pad_local = m_pad;
+    FOS_REQUIRE(nranks == 1, "row sharding is implemented for dense storage only");
+    nnz = colptr[n] - base;
+    FOS_REQUIRE(nnz >= 0 && nnz < (int64_t)2147483647, "nnz out of int32 range");
+    std::vector<int32_t> cptr((size_t)n + 1), cidx((size_t)nnz);
+    std::vector<double> cval((size_t)nnz);
+    for (int64_t j = 0; j <= n; j++) cptr[(size_t)j] = (int32_t)(colptr[j] - base);
+    std::vector<int32_t> rcount((size_t)m + 1, 0);
+    for (int64_t k = 0; k < nnz; k++) {
+        int64_t i = rowval[k] - base;
+        FOS_REQUIRE(i >= 0 && i < m, "row index out of range in CSC input");
+        cidx[(size_t)k] = (int32_t)i;
+        cval[(size_t)k] = nzval[k];
+        rcount[(size_t)i + 1]++;
+    }
+    std::vector<int32_t> rptr((size_t)m + 1, 0);
+    for (int64_t i = 0; i < m; i++) rptr[(size_t)i + 1] = rptr[(size_t)i] + rcount[(size_t)i + 1];
+    std::vector<int32_t> fill(rptr.begin(), rptr.end() - 1), ridx((size_t)nnz);
+    std::vector<double> rval((size_t)nnz);
+    for (int64_t j = 0; j < n; j++)
+        for (int32_t k = cptr[(size_t)j]; k < cptr[(size_t)j + 1]; k++) {
+            int32_t i = cidx[(size_t)k];
+            int32_t pos = fill[(size_t)i]++;
+            ridx[(size_t)pos] = (int32_t)j;
+            rval[(size_t)pos] = cval[(size_t)k];
+        }
+    csc_ptr.upload(cptr);
+    csc_idx.upload(cidx);
+    csc_val.upload(cval);
+    csr_ptr.upload(rptr);
+    csr_idx.upload(ridx);
+    csr_val.upload(rval);
+    full_ax.alloc((size_t)2 * m_pad);
+    full_atw.alloc((size_t)2 * n_pad);
+    d_one_band.upload(std::vector<int32_t>{0, 1});
+}
+
+double MatOp::bytes_per_pass() const
+{
+    if (kind == 1) return 8.0 * (double)m_local * (double)n;
+    return 2.0 * 12.0 * (double)nnz;  // CSR pass + CSC pass, 8-byte value + 4-byte index
+}
+
+MVView MatOp::view_full(int NV, const double *ax, const double *atw) const
+{
+    (void)NV;
+    MVView V;
+    V.rowpart = ax;
+    V.nb = 1;
+    V.rp_sb = 0;
+    V.rp_sv = m_pad;
+    V.colpart = atw;
+    V.slot_base = d_one_band.p;
+    V.bw_shift = 62;
+    V.bw_mask = (int64_t)0x3fffffffffffffffLL;
+    V.cp_ss = 0;
+    V.cp_sv = n_pad;
+    return V;
+}
+
+template <int NV>
+MVView MatOp::run_t(const double *const *X, const double *const *W, const int32_t *skip, cudaStream_t st)
+{
+    K1Args<NV> a;
+    for (int v = 0; v < NV; v++) {
+        a.X[v] = X[v];
+        a.W[v] = W[v] + row_begin;
+    }
+    a.skip_flag = skip;
+    a.n_pad = n_pad;
+    a.m_pad_local = m_pad_local;
+    MVView V;
+    if (kind == 1 && impl == 0) {
+        a.rowpart = rowpart.p;
+        a.colpart = colpart.p;
+        a.cta_unit_begin = d_unit_begin.p;
+        a.band_slot_base = d_slot_base.p;
+        a.band_first_cta = d_first_cta.p;
+        a.RT = plan.RT;
+        a.NB = plan.NB;
+        a.kc_last = plan.kc_last;
+        k1_dual_matvec_tma<NV><<<plan.G, K1_THREADS, k1_smem_bytes(NV), st>>>(tmap, a);
+        if (stats) stats->launches++;
+        V.rowpart = rowpart.p;
+        V.nb = plan.NB;
+        V.rp_sb = (int64_t)NV * m_pad_local;
+        V.rp_sv = m_pad_local;
+        V.colpart = colpart.p;
+        V.slot_base = d_slot_base.p;
+        V.bw_shift = K1_BW_SHIFT;
+        V.bw_mask = K1_BW - 1;
+        V.cp_ss = (int64_t)NV * K1_BW;
+        V.cp_sv = K1_BW;
+    } else if (kind == 1) {
+        // plain path: complete results for the local rows
+        a.rowpart = full_ax.p + (nranks > 1 ? 0 : 0);
+        a.colpart = full_atw.p;
+        a.m_pad_local = m_pad_local;
+        const int wpb = 8;
+        k1_simple_rows<NV><<<(unsigned)((m_local + wpb - 1) / wpb), 256, 0, st>>>(A, lda, m_local, n, a);
+        dim3 g((unsigned)((n + 255) / 256), (unsigned)nchunk);
+        k1_simple_cols<NV><<<g, 256, 0, st>>>(A, lda, m_local, n, a, scratch.p);
+        k1_simple_cols_sum<NV><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, scratch.p, nchunk, n, n_pad);
+        if (stats) stats->launches += 3;
+        V = view_full(NV, full_ax.p, full_atw.p);
+        V.rp_sv = m_pad_local;
+    } else {
+        a.rowpart = full_ax.p;
+        a.colpart = full_atw.p;
+        const int wpb = 8;
+        spmv_rows<NV><<<(unsigned)((m + wpb - 1) / wpb), 256, 0, st>>>(csr_ptr.p, csr_idx.p, csr_val.p, m, a, 0, m_pad);
+        spmv_rows<NV><<<(unsigned)((n + wpb - 1) / wpb), 256, 0, st>>>(csc_ptr.p, csc_idx.p, csc_val.p, n, a, 1, n_pad);
+        if (stats) stats->launches += 2;
+        V = view_full(NV, full_ax.p, full_atw.p);
+    }
+    if (stats) stats->total_passes++;
+    if (nranks > 1) {
+        // fold the local partials into the exchange buffer, all-reduce over NVLink, hand out
+        // a complete view.  Rows owned by other ranks are zero in the local contribution.
+        const int64_t total = n + m_local;
+        int grid = (int)std::min<int64_t>((total + VBLOCK - 1) / VBLOCK, 4 * (int64_t)num_sms);
+        k1_finalize_local<NV><<<grid, VBLOCK, 0, st>>>(V, n, n_pad, m_local, row_begin, m_pad, xbuf.p, skip);
+        if (stats) stats->launches++;
+        const size_t count = (size_t)NV * (size_t)(n_pad + m_pad);
+        int rc = nccl_api().AllReduce(xbuf.p, xbuf.p, count, /*ncclFloat64*/ 8, /*ncclSum*/ 0, comm, st);
+        if (rc != 0) throw Error(FOS_ERR_COMM, std::string("ncclAllReduce failed: ") + nccl_api().GetErrorString(rc));
+        V = view_full(NV, xbuf.p + (size_t)NV * n_pad, xbuf.p);
+    }
+    return V;
+}
+
+MVView MatOp::run(int NV, const double *const *X, const double *const *W, const int32_t *skip, cudaStream_t st)
+{
+    FOS_REQUIRE(kind != 0, "matrix not loaded");
+    MVView V = (NV == 1) ? run_t<1>(X, W, skip, st) : run_t<2>(X, W, skip, st);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) throw Error(FOS_ERR_CUDA, std::string("mat-vec launch failed: ") + cudaGetErrorString(e));
+    return V;
+}
+
+// ---------------------------------------------------------------------------------------
+// NCCL via dlopen
+// ---------------------------------------------------------------------------------------
+NcclApi &nccl_api()
+{
+    static NcclApi api;
+    if (api.lib) return api;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    void *lib = nullptr;
+    for (const char *nm : names) {
+        lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (lib) break;
+    }
+    if (!lib) throw Error(FOS_ERR_COMM, std::string("cannot dlopen libnccl.so.2: ") + dlerror());
+    auto sym = [&](const char *s) {
+        void *p = dlsym(lib, s);
+        if (!p) throw Error(FOS_ERR_COMM, std::string("NCCL symbol missing: ") + s);
+        return p;
+    };
+    api.GetUniqueId = (int (*)(NcclId *))sym("ncclGetUniqueId");
+    api.CommInitRank = (int (*)(void **, int, NcclId, int))sym("ncclCommInitRank");
+    api.CommDestroy = (int (*)(void *))sym("ncclCommDestroy");
+    api.AllReduce = (int (*)(const void *, void *, size_t, int, int, void *, cudaStream_t))sym("ncclAllReduce");
+    api.GetErrorString = (const char *(*)(int))sym("ncclGetErrorString");
+    api.lib = lib;
+    return api;
+}
+
+}  // namespace fos

@@ -1,0 +1,191 @@
+// psd.cu -- K5: projection onto the PSD cone, IndPSD(scaling=true) of ProximalOperators.jl as
+// mapped at cones.jl:11 (dual through Moreau, cones.jl:80-85).
+//
+// Input/output: packed lower triangle, column-major, off-diagonals carrying the sqrt(2) svec
+// scaling (MathProgBase).  Algorithm: diag *= sqrt2 -> symmetric eigendecomposition -> clamp
+// the eigenvalues at 0 -> V max(L,0) V' -> repack, diag /= sqrt2.
+//
+// Eigendecomposition = parallel two-sided (symmetric) Jacobi with round-robin pair ordering:
+// each of the D-1 steps of a sweep applies D/2 disjoint plane rotations at once
+// (S <- J' S J, V <- V J).  One CTA per cone; S and V live in shared memory when
+// 2*d*d*8 bytes fit (d <= 112), otherwise in a global workspace (L2 resident).
+#include <algorithm>
+
+#include "solver.cuh"
+
+namespace fos {
+
+constexpr int PSD_THREADS = 512;
+constexpr int PSD_SMEM_MAX_D = 112;
+constexpr int PSD_MAX_SWEEPS = 40;
+
+__device__ __forceinline__ void rr_pair(int s, int k, int D, int &a, int &b)
+{
+    // round-robin tournament: player D-1 is fixed, the others rotate
+    const int M = D - 1;
+    if (k == 0) {
+        a = D - 1;
+        b = s;
+    } else {
+        a = (s + k) % M;
+        b = (s - k + M) % M;
+    }
+    if (a > b) {
+        const int t = a;
+        a = b;
+        b = t;
+    }
+}
+
+__global__ void __launch_bounds__(PSD_THREADS)
+k5_psd_jacobi(const PsdCone *__restrict__ cones, const double *__restrict__ in, double *__restrict__ proj,
+              double *__restrict__ work, int64_t work_stride, int use_smem)
+{
+    extern __shared__ double psd_smem[];
+    __shared__ int s_rot;
+    __shared__ double s_red[PSD_THREADS / 32];
+    __shared__ double s_thr;
+    const PsdCone C = cones[blockIdx.x];
+    const int d = C.d;
+    const int D = (d + 1) & ~1;  // even number of players; index d (if any) is a dummy
+    double *S = use_smem ? psd_smem : work + (size_t)blockIdx.x * work_stride;
+    double *V = S + (size_t)d * d;
+    double *cs = V + (size_t)d * d;  // [D/2][2]
+    const double sq2 = 1.4142135623730951;
+    const double sgn = C.dual ? -1.0 : 1.0;  // dual: project -x, then add x
+
+    // ---- unpack ----
+    for (int64_t idx = threadIdx.x; idx < (int64_t)d * d; idx += PSD_THREADS) {
+        const int i = (int)(idx / d), j = (int)(idx % d);
+        const int lo = i > j ? i : j, hi = i > j ? j : i;  // lower triangle element (lo, hi), column hi
+        const int64_t k = (int64_t)hi * d - (int64_t)hi * (hi - 1) / 2 + (lo - hi);
+        double v = sgn * in[C.off + k];
+        if (i == j) v *= sq2;
+        S[idx] = v;
+        V[idx] = (i == j) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    // rotation threshold: |a_pq| > 1e-17 * ||S||_F (entries below it cannot move an eigenvalue by more
+    // than rounding); annihilated entries are set to exactly 0, so the iteration terminates.
+    {
+        double acc = 0.0;
+        for (int64_t idx = threadIdx.x; idx < (int64_t)d * d; idx += PSD_THREADS) acc = fma(S[idx], S[idx], acc);
+        acc = warp_sum(acc);
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int k = 0; k < PSD_THREADS / 32; k++) t += s_red[k];
+            s_thr = 1e-17 * sqrt(t);
+        }
+        __syncthreads();
+    }
+    const double thr = s_thr;
+
+    // ---- Jacobi sweeps ----
+    const int npairs = D / 2;
+    for (int sweep = 0; sweep < PSD_MAX_SWEEPS; sweep++) {
+        if (threadIdx.x == 0) s_rot = 0;
+        __syncthreads();
+        for (int step = 0; step < D - 1; step++) {
+            // phase 1: rotation parameters from the current S
+            for (int k = threadIdx.x; k < npairs; k += PSD_THREADS) {
+                int p, q;
+                rr_pair(step, k, D, p, q);
+                double c = 1.0, s = 0.0;
+                if (q < d) {
+                    const double apq = S[(size_t)p * d + q];
+                    const double app = S[(size_t)p * d + p], aqq = S[(size_t)q * d + q];
+                    if (fabs(apq) > thr) {
+                        const double theta = (aqq - app) / (2.0 * apq);
+                        const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                        c = 1.0 / sqrt(t * t + 1.0);
+                        s = t * c;
+                        s_rot = 1;
+                    }
+                }
+                cs[2 * k] = c;
+                cs[2 * k + 1] = s;
+            }
+            __syncthreads();
+            // phase 2: columns  S <- S J ,  V <- V J
+            for (int idx = threadIdx.x; idx < npairs * d; idx += PSD_THREADS) {
+                const int k = idx / d, row = idx - k * d;
+                const double c = cs[2 * k], s = cs[2 * k + 1];
+                if (s == 0.0) continue;
+                int p, q;
+                rr_pair(step, k, D, p, q);
+                const size_t ip = (size_t)row * d + p, iq = (size_t)row * d + q;
+                const double sp = S[ip], sq = S[iq];
+                S[ip] = c * sp - s * sq;
+                S[iq] = s * sp + c * sq;
+                const double vp = V[ip], vq = V[iq];
+                V[ip] = c * vp - s * vq;
+                V[iq] = s * vp + c * vq;
+            }
+            __syncthreads();
+            // phase 3: rows  S <- J' S
+            for (int idx = threadIdx.x; idx < npairs * d; idx += PSD_THREADS) {
+                const int k = idx / d, col = idx - k * d;
+                const double c = cs[2 * k], s = cs[2 * k + 1];
+                if (s == 0.0) continue;
+                int p, q;
+                rr_pair(step, k, D, p, q);
+                const size_t ip = (size_t)p * d + col, iq = (size_t)q * d + col;
+                const double sp = S[ip], sq = S[iq];
+                S[ip] = (col == q) ? 0.0 : c * sp - s * sq;  // a_pq := 0 exactly
+                S[iq] = (col == p) ? 0.0 : s * sp + c * sq;  // a_qp := 0 exactly
+            }
+            __syncthreads();
+        }
+        if (s_rot == 0) break;
+        __syncthreads();
+    }
+
+    // ---- eigenvalues -> clamp; scale the columns of V by sqrt(lambda+) so P = W W' ----
+    for (int idx = threadIdx.x; idx < d * d; idx += PSD_THREADS) {
+        const int e = idx % d;
+        const double lam = S[(size_t)e * d + e];
+        // keep lambda on the diagonal until every thread has read it: write scaled V to itself only
+        V[idx] = lam > 0.0 ? V[idx] * sqrt(lam) : 0.0;
+    }
+    __syncthreads();
+    // ---- P = W W' (lower triangle), repack, Moreau for the dual ----
+    const int64_t plen = (int64_t)d * (d + 1) / 2;
+    for (int64_t k = threadIdx.x; k < plen; k += PSD_THREADS) {
+        // invert k -> (col j, row i) of the packed lower triangle
+        int j = (int)floor(((2.0 * d + 1.0) - sqrt((2.0 * d + 1.0) * (2.0 * d + 1.0) - 8.0 * (double)k)) / 2.0);
+        while ((int64_t)j * d - (int64_t)j * (j - 1) / 2 > k) j--;
+        while ((int64_t)(j + 1) * d - (int64_t)(j + 1) * j / 2 <= k) j++;
+        const int i = j + (int)(k - ((int64_t)j * d - (int64_t)j * (j - 1) / 2));
+        double acc = 0.0;
+        const double *wi = V + (size_t)i * d, *wj = V + (size_t)j * d;
+        for (int e = 0; e < d; e++) acc = fma(wi[e], wj[e], acc);
+        if (i == j) acc /= sq2;
+        const double x = in[C.off + k];
+        proj[C.off + k] = C.dual ? __dadd_rn(x, acc) : acc;
+    }
+}
+
+void psd_project(Handle *h, ConeSet &K, const double *in, double *projbuf)
+{
+    const int nc = (int)K.psd.size();
+    if (nc == 0) return;
+    const int d = K.psd_max_d;
+    const int D = (d + 1) & ~1;
+    const size_t need = ((size_t)2 * d * d + (size_t)D) * sizeof(double);
+    const int use_smem = d <= PSD_SMEM_MAX_D ? 1 : 0;
+    int64_t stride = 0;
+    if (!use_smem) {
+        stride = (int64_t)2 * d * d + D;
+        if (K.psd_work.n < (size_t)stride * nc) K.psd_work.alloc((size_t)stride * nc);
+    }
+    if (use_smem)
+        FOS_CUDA(cudaFuncSetAttribute(k5_psd_jacobi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+    FOS_LAUNCH(h, k5_psd_jacobi, nc, PSD_THREADS, use_smem ? need : 0, K.d_psd.p, in, projbuf, K.psd_work.p, stride,
+               use_smem);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) throw Error(FOS_ERR_CUDA, std::string("PSD projection launch failed: ") + cudaGetErrorString(e));
+}
+
+}  // namespace fos

@@ -1,0 +1,671 @@
+// solver.cu -- the hot loop on the device: affine projection by CG on the KKT operator,
+// cone projection, relaxation, residual checks.  See solver.cuh for the object map.
+#include <algorithm>
+
+#include "solver.cuh"
+
+namespace fos {
+
+// =======================================================================================
+// handle lifecycle
+// =======================================================================================
+void Handle::create(int dev)
+{
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        throw Error(FOS_ERR_CUDA, std::string("no CUDA device available (this library has no CPU path): ") +
+                                      (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    FOS_REQUIRE(dev >= 0 && dev < count, "device index out of range");
+    device = dev;
+    FOS_CUDA(cudaSetDevice(dev));
+    cudaDeviceProp prop;
+    FOS_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10)
+        throw Error(FOS_ERR_CUDA, std::string("device ") + prop.name + " is sm_" + std::to_string(prop.major) +
+                                      std::to_string(prop.minor) + "; this library is built for sm_100a only");
+    num_sms = prop.multiProcessorCount;
+    FOS_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    d_ctrl.alloc(1);
+    FOS_CUDA(cudaMallocHost((void **)&h_ctrl, sizeof(Ctrl)));
+    memset(h_ctrl, 0, sizeof(Ctrl));
+    red_partials.alloc((size_t)RED_SLOTS * MAX_PARTIALS);
+    red_counter.alloc(1);
+    rb.partials = red_partials.p;
+    rb.counter = red_counter.p;
+    A.num_sms = num_sms;
+    A.stats = &stats;
+}
+
+Handle::~Handle()
+{
+    cudaSetDevice(device);
+    if (stream) cudaStreamSynchronize(stream);
+    if (comm) {
+        try {
+            nccl_api().CommDestroy(comm);
+        } catch (...) {
+        }
+    }
+    if (h_ctrl) cudaFreeHost(h_ctrl);
+    if (h_stage) cudaFreeHost(h_stage);
+    if (stream) cudaStreamDestroy(stream);
+}
+
+int Handle::vgrid(int64_t len) const
+{
+    int64_t g = (len + VBLOCK - 1) / VBLOCK;
+    int64_t cap = std::min<int64_t>(4 * (int64_t)num_sms, MAX_PARTIALS);
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+void Handle::ensure_stage(size_t n)
+{
+    if (h_stage_n >= n) return;
+    if (h_stage) cudaFreeHost(h_stage);
+    h_stage = nullptr;
+    FOS_CUDA(cudaMallocHost((void **)&h_stage, n * sizeof(double)));
+    h_stage_n = n;
+    d_stage.alloc(n);
+}
+
+void Handle::pack_from_host(const double *z, double *dst)
+{
+    ensure_stage((size_t)N);
+    memcpy(h_stage, z, (size_t)N * sizeof(double));
+    FOS_CUDA(cudaMemcpyAsync(d_stage.p, h_stage, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, stream));
+    FOS_LAUNCH(this, k_pack, vgrid(L.NP), VBLOCK, 0, seg, d_stage.p, dst, L.NP);
+    FOS_CUDA(cudaStreamSynchronize(stream));
+}
+
+void Handle::unpack_to_host(const double *src, double *z)
+{
+    ensure_stage((size_t)N);
+    FOS_LAUNCH(this, k_unpack, vgrid(N), VBLOCK, 0, seg, src, d_stage.p, N);
+    FOS_CUDA(cudaMemcpyAsync(h_stage, d_stage.p, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    FOS_CUDA(cudaStreamSynchronize(stream));
+    memcpy(z, h_stage, (size_t)N * sizeof(double));
+}
+
+void Handle::sync_ctrl()
+{
+    FOS_CUDA(cudaMemcpyAsync(h_ctrl, d_ctrl.p, sizeof(Ctrl), cudaMemcpyDeviceToHost, stream));
+    FOS_CUDA(cudaStreamSynchronize(stream));
+}
+
+void Handle::ensure_recs(int cap)
+{
+    if (cap <= rec_cap) return;
+    d_recs.alloc((size_t)cap * FOS_REC_LEN);
+    rec_cap = cap;
+}
+
+// =======================================================================================
+// cone set
+// =======================================================================================
+void ConeSet::build(int64_t NP_, const std::vector<ConeSeg> &segs)
+{
+    NP = NP_;
+    std::vector<uint8_t> h_ops((size_t)NP, OP_ZERO);
+    std::vector<int32_t> h_cone_of((size_t)NP, 0);
+    std::vector<SocCone> h_soc;
+    std::vector<int32_t> h_chunk_cone;
+    psd.clear();
+    psd_max_d = 0;
+    for (const ConeSeg &s : segs) {
+        FOS_REQUIRE(s.off >= 0 && s.off + s.len <= NP && s.len >= 0, "cone segment out of range");
+        uint8_t op = OP_ZERO;
+        switch (s.type) {
+        case FOS_CONE_FREE: op = s.dual ? OP_ZERO : OP_COPY; break;  // cones.jl:100
+        case FOS_CONE_ZERO: op = s.dual ? OP_COPY : OP_ZERO; break;  // cones.jl:98
+        case FOS_CONE_NONNEG: op = OP_MAX0; break;                   // cones.jl:101
+        case FOS_CONE_NONPOS: op = OP_MIN0; break;                   // cones.jl:102
+        case FOS_CONE_SOC: {
+            if (s.len == 0) continue;
+            SocCone c;
+            c.head = s.off;
+            c.len = s.len;
+            c.dual = s.dual;
+            c.pad_ = 0;
+            c.chunk0 = (int32_t)h_chunk_cone.size();
+            int64_t tail = s.len - 1;
+            c.nchunk = (int32_t)std::max<int64_t>(1, (tail + SOC_CHUNK - 1) / SOC_CHUNK);
+            for (int k = 0; k < c.nchunk; k++) h_chunk_cone.push_back((int32_t)h_soc.size());
+            h_ops[(size_t)s.off] = s.dual ? OP_SOCD_HEAD : OP_SOC_HEAD;
+            h_cone_of[(size_t)s.off] = (int32_t)h_soc.size();
+            for (int64_t k = 1; k < s.len; k++) {
+                h_ops[(size_t)(s.off + k)] = s.dual ? OP_SOCD_TAIL : OP_SOC_TAIL;
+                h_cone_of[(size_t)(s.off + k)] = (int32_t)h_soc.size();
+            }
+            h_soc.push_back(c);
+            continue;
+        }
+        case FOS_CONE_SDP: {
+            if (s.len == 0) continue;
+            int64_t d = (int64_t)std::llround(std::sqrt(0.25 + 2.0 * (double)s.len) - 0.5);
+            FOS_REQUIRE(d * (d + 1) / 2 == s.len, "SDP cone length is not d(d+1)/2");
+            PsdCone pc;
+            pc.off = s.off;
+            pc.d = (int32_t)d;
+            pc.dual = s.dual;
+            psd.push_back(pc);
+            psd_max_d = std::max<int>(psd_max_d, (int)d);
+            for (int64_t k = 0; k < s.len; k++) h_ops[(size_t)(s.off + k)] = OP_PRE;
+            continue;
+        }
+        default:
+            throw Error(FOS_ERR_UNSUPPORTED, "cone type " + std::to_string(s.type) +
+                                                 " is outside the hot-path scope (SOCRotated/Exp cones: SURVEY 8f)");
+        }
+        for (int64_t k = 0; k < s.len; k++) h_ops[(size_t)(s.off + k)] = op;
+    }
+    ops.upload(h_ops);
+    cone_of.upload(h_cone_of);
+    nsoc = (int)h_soc.size();
+    nchunks = (int)h_chunk_cone.size();
+    if (nsoc > 0) {
+        soc.upload(h_soc);
+        chunk_cone.upload(h_chunk_cone);
+        soc_scale.alloc((size_t)nsoc);
+        chunk_sum.alloc((size_t)nchunks);
+    }
+    counter.alloc(1);
+    if (!psd.empty()) d_psd.upload(psd);
+}
+
+void Handle::cone_project(ConeSet &K, const double *in, double *projbuf, int epi, const EpiArgs &E)
+{
+    if (K.nsoc > 0)
+        FOS_LAUNCH(this, k4_soc_norms, K.nchunks, VBLOCK, 0, in, K.soc.p, K.nsoc, K.chunk_cone.p, K.chunk_sum.p,
+                   K.soc_scale.p, K.counter.p);
+    if (!K.psd.empty()) psd_project(this, K, in, projbuf);
+    const int g = vgrid(K.NP);
+#define CONE_CASE(EPI)                                                                                            \
+    case EPI:                                                                                                     \
+        FOS_LAUNCH(this, k4_cone_apply<EPI>, g, VBLOCK, 0, K.NP, in, projbuf, K.ops.p, K.cone_of.p, K.soc_scale.p, \
+                   E, d_ctrl.p, rb);                                                                              \
+        break;
+    switch (epi) {
+        CONE_CASE(EPI_NONE)
+        CONE_CASE(EPI_GAP)
+        CONE_CASE(EPI_GAPA)
+        CONE_CASE(EPI_FISTA)
+        CONE_CASE(EPI_DYKSTRA)
+        CONE_CASE(EPI_GAPP_PROJ)
+        CONE_CASE(EPI_LS)
+    default: throw Error(FOS_ERR_INVALID, "bad epilogue");
+    }
+#undef CONE_CASE
+}
+
+// =======================================================================================
+// loading
+// =======================================================================================
+static void add_cones(std::vector<ConeSeg> &segs, int64_t base, int64_t nc, const int32_t *t, const int64_t *l,
+                      int dual)
+{
+    int64_t off = base;
+    for (int64_t k = 0; k < nc; k++) {
+        ConeSeg s;
+        s.type = t[k];
+        s.dual = dual;
+        s.off = off;
+        s.len = l[k];
+        FOS_REQUIRE(l[k] >= 0, "negative cone length");
+        segs.push_back(s);
+        off += l[k];
+    }
+}
+
+void Handle::finish_load_common(const std::vector<ConeSeg> &segs)
+{
+    const size_t NP = (size_t)L.NP;
+    for (DevBuf<double> *b : {&rhs, &sol, &r, &p, &Ap, &x, &tmp1, &tmp2, &proj, &fy, &fxold, &dp, &dq, &dy, &w1, &w2,
+                              &w3, &prev})
+        b->alloc(NP);
+    cones.build(L.NP, segs);
+    s1_calls = 1;
+    cgiter = 0;
+    firstrun = true;
+    warn_maxit = false;
+    status = FOS_STATUS_CONTINUE;
+    checked = false;
+    stats = Stats();
+    FOS_CUDA(cudaMemset(d_ctrl.p, 0, sizeof(Ctrl)));
+    ensure_recs(256);
+    ensure_stage((size_t)N);
+    loaded = true;
+    set_algorithm(FOS_ALG_GAP, 0.8, 1.8, 1.8, 0.0, 100);
+}
+
+// HSDE(model) (problemforms/HSDE/HSDE.jl:7-29, indirect branch) on a matrix already in `A`
+void Handle::load_conic(int64_t m, int64_t n, const double *b, const double *c, int64_t nc1, const int32_t *t1,
+                        const int64_t *l1, int64_t nc2, const int32_t *t2, const int64_t *l2)
+{
+    int64_t s1 = 0, s2 = 0;
+    for (int64_t k = 0; k < nc1; k++) s1 += l1[k];
+    for (int64_t k = 0; k < nc2; k++) s2 += l2[k];
+    FOS_REQUIRE(s1 == m, "constraint cones do not cover 1:m (cones.jl:66-72)");
+    FOS_REQUIRE(s2 == n, "variable cones do not cover 1:n (cones.jl:66-72)");
+    L.form = 0;
+    L.n = n;
+    L.m = m;
+    L.n_pad = ru(n, PAD);
+    L.m_pad = ru(m, PAD);
+    L.LP = L.n_pad + L.m_pad + PAD;
+    L.NP = 2 * L.LP;
+    const int64_t l = m + n + 1;
+    N = 2 * l;
+    seg.nseg = 6;
+    const int64_t lens[6] = {n, m, 1, n, m, 1};
+    const int64_t srcs[6] = {0, n, n + m, l, l + n, l + n + m};
+    const int64_t dsts[6] = {0, L.n_pad, L.n_pad + L.m_pad, L.LP, L.LP + L.n_pad, L.LP + L.n_pad + L.m_pad};
+    for (int k = 0; k < 6; k++) {
+        seg.len[k] = lens[k];
+        seg.src[k] = srcs[k];
+        seg.dst[k] = dsts[k];
+    }
+    std::vector<double> hb((size_t)L.m_pad, 0.0), hc((size_t)L.n_pad, 0.0);
+    double sb = 0, sc = 0;
+    for (int64_t i = 0; i < m; i++) {
+        hb[(size_t)i] = b[i];
+        sb += b[i] * b[i];
+    }
+    for (int64_t j = 0; j < n; j++) {
+        hc[(size_t)j] = c[j];
+        sc += c[j] * c[j];
+    }
+    nb = std::sqrt(sb);
+    ncn = std::sqrt(sc);
+    d_b.upload(hb);
+    d_c.upload(hc);
+    beta = 1.0;
+    decreasing = true;  // HSDE.jl:22
+    // DualConeProduct (cones.jl:114-142): K2 x K1* x R+ x K2* x K1 x R+
+    std::vector<ConeSeg> segs;
+    add_cones(segs, 0, nc2, t2, l2, 0);
+    add_cones(segs, L.n_pad, nc1, t1, l1, 1);
+    segs.push_back(ConeSeg{FOS_CONE_NONNEG, 0, L.n_pad + L.m_pad, 1});
+    add_cones(segs, L.LP, nc2, t2, l2, 1);
+    add_cones(segs, L.LP + L.n_pad, nc1, t1, l1, 0);
+    segs.push_back(ConeSeg{FOS_CONE_NONNEG, 0, L.LP + L.n_pad + L.m_pad, 1});
+    finish_load_common(segs);
+}
+
+// Feasibility(AffinePlusLinear(A,b,q,beta), ConeProduct, an+am)
+void Handle::load_affine(int64_t am, int64_t an, const double *b, const double *q, int32_t beta_, int32_t decr,
+                         int64_t nc, const int32_t *t, const int64_t *l)
+{
+    FOS_REQUIRE(beta_ == 1 || beta_ == -1, "beta must be 1 or -1 (affinepluslinear.jl:73)");
+    int64_t s1 = 0;
+    for (int64_t k = 0; k < nc; k++) s1 += l[k];
+    FOS_REQUIRE(s1 == am + an, "cones do not cover 1:(an+am)");
+    L.form = 1;
+    L.n = an;
+    L.m = am;
+    L.n_pad = ru(an, PAD);
+    L.m_pad = ru(am, PAD);
+    L.LP = 0;
+    L.NP = L.n_pad + L.m_pad;
+    N = an + am;
+    seg.nseg = 2;
+    seg.len[0] = an; seg.src[0] = 0;  seg.dst[0] = 0;
+    seg.len[1] = am; seg.src[1] = an; seg.dst[1] = L.n_pad;
+    std::vector<double> hq((size_t)L.n_pad, 0.0);
+    for (int64_t j = 0; j < an; j++) hq[(size_t)j] = q ? q[j] : 0.0;
+    d_q.upload(hq);
+    beta = (double)beta_;
+    decreasing = decr != 0;
+    // cones over [x; z]: split the contiguous cone list at the x/z boundary of the padded layout.
+    std::vector<ConeSeg> segs;
+    int64_t off = 0;
+    for (int64_t k = 0; k < nc; k++) {
+        FOS_REQUIRE(l[k] >= 0, "negative cone length");
+        const int64_t a0 = off, a1 = off + l[k];
+        if (a1 <= an) segs.push_back(ConeSeg{t[k], 0, a0, l[k]});
+        else if (a0 >= an) segs.push_back(ConeSeg{t[k], 0, L.n_pad + (a0 - an), l[k]});
+        else {
+            FOS_REQUIRE(t[k] != FOS_CONE_SOC && t[k] != FOS_CONE_SDP,
+                        "a SOC/SDP cone may not straddle the x/z boundary of the affine form");
+            segs.push_back(ConeSeg{t[k], 0, a0, an - a0});
+            segs.push_back(ConeSeg{t[k], 0, L.n_pad, a1 - an});
+        }
+        off = a1;
+    }
+    finish_load_common(segs);
+    // rhs2 = b (affinepluslinear.jl:76-77)
+    std::vector<double> hb((size_t)L.m_pad, 0.0);
+    for (int64_t i = 0; i < am; i++) hb[(size_t)i] = b ? b[i] : 0.0;
+    FOS_CUDA(cudaMemcpy(rhs.p + L.n_pad, hb.data(), (size_t)L.m_pad * 8, cudaMemcpyHostToDevice));
+}
+
+// =======================================================================================
+// operators
+// =======================================================================================
+// one pass over A feeding the KKT product of v
+MVView Handle::kkt_pass(const double *v, const int32_t *skip)
+{
+    if (L.form == 0) {
+        const double *X[2] = {v, v + L.LP};
+        const double *W[2] = {v + L.n_pad, v + L.LP + L.n_pad};
+        return A.run(2, X, W, skip, stream);
+    }
+    const double *X[1] = {v};
+    const double *W[1] = {L.form == 2 ? v : v + L.n_pad};
+    return A.run(1, X, W, skip, stream);
+}
+
+void Handle::kkt_mul(const double *in, double *out)
+{
+    MVView V = kkt_pass(in, nullptr);
+    if (L.form == 0)
+        FOS_LAUNCH(this, k2_kkt_hsde<K2_OUT>, vgrid(L.LP), VBLOCK, 0, L, V, in, d_c.p, d_b.p, out, nullptr, nullptr,
+                   nullptr, d_ctrl.p, rb, 0);
+    else
+        FOS_LAUNCH(this, k2_kkt_plain<K2_OUT>, vgrid(L.NP), VBLOCK, 0, L, V, in, out, nullptr, nullptr, nullptr,
+                   d_ctrl.p, rb, 0);
+}
+
+void Handle::q_mul(const double *Bp, double *Yp, bool transpose)
+{
+    FOS_REQUIRE(L.form == 0, "q_mul needs the HSDE conic form");
+    const double *X[1] = {Bp};
+    const double *W[1] = {Bp + L.n_pad};
+    MVView V = A.run(1, X, W, nullptr, stream);
+    FOS_LAUNCH(this, k2_q_hsde, vgrid(L.LP), VBLOCK, 0, L, V, Bp, d_c.p, d_b.p, Yp, transpose ? 1 : 0, rb);
+}
+
+void Handle::cg_enqueue_iteration()
+{
+    const int32_t *skip = &d_ctrl.p->done;
+    MVView V = kkt_pass(p.p, skip);
+    if (L.form == 0)
+        FOS_LAUNCH(this, k2_kkt_hsde<K2_AP>, vgrid(L.LP), VBLOCK, 0, L, V, p.p, d_c.p, d_b.p, Ap.p, nullptr, nullptr,
+                   nullptr, d_ctrl.p, rb, 1);
+    else if (L.form == 1)
+        FOS_LAUNCH(this, k2_kkt_plain<K2_AP>, vgrid(L.NP), VBLOCK, 0, L, V, p.p, Ap.p, nullptr, nullptr, nullptr,
+                   d_ctrl.p, rb, 1);
+    else
+        FOS_LAUNCH(this, k2_spd<K2_AP>, vgrid(L.NP), VBLOCK, 0, L, V, p.p, Ap.p, nullptr, nullptr, nullptr, d_ctrl.p,
+                   rb, 1);
+    FOS_LAUNCH(this, k3_cg_update, vgrid(L.NP), VBLOCK, 0, L.NP, sol.p, r.p, p.p, Ap.p, d_ctrl.p, rb);
+    FOS_LAUNCH(this, k3_cg_dir, vgrid(L.NP), VBLOCK, 0, L.NP, p.p, r.p, d_ctrl.p);
+}
+
+// conjugategradient!(sol, KKT, rhs, r, p, Ap; tol, max_iters) (conjugategradients.jl:31-55).
+// Iterations are enqueued in batches; every kernel of a batch returns at once when the
+// device-side stop test has fired, so the host synchronises once per batch, not per iteration.
+void Handle::cg_solve(double tol, int max_iters)
+{
+    FOS_LAUNCH(this, k_cg_begin, 1, 1, 0, d_ctrl.p, tol, max_iters);
+    MVView V = kkt_pass(sol.p, nullptr);
+    if (L.form == 0)
+        FOS_LAUNCH(this, k2_kkt_hsde<K2_RESID>, vgrid(L.LP), VBLOCK, 0, L, V, sol.p, d_c.p, d_b.p, nullptr, rhs.p,
+                   r.p, p.p, d_ctrl.p, rb, 0);
+    else if (L.form == 1)
+        FOS_LAUNCH(this, k2_kkt_plain<K2_RESID>, vgrid(L.NP), VBLOCK, 0, L, V, sol.p, nullptr, rhs.p, r.p, p.p,
+                   d_ctrl.p, rb, 0);
+    else
+        FOS_LAUNCH(this, k2_spd<K2_RESID>, vgrid(L.NP), VBLOCK, 0, L, V, sol.p, nullptr, rhs.p, r.p, p.p, d_ctrl.p, rb,
+                   0);
+    int64_t enq = 0;
+    int batch = cg_batch > 0 ? cg_batch : (int)std::max<int64_t>(1, cgiter);  // adaptive: last solve's count
+    for (;;) {
+        batch = (int)std::min<int64_t>(batch, (int64_t)max_iters - enq);
+        if (batch < 1) batch = 1;
+        for (int k = 0; k < batch; k++) cg_enqueue_iteration();
+        enq += batch;
+        sync_ctrl();
+        if (h_ctrl->done) break;
+        FOS_REQUIRE(enq < (int64_t)max_iters + 4, "CG did not terminate (internal error)");
+        batch = cg_batch > 0 ? cg_batch : std::max(1, batch / 2);
+    }
+    cgiter = h_ctrl->iter;
+    stats.total_cg += cgiter;
+    if (h_ctrl->warn_maxit) warn_maxit = true;
+}
+
+// prox!(y, S::AffinePlusLinear, x) (affinepluslinear.jl:83-126).  Result: sol (= xinit).
+void Handle::s1_prox(const double *xin)
+{
+    if (L.form == 0) {
+        const double *X[1] = {xin + L.LP};
+        const double *W[1] = {xin + L.LP + L.n_pad};
+        MVView V = A.run(1, X, W, nullptr, stream);  // :94  (Q'x2 = -(Q x2))
+        FOS_LAUNCH(this, k2_rhs_hsde, vgrid(L.LP), VBLOCK, 0, L, V, xin, d_c.p, d_b.p, rhs.p, rb);  // :95
+    } else {
+        const double *X[1] = {xin};
+        const double *W[1] = {xin + L.n_pad};
+        MVView V = A.run(1, X, W, nullptr, stream);
+        FOS_LAUNCH(this, k2_rhs_plain, vgrid(L.n), VBLOCK, 0, L, V, xin, d_q.p, beta, rhs.p);
+    }
+    if (firstrun) {  // :101-104
+        FOS_CUDA(cudaMemcpyAsync(sol.p, xin, (size_t)L.NP * 8, cudaMemcpyDeviceToDevice, stream));
+        firstrun = false;
+    }
+    const double an = (double)(L.form == 0 ? (L.n + L.m + 1) : L.n);
+    const double floor_ = an * 2.220446049250313e-16;
+    double tol = floor_;
+    if (decreasing) tol = std::max(std::pow(0.2, std::sqrt((double)s1_calls)), floor_);  // :108-112
+    s1_calls += 1;                                                                       // :114
+    cg_solve(tol, 1000);                                                                 // :115-118
+}
+
+// y = sol with y2 .*= beta (affinepluslinear.jl:124)
+void Handle::sol_scaled_to(double *dst)
+{
+    FOS_LAUNCH(this, k_copy_scaled, vgrid(L.NP), VBLOCK, 0, L.NP, dst, sol.p, L.n_pad, L.form == 1 ? beta : 1.0);
+}
+
+void Handle::check(const double *z, int64_t i, bool override_)
+{
+    const bool due = (i % cur_checki == 0) || override_;
+    if (L.form == 0) {
+        if (!due) {  // HSDEStatus.jl:66-69
+            checked = false;
+            return;
+        }
+        const double *X[1] = {z};
+        const double *W[1] = {z + L.n_pad};
+        MVView V = A.run(1, X, W, nullptr, stream);
+        FOS_LAUNCH(this, k6_check_hsde, vgrid(L.LP), VBLOCK, 0, L, V, z, d_c.p, d_b.p, nb, ncn, cur_eps, i,
+                   (int)cgiter, d_ctrl.p, d_recs.p, rec_cap, rb);
+    } else {
+        FOS_LAUNCH(this, k6_check_feas, vgrid(L.NP), VBLOCK, 0, L.NP, z, prev.p, due ? 1 : 0, cur_eps, i, d_ctrl.p,
+                   d_recs.p, rec_cap, rb);
+        if (!due) {
+            checked = false;
+            return;
+        }
+    }
+    sync_ctrl();
+    status = h_ctrl->status;
+    checked = true;
+}
+
+// =======================================================================================
+// algorithms
+// =======================================================================================
+void Handle::set_algorithm(int alg_, double a, double a1, double a2, double bA, int64_t ip)
+{
+    FOS_REQUIRE(alg_ >= FOS_ALG_GAP && alg_ <= FOS_ALG_GAPP, "unknown algorithm code");
+    FOS_REQUIRE(ip >= 1, "iproj must be >= 1");
+    alg = alg_;
+    alpha = a;
+    alpha1 = a1;
+    alpha2 = a2;
+    betaA = bA;
+    iproj = ip;
+    fista_t = 1.0;  // fista.jl:24
+    if (loaded) {
+        const size_t bytes = (size_t)L.NP * 8;
+        FOS_CUDA(cudaMemsetAsync(fy.p, 0, bytes, stream));
+        FOS_CUDA(cudaMemsetAsync(fxold.p, 0, bytes, stream));
+        FOS_CUDA(cudaMemsetAsync(dp.p, 0, bytes, stream));  // dykstra.jl:22
+        FOS_CUDA(cudaMemsetAsync(dq.p, 0, bytes, stream));
+        sync_ctrl();
+        h_ctrl->alpha12 = 2.0;  // gapa.jl:29
+        FOS_CUDA(cudaMemcpyAsync(d_ctrl.p, h_ctrl, sizeof(Ctrl), cudaMemcpyHostToDevice, stream));
+        FOS_CUDA(cudaStreamSynchronize(stream));
+    }
+}
+
+void Handle::step(int64_t i)
+{
+    const int g = vgrid(L.NP);
+    const int64_t p2off = L.n_pad;
+    const double p2scale = L.form == 1 ? beta : 1.0;
+    EpiArgs E{};
+    E.tmp2 = tmp2.p;
+    E.x = x.p;
+    E.betaA = betaA;
+    switch (alg) {
+    case FOS_ALG_GAP:
+    case FOS_ALG_GAPA: {
+        const bool ada = alg == FOS_ALG_GAPA;
+        s1_prox(x.p);  // gap.jl:45
+        FOS_LAUNCH(this, k_relax, g, VBLOCK, 0, L.NP, tmp1.p, alpha1, sol.p, 1.0 - alpha1, x.p, p2off, p2scale,
+                   d_ctrl.p, ada ? 1 : 0);  // :48
+        E.a2 = alpha2;
+        E.om_a2 = 1.0 - alpha2;
+        E.a = alpha;
+        E.om_a = 1.0 - alpha;
+        cone_project(cones, tmp1.p, proj.p, ada ? EPI_GAPA : EPI_GAP, E);  // :55,58,78
+        check(proj.p, i, false);                                           // :56
+        break;
+    }
+    case FOS_ALG_FISTA: {
+        if (i == 1) FOS_CUDA(cudaMemcpyAsync(fy.p, x.p, (size_t)L.NP * 8, cudaMemcpyDeviceToDevice, stream));  // :31-33
+        s1_prox(fy.p);  // :35
+        FOS_LAUNCH(this, k_relax, g, VBLOCK, 0, L.NP, tmp1.p, alpha, sol.p, 1.0 - alpha, fy.p, p2off, p2scale,
+                   d_ctrl.p, 0);  // :37
+        const double told = fista_t;
+        fista_t = (1.0 + std::sqrt(1.0 + 4.0 * told * told)) / 2.0;  // :45
+        E.coef = (told - 1.0) / fista_t;                             // :46
+        E.aux1 = fxold.p;
+        E.aux2 = fy.p;
+        cone_project(cones, tmp1.p, proj.p, EPI_FISTA, E);  // :39-41,46
+        check(proj.p, i, false);
+        break;
+    }
+    case FOS_ALG_DYKSTRA: {
+        FOS_LAUNCH(this, k_add_scaled, g, VBLOCK, 0, L.NP, w1.p, x.p, 1.0, dp.p, d_ctrl.p, 0);  // x + p
+        s1_prox(w1.p);                                                                          // :29
+        sol_scaled_to(dy.p);
+        FOS_LAUNCH(this, k_dykstra_mid, g, VBLOCK, 0, L.NP, w1.p, dy.p, dp.p, dq.p, w2.p);  // :31, y + q
+        E.aux1 = dq.p;
+        cone_project(cones, w2.p, proj.p, EPI_DYKSTRA, E);  // :32,35
+        check(proj.p, i, false);                            // :33
+        break;
+    }
+    case FOS_ALG_GAPP: {
+        s1_prox(x.p);  // gapproj.jl:33
+        E.a2 = alpha2;
+        E.om_a2 = 1.0 - alpha2;
+        E.a = alpha;
+        E.om_a = 1.0 - alpha;
+        if (i % iproj == 0) {  // :34
+            sol_scaled_to(tmp1.p);
+            cone_project(cones, tmp1.p, proj.p, EPI_NONE, E);  // :39
+            s1_prox(proj.p);                                   // :40
+            sol_scaled_to(w3.p);
+            FOS_LAUNCH(this, k_sub, g, VBLOCK, 0, L.NP, w3.p, w3.p, tmp1.p);  // :41 res
+            FOS_LAUNCH(this, k_ls_begin, 1, 1, 0, d_ctrl.p);
+            for (int k = 0; k <= 20; k++) {  // :46-56
+                const double at = std::ldexp(1.0, k);
+                FOS_LAUNCH(this, k_add_scaled, g, VBLOCK, 0, L.NP, w1.p, tmp1.p, at, w3.p, d_ctrl.p, 0);
+                E.ls_alpha = at;
+                cone_project(cones, w1.p, w2.p, EPI_LS, E);
+            }
+            FOS_LAUNCH(this, k_add_scaled, g, VBLOCK, 0, L.NP, tmp1.p, tmp1.p, 0.0, w3.p, d_ctrl.p, 1);  // :58
+            cone_project(cones, tmp1.p, proj.p, EPI_GAPP_PROJ, E);                                      // :59,61,62
+            check(proj.p, i, false);                                                                    // :60
+        } else {
+            FOS_LAUNCH(this, k_relax, g, VBLOCK, 0, L.NP, tmp1.p, alpha1, sol.p, 1.0 - alpha1, x.p, p2off, p2scale,
+                       d_ctrl.p, 0);                          // :64
+            cone_project(cones, tmp1.p, proj.p, EPI_GAP, E);  // :66,68,70
+            check(proj.p, i, false);                          // :67
+        }
+        break;
+    }
+    default: throw Error(FOS_ERR_INVALID, "unknown algorithm");
+    }
+}
+
+// getsol (gap.jl:82-87 and the identical methods of the other algorithms): P2(P1(x)).
+// Result in proj (and tmp1/tmp2 hold what the reference leaves there).
+void Handle::getsol()
+{
+    s1_prox(x.p);
+    sol_scaled_to(tmp1.p);
+    EpiArgs E{};
+    cone_project(cones, tmp1.p, proj.p, EPI_NONE, E);
+    if (alg == FOS_ALG_DYKSTRA)
+        FOS_CUDA(cudaMemcpyAsync(dy.p, proj.p, (size_t)L.NP * 8, cudaMemcpyDeviceToDevice, stream));
+    else
+        FOS_CUDA(cudaMemcpyAsync(tmp2.p, proj.p, (size_t)L.NP * 8, cudaMemcpyDeviceToDevice, stream));
+}
+
+// fresh status object, as status_generator builds one per solve! (HSDE.jl:26-27, Feasibility.jl:78-79)
+void Handle::begin_solve()
+{
+    status = FOS_STATUS_CONTINUE;
+    checked = false;
+    if (L.form == 1) {
+        std::vector<double> nanv((size_t)L.NP, std::nan(""));
+        FOS_CUDA(cudaMemcpy(prev.p, nanv.data(), (size_t)L.NP * 8, cudaMemcpyHostToDevice));
+    }
+}
+
+int64_t Handle::run(int64_t i_start, int64_t n_iters, int64_t checki, double eps, double *records,
+                    int64_t rec_cap_host, int64_t *n_rec, double *trace)
+{
+    require_loaded();
+    FOS_REQUIRE(checki >= 1, "checki must be >= 1");
+    FOS_REQUIRE(n_iters >= 0, "n_iters must be >= 0");
+    cur_checki = checki;
+    cur_eps = eps;
+    ensure_recs((int)std::min<int64_t>(n_iters / checki + 2, 1 << 20));
+    sync_ctrl();
+    h_ctrl->nrec = 0;
+    h_ctrl->status = status;
+    FOS_CUDA(cudaMemcpyAsync(d_ctrl.p, h_ctrl, sizeof(Ctrl), cudaMemcpyHostToDevice, stream));
+    int64_t done = 0;
+    for (int64_t i = i_start; i < i_start + n_iters; i++) {
+        cur_i = i;  // solverwrapper.jl:24
+        step(i);    // :25
+        if (trace) unpack_to_host(x.p, trace + done * N);
+        done++;
+        if (status != FOS_STATUS_CONTINUE) break;  // :26-28
+    }
+    sync_ctrl();
+    const int64_t nrec = h_ctrl->nrec;
+    if (n_rec) *n_rec = nrec;
+    const int64_t ncopy = std::min<int64_t>(std::min<int64_t>(nrec, rec_cap_host), rec_cap);
+    if (records && ncopy > 0)
+        FOS_CUDA(cudaMemcpy(records, d_recs.p, (size_t)ncopy * FOS_REC_LEN * 8, cudaMemcpyDeviceToHost));
+    return done;
+}
+
+// tail of iterate() (solverwrapper.jl:31-34)
+void Handle::finish(double *guess, double *record, int64_t *n_rec)
+{
+    require_loaded();
+    sync_ctrl();
+    h_ctrl->nrec = 0;
+    FOS_CUDA(cudaMemcpyAsync(d_ctrl.p, h_ctrl, sizeof(Ctrl), cudaMemcpyHostToDevice, stream));
+    getsol();
+    int64_t nrec = 0;
+    if (!checked) {
+        check(proj.p, cur_i, true);
+        nrec = 1;
+        if (record) FOS_CUDA(cudaMemcpy(record, d_recs.p, FOS_REC_LEN * 8, cudaMemcpyDeviceToHost));
+    }
+    if (n_rec) *n_rec = nrec;
+    if (guess) unpack_to_host(proj.p, guess);
+    else FOS_CUDA(cudaStreamSynchronize(stream));
+}
+
+}  // namespace fos

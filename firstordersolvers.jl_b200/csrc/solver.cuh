@@ -1,0 +1,243 @@
+// solver.cuh -- host-side state of one solver handle: device buffers, the matrix operator
+// (dense TMA / plain / sparse), the affine projection S1 (CG on the KKT operator), the cone
+// set S2 and the algorithm steps.  Mirrors, on the device, the objects of the reference:
+//   AffinePlusLinear  utilities/affinepluslinear.jl:58-126
+//   DualConeProduct   cones.jl:114-142
+//   GAPData/...       solvers/*.jl
+//   HSDEStatus        problemforms/HSDE/HSDEStatus.jl
+#pragma once
+#include <cmath>
+#include <memory>
+
+#include "common.cuh"
+#include "kernels.cuh"
+#include "matvec.cuh"
+
+namespace fos {
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    void alloc(size_t count, bool zero = true)
+    {
+        release();
+        n = count;
+        if (count == 0) count = 1;
+        cudaError_t e = cudaMalloc((void **)&p, count * sizeof(T));
+        if (e != cudaSuccess) {
+            p = nullptr;
+            throw Error(FOS_ERR_NOMEM, std::string("cudaMalloc of ") + std::to_string(count * sizeof(T)) +
+                                           " bytes failed: " + cudaGetErrorString(e));
+        }
+        if (zero) FOS_CUDA(cudaMemset(p, 0, count * sizeof(T)));
+    }
+    void upload(const std::vector<T> &h)
+    {
+        alloc(h.size(), false);
+        if (!h.empty()) FOS_CUDA(cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    }
+};
+
+struct Stats {
+    int64_t total_cg = 0;
+    int64_t total_passes = 0;
+    int64_t launches = 0;
+};
+
+// ---- NCCL through dlopen: no link-time dependency; binds to whichever libnccl.so.2 the
+// process already has loaded (torch's bundled one when driven from Python). ---------------
+struct NcclId {
+    char bytes[FOS_COMM_ID_BYTES];
+};
+struct NcclApi {
+    void *lib = nullptr;
+    int (*GetUniqueId)(NcclId *) = nullptr;
+    int (*CommInitRank)(void **, int, NcclId, int) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+NcclApi &nccl_api();  // loads on first use, throws FOS_ERR_COMM if unavailable
+
+// =======================================================================================
+// MatOp: the m x n matrix A on the device and its fused dual mat-vec
+// =======================================================================================
+struct MatOp {
+    int kind = 0;  // 0 none, 1 dense, 2 sparse
+    int64_t m = 0, n = 0, n_pad = 0, m_pad = 0;
+    int64_t m_local = 0, row_begin = 0, m_pad_local = 0;
+    // dense
+    DevBuf<double> A_own;
+    const double *A = nullptr;
+    int64_t lda = 0;
+    CUtensorMap tmap;
+    K1Plan plan;
+    DevBuf<int32_t> d_unit_begin, d_slot_base, d_first_cta;
+    DevBuf<double> rowpart, colpart;
+    // plain path + sparse path: complete results
+    DevBuf<double> full_ax, full_atw, scratch;
+    DevBuf<int32_t> d_one_band;  // {0, 1}
+    int nchunk = 0;
+    // sparse
+    DevBuf<int32_t> csr_ptr, csr_idx, csc_ptr, csc_idx;
+    DevBuf<double> csr_val, csc_val;
+    int64_t nnz = 0;
+    // multi-GPU exchange
+    int nranks = 1, rank = 0;
+    void *comm = nullptr;
+    DevBuf<double> xbuf;
+
+    int impl = 0;  // 0 TMA, 1 plain
+    int num_sms = 148;
+    Stats *stats = nullptr;
+
+    void init_dense(int64_t m_, int64_t n_, const double *Asrc, int64_t lda_src, int location, int64_t row_begin_,
+                    int64_t row_count, int grid_ctas, cudaStream_t st);
+    void init_sparse(int64_t m_, int64_t n_, const int64_t *colptr, const int64_t *rowval, const double *nzval,
+                     int64_t base, cudaStream_t st);
+    double bytes_per_pass() const;
+    // Runs one pass; X[v] have n_pad entries, W[v] have m_pad entries (global rows).
+    MVView run(int NV, const double *const *X, const double *const *W, const int32_t *skip, cudaStream_t st);
+
+    template <int NV>
+    MVView run_t(const double *const *X, const double *const *W, const int32_t *skip, cudaStream_t st);
+    MVView view_full(int NV, const double *ax, const double *atw) const;
+};
+
+// =======================================================================================
+// ConeSet: a product of cones over a padded vector (DualConeProduct / ConeProduct)
+// =======================================================================================
+struct ConeSeg {
+    int32_t type;  // FOS_CONE_*
+    int32_t dual;  // proxDual!
+    int64_t off;   // padded offset
+    int64_t len;
+};
+struct PsdCone {
+    int64_t off;
+    int32_t d;
+    int32_t dual;
+};
+struct ConeSet {
+    int64_t NP = 0;
+    DevBuf<uint8_t> ops;
+    DevBuf<int32_t> cone_of;
+    DevBuf<SocCone> soc;
+    DevBuf<SocScale> soc_scale;
+    DevBuf<int32_t> chunk_cone;
+    DevBuf<double> chunk_sum;
+    DevBuf<unsigned int> counter;
+    int nsoc = 0, nchunks = 0;
+    std::vector<PsdCone> psd;
+    DevBuf<PsdCone> d_psd;
+    DevBuf<double> psd_work;
+    int psd_max_d = 0;
+    void build(int64_t NP_, const std::vector<ConeSeg> &segs);
+};
+
+struct Handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int num_sms = 148;
+    std::string err;
+    // options
+    int matvec_impl = 0, grid_ctas = 0, cg_batch = 0;
+    // problem
+    bool loaded = false;
+    Lay L{};
+    SegMap seg{};
+    int64_t N = 0;
+    MatOp A;
+    DevBuf<double> d_b, d_c, d_q;  // HSDE: b (m_pad), c (n_pad).  plain: q (n_pad)
+    double nb = 0, ncn = 0;
+    double beta = 1.0;
+    bool decreasing = true;
+    // S1
+    DevBuf<double> rhs, sol, r, p, Ap;
+    int64_t s1_calls = 1, cgiter = 0;
+    bool firstrun = true;
+    bool warn_maxit = false;
+    // algorithm
+    int alg = FOS_ALG_GAP;
+    double alpha = 0.8, alpha1 = 1.8, alpha2 = 1.8, betaA = 0.0;
+    int64_t iproj = 100;
+    double fista_t = 1.0;
+    DevBuf<double> x, tmp1, tmp2, proj, fy, fxold, dp, dq, dy, w1, w2, w3, prev;
+    ConeSet cones;
+    // control
+    DevBuf<Ctrl> d_ctrl;
+    Ctrl *h_ctrl = nullptr;  // pinned
+    DevBuf<double> red_partials;
+    DevBuf<unsigned int> red_counter;
+    RedBuf rb{};
+    DevBuf<double> d_recs;
+    int rec_cap = 0;
+    DevBuf<double> d_stage;
+    double *h_stage = nullptr;  // pinned
+    size_t h_stage_n = 0;
+    int status = FOS_STATUS_CONTINUE;
+    bool checked = false;
+    Stats stats;
+    // comm
+    int rank = 0, nranks = 1;
+    void *comm = nullptr;
+    // run parameters remembered for finish()
+    int64_t cur_i = 0, cur_checki = 100;
+    double cur_eps = 1e-5;
+
+    ~Handle();
+    void create(int dev);
+    void require_loaded() const { FOS_REQUIRE(loaded, "no problem loaded on this handle"); }
+    // loading
+    void finish_load_common(const std::vector<ConeSeg> &segs);
+    void load_conic(int64_t m, int64_t n, const double *b, const double *c, int64_t nc1, const int32_t *t1,
+                    const int64_t *l1, int64_t nc2, const int32_t *t2, const int64_t *l2);
+    void load_affine(int64_t am, int64_t an, const double *b, const double *q, int32_t beta_, int32_t decr,
+                     int64_t nc, const int32_t *t, const int64_t *l);
+    // vectors
+    int vgrid(int64_t len) const;
+    void ensure_stage(size_t n);
+    void pack_from_host(const double *z, double *dst);
+    void unpack_to_host(const double *src, double *z);
+    // operators
+    MVView kkt_pass(const double *v, const int32_t *skip);
+    void kkt_mul(const double *in, double *out);
+    void q_mul(const double *Bp, double *Yp, bool transpose);
+    void s1_prox(const double *xin);
+    void cg_solve(double tol, int max_iters);
+    void cg_enqueue_iteration();
+    void sol_scaled_to(double *dst);
+    void cone_project(ConeSet &K, const double *in, double *projbuf, int epi, const EpiArgs &E);
+    void check(const double *z, int64_t i, bool override_);
+    void sync_ctrl();
+    // algorithm steps
+    void set_algorithm(int alg_, double a, double a1, double a2, double bA, int64_t ip);
+    void step(int64_t i);
+    void getsol();
+    void begin_solve();
+    int64_t run(int64_t i_start, int64_t n_iters, int64_t checki, double eps, double *records, int64_t rec_cap_host,
+                int64_t *n_rec, double *trace);
+    void finish(double *guess, double *record, int64_t *n_rec);
+    void ensure_recs(int cap);
+};
+
+#define FOS_LAUNCH(h, kernel, grid, block, smem, ...)                  \
+    do {                                                               \
+        kernel<<<(grid), (block), (smem), (h)->stream>>>(__VA_ARGS__); \
+        (h)->stats.launches++;                                         \
+    } while (0)
+
+void psd_project(Handle *h, ConeSet &K, const double *in, double *projbuf);  // K5, psd.cu
+
+}  // namespace fos

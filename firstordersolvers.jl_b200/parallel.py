@@ -1,0 +1,63 @@
+"""Multi-GPU plumbing: one process per GPU (``torchrun``), ``torch.distributed`` only for the
+rendezvous.  The data path is inside the CUDA library: A is row-sharded, every rank runs the
+fused mat-vec on its rows and the A' partial sums (+ the owners' A x rows) are all-reduced
+with NCCL over NVLink (new functionality, the reference has no parallelism).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+SHARD_ALIGN = 16  # row_begin must be a multiple of the 16-row tile (fos_load_conic_dense)
+
+
+def row_shard(m: int, rank: int, nranks: int, align: int = SHARD_ALIGN):
+    """Rows [begin, begin+count) owned by `rank`: contiguous, multiple-of-`align` boundaries,
+    balanced to within one `align` block; ranks past the end get count = 0."""
+    if not (0 <= rank < nranks):
+        raise ValueError("rank out of range")
+    blocks = (m + align - 1) // align
+    base, extra = divmod(blocks, nranks)
+    b0 = rank * base + min(rank, extra)
+    nb = base + (1 if rank < extra else 0)
+    begin = min(b0 * align, m)
+    end = min((b0 + nb) * align, m)
+    return begin, end - begin
+
+
+def batch_shard(nproblems: int, rank: int, nranks: int):
+    """Independent problems [begin, begin+count) of a batch owned by `rank` (no collective)."""
+    base, extra = divmod(nproblems, nranks)
+    begin = rank * base + min(rank, extra)
+    return begin, base + (1 if rank < extra else 0)
+
+
+def exchange_comm_id(rank: int, make_id, dist=None):
+    """Rank 0 creates the 128-byte NCCL unique id (``make_id()``), everyone receives it through
+    ``torch.distributed`` (any backend; gloo on CPU in the tests)."""
+    import torch
+    if dist is None:
+        import torch.distributed as dist
+    buf = torch.zeros(_lib.FOS_COMM_ID_BYTES, dtype=torch.uint8)
+    if rank == 0:
+        buf.copy_(torch.from_numpy(np.frombuffer(make_id(), dtype=np.uint8).copy()))
+    dist.broadcast(buf, src=0)
+    return bytes(buf.numpy().tobytes())
+
+
+def nccl_unique_id() -> bytes:
+    L = _lib.load()
+    arr = (C.c_uint8 * _lib.FOS_COMM_ID_BYTES)()
+    rc = L.fos_comm_unique_id(arr)
+    if rc != 0:
+        raise _lib.FosError(rc, (L.fos_last_error(None) or b"").decode())
+    return bytes(arr)
+
+
+def init_comm(handle, rank: int, nranks: int, comm_id: bytes):
+    """fos_comm_init on a ``Handle`` (before loading the problem)."""
+    arr = (C.c_uint8 * _lib.FOS_COMM_ID_BYTES).from_buffer_copy(comm_id)
+    handle.ck(handle.L.fos_comm_init(handle.h, rank, nranks, arr))

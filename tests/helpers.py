@@ -1,0 +1,93 @@
+"""Shared helpers of the parity tests: load the same (c, A, b, cones) into the CUDA library
+(through the C ABI) and into the oracle."""
+import ctypes as C
+
+import numpy as np
+import scipy.sparse as sp
+
+CONE = {"Free": 0, "Zero": 1, "NonNeg": 2, "NonPos": 3, "SOC": 4, "SOCRotated": 5, "SDP": 6}
+
+
+def rel_err(a, b):
+    a = np.asarray(a, float)
+    b = np.asarray(b, float)
+    den = max(np.abs(b).max(initial=0.0), 1e-300)
+    return float(np.abs(a - b).max(initial=0.0) / den)
+
+
+def load_conic(fos, P, storage="auto", **options):
+    """ConicProblem -> fos Handle with the problem loaded (C ABI: fos_load_conic_csc/dense)."""
+    from fos_b200 import model as M
+    H = fos.Handle(0)
+    for k, v in options.items():
+        H.set_option(k, v)
+    t1, l1 = M._cone_arrays(P.constr_cones, P.m, "constraint")
+    t2, l2 = M._cone_arrays(P.var_cones, P.n, "variable")
+    b = np.ascontiguousarray(P.b, float)
+    c = np.ascontiguousarray(P.c, float)
+    if storage == "dense_direct":
+        Ad = np.ascontiguousarray(P.A.toarray() if sp.issparse(P.A) else P.A, dtype=np.float64)
+        H.ck(H.L.fos_load_conic_dense(H.h, P.m, P.n, Ad.ctypes.data_as(C.c_void_p), P.n, 0, 0, P.m, M._d(b),
+                                      M._d(c), len(t1), M._i32p(t1), M._i64p(l1), len(t2), M._i32p(t2),
+                                      M._i64p(l2)))
+    else:
+        _, colptr, rowval, nzval = M._csc_arrays(P.A)
+        code = {"auto": 0, "dense": 1, "sparse": 2}[storage]
+        H.ck(H.L.fos_load_conic_csc(H.h, P.m, P.n, M._i64p(colptr), M._i64p(rowval), M._d(nzval), 0, M._d(b),
+                                    M._d(c), len(t1), M._i32p(t1), M._i64p(l1), len(t2), M._i32p(t2), M._i64p(l2),
+                                    code))
+    H.set_initial_iterate()
+    return H
+
+
+def load_affine(fos, A, b, q, beta, cones, decreasing=False, storage="auto", **options):
+    from fos_b200 import model as M
+    H = fos.Handle(0)
+    for k, v in options.items():
+        H.set_option(k, v)
+    Am, colptr, rowval, nzval = M._csc_arrays(A)
+    am, an = Am.shape
+    t, ln = M._cone_arrays(cones, am + an, "S2")
+    b = np.ascontiguousarray(b, float)
+    q = np.ascontiguousarray(q, float)
+    code = {"auto": 0, "dense": 1, "sparse": 2}[storage]
+    H.ck(H.L.fos_load_affine_csc(H.h, am, an, M._i64p(colptr), M._i64p(rowval), M._d(nzval), 0, M._d(b), M._d(q),
+                                 int(beta), 1 if decreasing else 0, len(t), M._i32p(t), M._i64p(ln), code))
+    H.set_initial_iterate()
+    return H
+
+
+ALG_SETUPS = {
+    # name: (oracle args, fos algorithm factory)
+    "DR": (("GAP", 0.5, 2.0, 2.0, 0.0, 100), lambda f: f.DR(0.5)),
+    "GAP": (("GAP", 0.8, 1.8, 1.8, 0.0, 100), lambda f: f.GAP()),
+    "AP": (("GAP", 1.0, 1.0, 1.0, 0.0, 100), lambda f: f.AP()),
+    "GAPA": (("GAPA", 1.0, 0.0, 0.0, 0.0, 100), lambda f: f.GAPA()),
+    "GAPA_b": (("GAPA", 0.8, 0.0, 0.0, 0.9, 100), lambda f: f.GAPA(0.8, 0.9)),
+    "FISTA": (("FISTA", 1.0, 0.0, 0.0, 0.0, 100), lambda f: f.FISTA()),
+    "Dykstra": (("Dykstra", 0.0, 0.0, 0.0, 0.0, 100), lambda f: f.Dykstra()),
+    "GAPP": (("GAPP", 0.8, 1.8, 1.8, 0.0, 7), lambda f: f.GAPP(direct=False, iproj=7)),
+}
+
+
+def set_alg_both(fos, H, O, name):
+    oargs, fac = ALG_SETUPS[name]
+    O.set_algorithm(*oargs)
+    H.set_algorithm(fac(fos))
+
+
+def sync_state_from_oracle(H, O, alg):
+    """Copy every persistent piece of solver state from the oracle into the GPU handle so that the
+    next iteration starts from bit-identical inputs (lock-step parity)."""
+    H.set_state("x", O.get_state("x"))
+    if O.s1_calls > 1:
+        H.set_state("xinit", O.get_state("xinit"))
+    H.set_info("s1_calls", O.s1_calls)
+    if alg.startswith("GAPA"):
+        H.set_info("alpha12", O.alpha12)
+    if alg == "FISTA":
+        H.set_state("fista_y", O.get_state("fista_y"))
+        H.set_info("fista_t", O.fista_t)
+    if alg == "Dykstra":
+        H.set_state("dykstra_p", O.get_state("dykstra_p"))
+        H.set_state("dykstra_q", O.get_state("dykstra_q"))
