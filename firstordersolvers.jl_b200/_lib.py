@@ -57,6 +57,7 @@ SIGNATURES = {
     "fos_cone_prox": (C.c_int32, [_h, _dp, _dp]),
     "fos_cg_dense": (C.c_int32, [_h, C.c_int64, _dp, _dp, _dp, C.c_double, C.c_int64, _i64p]),
     "fos_prox_cone": (C.c_int32, [_h, C.c_int32, C.c_int32, _dp, _dp, C.c_int64]),
+    "fos_get_stream": (C.c_int32, [_h, C.POINTER(C.c_uint64)]),
     "fos_k1_plan": (C.c_int32, [C.c_int64, C.c_int64, C.c_int32, _i32p, _i32p, C.c_int64, _i32p, _i32p, C.c_int64]),
     "fos_time_matvec": (C.c_int32, [_h, C.c_int32, C.c_int32, _dp, _dp]),
 }

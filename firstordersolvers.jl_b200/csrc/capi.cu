@@ -92,6 +92,9 @@ int32_t fos_set_option(fos_handle_t hh, const char *key, double value)
         h.grid_ctas = (int)value;
     } else if (k == "cg_batch") {
         h.cg_batch = (int)value;
+    } else if (k == "profile_matvec") {
+        h.A.profile = value != 0;
+        h.A.prof_reset();
     } else if (k == "use_graphs") {
         // reserved
     } else {
@@ -351,6 +354,13 @@ int32_t fos_get_info(fos_handle_t hh, int32_t which, double *out)
         h.sync_ctrl();
         *out = h.h_ctrl->ls_alphabest;
         break;
+    case 9: *out = h.A.prof_ms[2]; break;
+    case 10: *out = (double)h.A.prof_n[2]; break;
+    case 11: *out = h.A.prof_ms[1]; break;
+    case 12: *out = (double)h.A.prof_n[1]; break;
+    case 13: *out = (double)h.A.prof_skipped; break;
+    case 14: *out = h.A.bytes_per_pass(); break;
+    case 15: *out = (double)h.num_sms; break;
     default: throw Error(FOS_ERR_INVALID, "unknown info selector");
     }
     FOS_API_END(hh)
@@ -545,6 +555,14 @@ int32_t fos_prox_cone(fos_handle_t hh, int32_t cone_type, int32_t dual, const do
     h.cone_project(K, din.p, dout.p, EPI_NONE, E);
     FOS_CUDA(cudaMemcpyAsync(y, dout.p, (size_t)len * 8, cudaMemcpyDeviceToHost, h.stream));
     FOS_CUDA(cudaStreamSynchronize(h.stream));
+    FOS_API_END(hh)
+}
+
+int32_t fos_get_stream(fos_handle_t hh, uint64_t *stream_out)
+{
+    FOS_API_BEGIN(hh)
+    FOS_REQUIRE(stream_out != nullptr, "null output");
+    *stream_out = (uint64_t)(uintptr_t)hh->h.stream;
     FOS_API_END(hh)
 }
 

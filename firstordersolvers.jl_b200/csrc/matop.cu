@@ -144,6 +144,58 @@ void MatOp::init_sparse(int64_t m_, int64_t n_, const int64_t *colptr, const int
     d_one_band.upload(std::vector<int32_t>{0, 1});
 }
 
+MatOp::~MatOp()
+{
+    for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
+}
+void MatOp::prof_begin(int NV, cudaStream_t st)
+{
+    if (!profile) return;
+    if (ev_used + 2 > ev_pool.size()) {
+        for (int k = 0; k < 64; k++) {
+            cudaEvent_t e;
+            FOS_CUDA(cudaEventCreate(&e));
+            ev_pool.push_back(e);
+        }
+    }
+    ev_nv.resize(ev_pool.size() / 2);
+    ev_nv[ev_used / 2] = NV;
+    FOS_CUDA(cudaEventRecord(ev_pool[ev_used], st));
+}
+void MatOp::prof_end(cudaStream_t st)
+{
+    if (!profile) return;
+    FOS_CUDA(cudaEventRecord(ev_pool[ev_used + 1], st));
+    ev_used += 2;
+}
+void MatOp::prof_collect()
+{
+    if (!profile) return;
+    // launches faster than 25 TB/s did no work: they are the predicated no-ops of a CG batch
+    const double min_ms = bytes_per_pass() / 25e12 * 1e3;
+    for (size_t k = 0; k + 1 < ev_used; k += 2) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ev_pool[k], ev_pool[k + 1]) != cudaSuccess) continue;
+        const int nv = ev_nv[k / 2];
+        if ((double)ms < min_ms) {
+            prof_skipped++;
+            continue;
+        }
+        prof_ms[nv] += ms;
+        prof_n[nv]++;
+    }
+    ev_used = 0;
+}
+void MatOp::prof_reset()
+{
+    ev_used = 0;
+    for (int k = 0; k < 3; k++) {
+        prof_ms[k] = 0;
+        prof_n[k] = 0;
+    }
+    prof_skipped = 0;
+}
+
 double MatOp::bytes_per_pass() const
 {
     if (kind == 1) return 8.0 * (double)m_local * (double)n;
@@ -241,7 +293,9 @@ MVView MatOp::run_t(const double *const *X, const double *const *W, const int32_
 MVView MatOp::run(int NV, const double *const *X, const double *const *W, const int32_t *skip, cudaStream_t st)
 {
     FOS_REQUIRE(kind != 0, "matrix not loaded");
+    prof_begin(NV, st);
     MVView V = (NV == 1) ? run_t<1>(X, W, skip, st) : run_t<2>(X, W, skip, st);
+    prof_end(st);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) throw Error(FOS_ERR_CUDA, std::string("mat-vec launch failed: ") + cudaGetErrorString(e));
     return V;

@@ -93,6 +93,7 @@ void Handle::sync_ctrl()
 {
     FOS_CUDA(cudaMemcpyAsync(h_ctrl, d_ctrl.p, sizeof(Ctrl), cudaMemcpyDeviceToHost, stream));
     FOS_CUDA(cudaStreamSynchronize(stream));
+    A.prof_collect();
 }
 
 void Handle::ensure_recs(int cap)

@@ -101,6 +101,19 @@ struct MatOp {
     int impl = 0;  // 0 TMA, 1 plain
     int num_sms = 148;
     Stats *stats = nullptr;
+    // in-situ timing of the mat-vec launches (bench.py roofline): CUDA events around every launch
+    bool profile = false;
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<int> ev_nv;
+    size_t ev_used = 0;
+    double prof_ms[3] = {0, 0, 0};
+    int64_t prof_n[3] = {0, 0, 0};
+    int64_t prof_skipped = 0;
+    void prof_begin(int NV, cudaStream_t st);
+    void prof_end(cudaStream_t st);
+    void prof_collect();  // call after a stream synchronisation
+    void prof_reset();
+    ~MatOp();
 
     void init_dense(int64_t m_, int64_t n_, const double *Asrc, int64_t lda_src, int location, int64_t row_begin_,
                     int64_t row_count, int grid_ctas, cudaStream_t st);

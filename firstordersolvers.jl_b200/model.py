@@ -154,7 +154,8 @@ class _Handle:
     _STATE = {"x": 0, "tmp1": 1, "tmp2": 2, "xinit": 3, "rhs": 4, "proj": 5, "fista_y": 6, "dykstra_p": 7,
               "dykstra_q": 8}
     _INFO = {"s1_calls": 0, "cgiter": 1, "alpha12": 2, "fista_t": 3, "cg_warned": 4, "total_cg": 5,
-             "total_passes": 6, "launches": 7, "alphabest": 8}
+             "total_passes": 6, "launches": 7, "alphabest": 8, "mv2_ms": 9, "mv2_n": 10, "mv1_ms": 11, "mv1_n": 12,
+             "mv_skipped": 13, "bytes_per_pass": 14, "num_sms": 15}
 
     def get_state(self, which):
         z = np.empty(self.n())
@@ -239,6 +240,11 @@ class _Handle:
         y = np.empty_like(x)
         self.ck(self.L.fos_prox_cone(self.h, CONE_CODES[name], 1 if dual else 0, _d(x), _d(y), x.size))
         return y
+
+    def stream(self):
+        out = C.c_uint64(0)
+        self.ck(self.L.fos_get_stream(self.h, C.byref(out)))
+        return int(out.value)
 
     def time_matvec(self, nvec=2, reps=10):
         ms = C.c_double(0)

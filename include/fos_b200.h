@@ -96,7 +96,8 @@ const char *fos_last_error(fos_handle_t h);
  *   "matvec_impl"  0 = TMA-staged fused kernel (default), 1 = plain two-kernel reference path
  *   "grid_ctas"    number of persistent CTAs of the fused kernel (default = #SMs)
  *   "cg_batch"     CG iterations enqueued per host synchronisation (default adaptive = 0)
- *   "use_graphs"   1 = replay the CG iteration as a CUDA graph (default 1)               */
+ *   "profile_matvec" 1 = CUDA events around every mat-vec launch (read back with fos_get_info)
+ *   "use_graphs"   reserved                                                                */
 int32_t fos_set_option(fos_handle_t h, const char *key, double value);
 
 /* ====================================================================================== */
@@ -161,7 +162,10 @@ int32_t fos_set_state(fos_handle_t h, int32_t which, const double *buf, int64_t 
 /* Scalars.  which: 0 S1.i (call counter, affinepluslinear.jl:66), 1 S1.cgiter (:67),
  * 2 GAPA alpha12 (gapa.jl:18), 3 FISTA t (fista.jl:14), 4 CG-hit-max-iters flag (the @warn of
  * conjugategradients.jl:53), 5 total CG iterations so far, 6 total passes over A so far,
- * 7 kernel launches so far, 8 GAPP alpha_best of the last projected step. */
+ * 7 kernel launches so far, 8 GAPP alpha_best of the last projected step; with the option
+ * "profile_matvec" = 1: 9 / 10 summed milliseconds / count of 2-RHS mat-vec launches, 11 / 12 the
+ * same for 1-RHS launches, 13 predicated no-op launches; 14 algorithmic bytes of one pass over A,
+ * 15 number of SMs. */
 int32_t fos_get_info(fos_handle_t h, int32_t which, double *out);
 /* Restores a scalar: which = 0 (S1.i), 2 (alpha12) or 3 (FISTA t). */
 int32_t fos_set_info(fos_handle_t h, int32_t which, double value);
@@ -220,6 +224,9 @@ int32_t fos_k1_plan(int64_t m_local, int64_t n, int32_t ctas, int32_t *dims_out,
 /* ====================================================================================== */
 /* measurement helpers (bench.py)                                                         */
 /* ====================================================================================== */
+/* The CUDA stream (cudaStream_t as an integer) all work of this handle is enqueued on, so that a
+ * caller can bracket calls with its own CUDA events (torch.cuda.ExternalStream). */
+int32_t fos_get_stream(fos_handle_t h, uint64_t *stream_out);
 /* Times `reps` launches of the fused dual mat-vec (nvec = 1 or 2 right-hand sides per
  * direction) on the loaded matrix with CUDA events on the library's stream; returns the
  * average milliseconds per launch and the algorithmic bytes one launch streams. */

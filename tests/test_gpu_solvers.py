@@ -1,0 +1,224 @@
+"""GPU parity tests, solver level (through the C ABI): GAP/DR/AP/GAPA/FISTA/Dykstra/GAPP steps,
+status checks, getsol and the forced final check, against the CPU oracle.
+
+Two kinds of comparison ("parity budget"):
+
+* LOCK-STEP: before every iteration the GPU handle is given the oracle's state (iterate, CG warm
+  start, S1 call counter, algorithm scalars); both sides then run ONE iteration and the results
+  are compared at 1e-10 relative.  This is the north-star per-iteration bar: it checks the
+  exact algorithm (same CG iteration count, same stopping decisions) at every point of the
+  trajectory without letting the reference algorithm's own rounding amplification compound
+  (its truncated CG on the indefinite KKT matrix amplifies 1e-16 perturbations by ~1e4 per
+  solve: two CPU restatements, or float64 vs long double, drift apart just as much).
+* FREE-RUNNING: same status, same iteration count, same check iterations; residual histories
+  and the solution agree within the drift that two CPU restatements show between themselves.
+"""
+import numpy as np
+import pytest
+
+from helpers import ALG_SETUPS, load_affine, load_conic, rel_err, set_alg_both, sync_state_from_oracle
+
+pytestmark = pytest.mark.gpu
+
+STEP_TOL = 1e-10  # north_star: per-iteration iterates within 1e-10 relative (lock-step)
+
+
+def _problem(problems, kind):
+    if kind == "nnls":          # C1: README NNLS 40x50 -> m=91, n=51 (SOC + NonNeg)
+        return problems.nnls_conic(40, 50, seed=1)
+    if kind == "lasso":         # C2 at test scale (Zero + NonNeg), dense
+        return problems.lasso_like(120, 260, seed=2)
+    if kind == "socls":         # C3 at test scale (two SOCs, one > 2048 entries)
+        return problems.soc_constrained_ls(2100, 40, seed=3)
+    if kind == "sdp":           # C4 at test scale
+        return problems.sdp_nearest_correlation(6, seed=4)
+    raise KeyError(kind)
+
+
+CASES = [("nnls", "DR"), ("nnls", "GAP"), ("nnls", "AP"), ("nnls", "GAPA"), ("nnls", "GAPA_b"), ("nnls", "FISTA"),
+         ("nnls", "Dykstra"), ("nnls", "GAPP"), ("lasso", "DR"), ("lasso", "GAPA"), ("socls", "GAPA"),
+         ("socls", "DR"), ("sdp", "GAP"), ("sdp", "DR")]
+
+
+@pytest.mark.parametrize("kind,alg", CASES)
+def test_lockstep_iterations(fos, oracle, kind, alg):
+    from fos_b200 import problems
+    P = _problem(problems, kind)
+    O = oracle.OracleConic(P.c, P.A, P.b, P.constr_cones, P.var_cones)
+    H = load_conic(fos, P)
+    set_alg_both(fos, H, O, alg)
+    O.set_iterate(O.initial_value())
+    n_iter, checki, eps = 40, 5, 1e-9
+    worst = 0.0
+    H.ck(H.L.fos_begin_solve(H.h))
+    for i in range(1, n_iter + 1):
+        sync_state_from_oracle(H, O, alg)
+        ro = O.run(i, 1, checki=checki, eps=eps)
+        done, st, rec, _ = H.run(i, 1, checki, eps)
+        assert done == 1
+        assert H.info("cgiter") == O.cgiter, f"iteration {i}: CG count {H.info('cgiter')} vs {O.cgiter}"
+        assert H.info("s1_calls") == O.s1_calls
+        e = rel_err(H.get_iterate(), O.get_state("x"))
+        worst = max(worst, e)
+        assert e < STEP_TOL, f"iteration {i}: iterate differs by {e:.3e}"
+        if alg.startswith("GAPA"):
+            assert abs(H.info("alpha12") - O.alpha12) < 1e-9
+        if i % checki == 0:  # p/d/g residual records
+            ho = ro["history"]
+            assert len(rec) == 1 and len(ho["i"]) == 1
+            assert rec[0, 0] == ho["i"][0] == i
+            for col, key in ((1, "p"), (2, "d"), (3, "g"), (4, "ctx"), (5, "bty"), (6, "kappa"), (7, "tau")):
+                assert abs(rec[0, col] - ho[key][0]) <= 1e-9 * max(1.0, abs(ho[key][0])) + 1e-10 * abs(ho[key][0]), key
+            assert rec[0, 8] == ho["cgiter"][0]
+            assert rec[0, 9] == ho["status"][0]
+        else:
+            assert len(rec) == 0
+    print(f"{kind}/{alg}: worst one-step relative deviation {worst:.2e}")
+
+
+@pytest.mark.parametrize("kind,alg,eps,max_iters", [("nnls", "DR", 1e-5, 2000), ("lasso", "DR", 1e-5, 3000),
+                                                    ("socls", "GAPA", 1e-5, 3000), ("sdp", "GAP", 1e-5, 3000),
+                                                    ("nnls", "GAPA", 1e-6, 3000)])
+def test_free_running_solve(fos, oracle, kind, alg, eps, max_iters):
+    """Same status and iteration count at eps; histories within the reference algorithm's own drift."""
+    from fos_b200 import problems
+    P = _problem(problems, kind)
+    O = oracle.OracleConic(P.c, P.A, P.b, P.constr_cones, P.var_cones)
+    H = load_conic(fos, P)
+    set_alg_both(fos, H, O, alg)
+    O.set_iterate(O.initial_value())
+    ro = O.solve(max_iters=max_iters, checki=100, eps=eps)
+    done, st, rec, guess = H.solve(max_iters, 100, eps)
+    assert fos.model.STATUS_SYMBOLS[st] == ro["status"]
+    assert done == ro["iterations"]
+    ho = ro["history"]
+    assert list(rec[:, 0]) == list(ho["i"])
+    assert list(rec[:, 9]) == list(ho["status"])
+    # first check: little accumulated drift; later checks: relative to the residual scale at that point
+    for col, key in ((1, "p"), (2, "d"), (3, "g")):
+        np.testing.assert_allclose(rec[:, col], ho[key], rtol=2e-3, atol=1e-3 * eps)
+    xo = np.concatenate(O.populate_solution(ro["guess"]))
+    n, m = P.n, P.m
+    l = n + m + 1
+    tau = guess[l - 1]
+    xg = np.concatenate([guess[:n] / tau, guess[n:n + m] / tau, guess[l + n:l + n + m] / tau])
+    assert rel_err(xg, xo) < 1e-4
+
+
+def test_solve_tail_forced_check_and_getsol_side_effects(fos, oracle):
+    """a-Q 1-3: forced final check iff the last iteration was not a check iteration; getsol runs one
+    more CG solve that advances S1.i; a second solve! continues the tolerance schedule."""
+    from fos_b200 import problems
+    P = problems.nnls_conic(10, 12, seed=3)
+    O = oracle.OracleConic(P.c, P.A, P.b, P.constr_cones, P.var_cones)
+    H = load_conic(fos, P)
+    set_alg_both(fos, H, O, "DR")
+    O.set_iterate(O.initial_value())
+    ro = O.solve(max_iters=37, checki=10, eps=1e-12)
+    done, st, rec, guess = H.solve(37, 10, 1e-12)
+    assert done == 37 and ro["iterations"] == 37
+    assert list(rec[:, 0]) == [10, 20, 30, 37] == list(ro["history"]["i"])  # forced check recorded at i = 37
+    assert H.info("s1_calls") == O.s1_calls == 39                           # 37 steps + getsol, counter starts at 1
+    assert fos.model.STATUS_SYMBOLS[st] == ro["status"] == "Indeterminate"
+    assert rel_err(guess, ro["guess"]) < 1e-6
+    # second solve on the same model: schedule continues (a-Q 2)
+    O.set_iterate(O.initial_value())
+    H.set_initial_iterate()
+    ro2 = O.solve(max_iters=40, checki=10, eps=1e-12)
+    done2, st2, rec2, _ = H.solve(40, 10, 1e-12)
+    assert list(rec2[:, 0]) == [10, 20, 30, 40] == list(ro2["history"]["i"])  # no forced check
+    assert H.info("s1_calls") == O.s1_calls == 80
+    assert list(rec2[:, 8]) == list(ro2["history"]["cgiter"])
+
+
+# ---------------------------------------------------------------------------------------------
+# Feasibility form (test/testfeasibility.jl with S1 = AffinePlusLinear)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("alg,checki,expect", [("DR", 10, "Optimal"), ("GAPA", 100, "Optimal"),
+                                               ("GAPP", 100, "Optimal"), ("AP", 1, None), ("GAP", 100, None),
+                                               ("FISTA", 100, None), ("Dykstra", 100, None)])
+def test_feasibility_solvers(fos, oracle, alg, checki, expect):
+    from fos_b200 import problems
+    A, b, cones = problems.feasibility_problem(50, 100, seed=2)
+    O = oracle.OracleFeasibility(A, b, np.zeros(100), 1, cones)
+    H = load_affine(fos, A, b, np.zeros(100), 1, cones)
+    oargs, fac = ALG_SETUPS[alg]
+    if alg == "GAPP":
+        oargs = ("GAPP", 0.8, 1.8, 1.8, 0.0, 100)
+        fac = lambda f: f.GAPP(direct=False, iproj=100)  # noqa: E731
+    O.set_algorithm(*oargs)
+    H.set_algorithm(fac(fos))
+    O.set_iterate(O.initial_value())
+    max_iters = 3000
+    ro = O.solve(max_iters=max_iters, checki=checki, eps=1e-8)
+    done, st, rec, guess = H.solve(max_iters, checki, 1e-8)
+    status = fos.model.STATUS_SYMBOLS[st]
+    assert status == ro["status"]
+    if expect:
+        assert status == expect
+        x = guess[:100]
+        assert x.min() > -1e-12                       # testfeasibility.jl:18
+        assert np.abs(A @ x - b).max() < 1e-6         # :19 / :42
+    # iteration counts: the err <= eps test sits on a steep slope, allow one check interval of slack
+    assert abs(done - ro["iterations"]) <= checki
+    k = min(len(rec), len(ro["history"]["i"]), 5)
+    assert list(rec[:k, 0]) == list(ro["history"]["i"][:k])
+    assert np.isnan(rec[0, 1]) == np.isnan(ro["history"]["p"][0])  # first err is NaN only when checki == 1
+
+
+def test_feasibility_lockstep(fos, oracle):
+    from fos_b200 import problems
+    A, b, cones = problems.feasibility_problem(30, 70, seed=5)
+    for alg in ("DR", "GAPA", "FISTA", "Dykstra"):
+        O = oracle.OracleFeasibility(A, b, np.zeros(70), 1, cones)
+        H = load_affine(fos, A, b, np.zeros(70), 1, cones)
+        set_alg_both(fos, H, O, alg)
+        O.set_iterate(O.initial_value())
+        H.ck(H.L.fos_begin_solve(H.h))
+        for i in range(1, 31):
+            sync_state_from_oracle(H, O, alg)
+            O.run(i, 1, checki=7, eps=1e-12)
+            H.run(i, 1, 7, 1e-12)
+            assert H.info("cgiter") == O.cgiter
+            assert rel_err(H.get_iterate(), O.get_state("x")) < STEP_TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference-facing Python API end to end (ConicModel / loadproblem! / optimize!)
+# ---------------------------------------------------------------------------------------------
+def test_mathprogbase_api_end_to_end(fos, oracle, capsys):
+    from scipy.optimize import nnls
+    from fos_b200 import problems
+    P = problems.nnls_conic(40, 50, seed=1)
+    alg = fos.GAP(0.5, 2.0, 2.0, max_iters=2000, verbose=1, debug=2)       # README.md:27
+    model = fos.ConicModel(alg)
+    fos.loadproblem(model, P.c, P.A, P.b, [("SOC", range(1, 42)), ("NonNeg", range(42, 92))],
+                    [("Free", range(1, 52))])
+    fos.optimize(model)
+    out = capsys.readouterr().out.splitlines()
+    assert out[2] == " Iter | pri res | dua res | rel gap | pri obj | dua obj | kap/tau | cg  | time"  # testprint.jl:15
+    assert out[4][:7] == "   100|"                                                                     # testprint.jl:17
+    assert any(line.startswith("Found solution i=") for line in out)
+    assert fos.status(model) == "Optimal"
+    rng = np.random.default_rng(1)
+    D, d = rng.standard_normal((40, 50)), rng.standard_normal(40)
+    _, rn = nnls(D, d)
+    assert abs(fos.getobjval(model) - rn) < 1e-4 * rn
+    assert fos.getsolution(model)[1:].min() > -1e-6
+    assert fos.numvar(model) == 51 and fos.numconstr(model) == 91
+    its, ps = model.history.get("p")
+    assert its[0] == 100 and len(ps) == len(its)
+    for key in ("p", "d", "g", "ctx", "bty", "κ", "τ", "t", "cgiter", "x", "y", "s"):
+        assert key in model.history
+    assert model.enditr == -1
+
+
+def test_feasibility_api_end_to_end(fos):
+    from fos_b200 import problems
+    A, b, cones = problems.feasibility_problem(50, 100, seed=2)
+    prob = fos.Feasibility(fos.AffinePlusLinear(A, b, np.zeros(100), 1), fos.ConeProduct(cones), 150)
+    sol, model = fos.solve(prob, fos.DR(eps=1e-8, verbose=0), checki=10)   # testfeasibility.jl:15
+    assert sol.status == "Optimal"
+    assert sol.x[:100].min() > -1e-12
+    assert np.abs(A @ sol.x[:100] - b).max() < 1e-6
+    assert "err" in model.history and "t" in model.history

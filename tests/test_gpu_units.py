@@ -1,0 +1,228 @@
+"""GPU parity tests, unit level: every call goes through the C ABI (include/fos_b200.h) and is
+compared with the CPU oracle on the same seeded inputs.  These mirror the reference's unit tests
+(test/HSDEAffine.jl, test/affinepluslinear.jl, test/conjugateGradient.jl, test/testPSD.jl).
+
+Tolerances (FP64): single operator applications 1e-12 relative (different summation order only);
+a whole truncated CG solve 1e-9 (the indefinite KKT recurrence amplifies rounding ~1e4x,
+DESIGN.md "parity budget")."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from helpers import load_affine, load_conic, rel_err
+
+pytestmark = pytest.mark.gpu
+
+OP_TOL = 1e-12
+CG_TOL = 1e-9
+
+
+def _rand_conic(problems, m, n, seed, density=None):
+    h = m // 2
+    return problems.random_feasible_conic(m, n, [("Zero", h), ("NonNeg", m - h)], seed=seed, density=density)
+
+
+# shapes chosen to hit: tiny, ragged edges in both directions, exactly one tile, several bands,
+# more row groups than CTAs
+SHAPES = [(5, 3), (91, 51), (16, 512), (17, 513), (200, 2049), (1000, 300), (333, 4500), (2600, 2100)]
+
+
+@pytest.mark.parametrize("m,n", SHAPES)
+@pytest.mark.parametrize("path", ["tma", "plain", "sparse"])
+def test_a_q_kkt_products(fos, oracle, m, n, path):
+    from fos_b200 import problems
+    P = _rand_conic(problems, m, n, seed=m * 7 + n)
+    O = oracle.OracleConic(P.c, P.A, P.b, P.constr_cones, P.var_cones)
+    if path == "sparse":
+        H = load_conic(fos, P, storage="sparse")
+    else:
+        H = load_conic(fos, P, storage="dense", matvec_impl=0 if path == "tma" else 1)
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal(n)
+    w = rng.standard_normal(m)
+    assert rel_err(H.a_mul(x, m, n), O.a_mul(x)) < OP_TOL
+    assert rel_err(H.a_mul(w, m, n, transpose=True), O.a_mul(w, transpose=True)) < OP_TOL
+    B = rng.standard_normal(m + n + 1)
+    assert rel_err(H.q_mul(B), O.q_mul(B)) < OP_TOL                      # HSDEAffine.jl:41-59
+    assert rel_err(H.q_mul(B, transpose=True), O.q_mul(B, transpose=True)) < OP_TOL  # :61-65
+    v = rng.standard_normal(2 * (m + n + 1))
+    assert rel_err(H.kkt_mul(v), O.kkt_mul(v)) < OP_TOL                  # affinepluslinear.jl:37-49
+
+
+def test_tma_and_plain_paths_agree_bitwise_shape(fos):
+    """Both device paths on a multi-band, multi-CTA shape; the fused kernel must be deterministic."""
+    from fos_b200 import problems
+    P = _rand_conic(problems, 1500, 5000, seed=11)
+    H1 = load_conic(fos, P, storage="dense", matvec_impl=0)
+    H2 = load_conic(fos, P, storage="dense", matvec_impl=1)
+    v = np.random.default_rng(5).standard_normal(2 * (P.m + P.n + 1))
+    y1, y1b, y2 = H1.kkt_mul(v), H1.kkt_mul(v), H2.kkt_mul(v)
+    assert np.array_equal(y1, y1b)          # fixed-order reductions: bitwise reproducible
+    assert rel_err(y1, y2) < OP_TOL
+
+
+def test_dense_load_direct_and_odd_lda(fos, oracle):
+    from fos_b200 import problems
+    P = _rand_conic(problems, 123, 777, seed=5)
+    O = oracle.OracleConic(P.c, P.A, P.b, P.constr_cones, P.var_cones)
+    H = load_conic(fos, P, storage="dense_direct")
+    v = np.random.default_rng(1).standard_normal(2 * (P.m + P.n + 1))
+    assert rel_err(H.kkt_mul(v), O.kkt_mul(v)) < OP_TOL
+
+
+@pytest.mark.parametrize("beta", [1, -1])
+def test_affine_plus_linear_prox_matches_dense_solve(fos, oracle, beta):
+    """test/affinepluslinear.jl:28-68"""
+    rng = np.random.default_rng(10)
+    A = rng.standard_normal((10, 20))
+    x0, z0 = rng.standard_normal(20), rng.standard_normal(10)
+    q, b = rng.standard_normal(20), rng.standard_normal(10)
+    H = load_affine(fos, A, b, q, beta, [("Free", 30)])
+    O = oracle.OracleFeasibility(A, b, q, beta, [("Free", 30)])
+    xin = np.concatenate([x0, z0])
+    y = H.affine_prox(xin)
+    if beta == 1:
+        M = np.block([[np.eye(20), A.T], [A, -np.eye(10)]])
+        y3 = np.linalg.solve(M, np.concatenate([x0 - q + A.T @ z0, b]))
+    else:
+        M = np.block([[np.eye(20), -A.T], [A, np.eye(10)]])
+        y3 = np.linalg.solve(M, np.concatenate([x0 - q - A.T @ z0, b]))
+    np.testing.assert_allclose(y, y3, rtol=1e-9, atol=1e-9)
+    assert rel_err(y, O.affine_prox(xin)) < CG_TOL
+    assert H.info("cgiter") == O.cgiter
+    assert H.info("s1_calls") == O.s1_calls == 2
+    v = rng.standard_normal(30)
+    assert rel_err(H.kkt_mul(v), O.kkt_mul(v)) < OP_TOL
+
+
+@pytest.mark.parametrize("m,n,path", [(60, 90, "dense"), (60, 90, "sparse"), (300, 2100, "dense")])
+def test_hsde_affine_prox_sequence(fos, oracle, m, n, path):
+    """Three consecutive S1 proxes (warm start, decreasing tolerance 0.2^sqrt(i), call counter)."""
+    from fos_b200 import problems
+    P = _rand_conic(problems, m, n, seed=21)
+    O = oracle.OracleConic(P.c, P.A, P.b, P.constr_cones, P.var_cones)
+    H = load_conic(fos, P, storage=path)
+    rng = np.random.default_rng(2)
+    for k in range(3):
+        xin = rng.standard_normal(2 * (m + n + 1))
+        yo = O.affine_prox(xin)
+        # lock-step: same warm start and call counter on both sides
+        if k > 0:
+            H.set_info("s1_calls", O.s1_calls - 1)
+        yg = H.affine_prox(xin)
+        assert H.info("cgiter") == O.cgiter, f"CG iteration count differs at call {k}"
+        assert rel_err(yg, yo) < CG_TOL
+        assert rel_err(H.get_state("rhs"), O.get_state("rhs")) < OP_TOL
+        H.set_state("xinit", O.get_state("xinit"))
+
+
+def test_cg_dense_spd(fos, oracle):
+    """test/conjugateGradient.jl"""
+    rng = np.random.default_rng(2)
+    n = 300
+    A = rng.random((n, n))
+    A = A.T @ A
+    b = rng.standard_normal(n)
+    x0 = rng.standard_normal(n)
+    H = fos.Handle(0)
+    x, it = H.cg_dense(A, b, x0, max_iters=100)
+    xo, ito = oracle.cg_csc(A, b, x0, max_iters=100)
+    assert it == ito == 100
+    x, it = H.cg_dense(A, b, x, max_iters=5000)
+    n1 = np.linalg.norm(A @ x - b)
+    assert n1 < 1e-5
+    xcopy = x + 1e-5 * rng.standard_normal(n)
+    n2 = np.linalg.norm(A @ xcopy - b)
+    xcopy, _ = H.cg_dense(A, b, xcopy, max_iters=100)
+    assert np.linalg.norm(A @ xcopy - b) < 10 * n2
+    # short run, well conditioned: device and oracle agree closely
+    A2 = np.eye(50) + 0.1 * (lambda G: G @ G.T)(rng.standard_normal((50, 50))) / 50
+    b2 = rng.standard_normal(50)
+    xg, itg = H.cg_dense(A2, b2, np.zeros(50), tol=1e-10, max_iters=200)
+    xc, itc = oracle.cg_csc(A2, b2, np.zeros(50), tol=1e-10, max_iters=200)
+    assert itg == itc
+    assert rel_err(xg, xc) < 1e-12
+
+
+# ---------------------------------------------------------------------------------------------
+# cones
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,ln", [("Free", 37), ("Zero", 37), ("NonNeg", 1000), ("NonPos", 33), ("SOC", 1),
+                                     ("SOC", 2), ("SOC", 3), ("SOC", 2050), ("SOC", 10001)])
+@pytest.mark.parametrize("dual", [False, True])
+def test_prox_cone_elementwise_and_soc(fos, oracle, name, ln, dual):
+    H = fos.Handle(0)
+    rng = np.random.default_rng(ln)
+    for scale in (1.0, 10.0, 0.1):
+        x = rng.standard_normal(ln)
+        x[0] *= scale * (3 if name == "SOC" else 1)
+        assert rel_err(H.prox_cone(name, x, dual), oracle.prox_cone(name, x, dual)) < 1e-13
+    if name == "SOC" and ln > 1:
+        for t in (-1e3, 1e3):  # the two trivial branches
+            x = rng.standard_normal(ln)
+            x[0] = t
+            np.testing.assert_array_equal(H.prox_cone(name, x, dual), oracle.prox_cone(name, x, dual))
+
+
+YS = np.array([[-0.0064709, -0.22443], [-0.22443, -1.02411]])          # test/testPSD.jl:3-4
+P_PSD_YS = np.array([[0.03909044662082823, -0.00823811392936668],
+                     [-0.00823811392936668, 0.00173614084718757]])
+
+
+def test_psd_literal_known_answer(fos):
+    from fos_b200 import problems
+    H = fos.Handle(0)
+    P = problems.smat(H.prox_cone("SDP", problems.svec(YS)))
+    np.testing.assert_allclose(P, P_PSD_YS, rtol=1e-10, atol=1e-14)
+    Pd = problems.smat(H.prox_cone("SDP", problems.svec(YS), dual=True))
+    np.testing.assert_allclose(Pd, P_PSD_YS, rtol=1e-10, atol=1e-14)
+
+
+@pytest.mark.parametrize("d", [1, 2, 3, 5, 16, 33, 64, 100, 130])
+@pytest.mark.parametrize("dual", [False, True])
+def test_psd_projection_vs_lapack(fos, d, dual):
+    from oracle import np_oracle as npo
+    H = fos.Handle(0)
+    rng = np.random.default_rng(d)
+    x = rng.standard_normal(d * (d + 1) // 2)
+    ref = npo.prox_cone_dual("SDP", x) if dual else npo.prox_cone("SDP", x)
+    got = H.prox_cone("SDP", x, dual)
+    assert rel_err(got, ref) < 1e-12
+    # degenerate spectrum: eigenvalues +-1 (a case one-sided Jacobi would get wrong)
+    if d >= 2 and not dual:
+        from fos_b200 import problems
+        G, _ = np.linalg.qr(rng.standard_normal((d, d)))
+        lam = np.where(np.arange(d) % 2 == 0, 1.0, -1.0)
+        S = (G * lam) @ G.T
+        got = problems.smat(H.prox_cone("SDP", problems.svec(S)))
+        np.testing.assert_allclose(got, (G * np.maximum(lam, 0)) @ G.T, atol=1e-12)
+
+
+def test_dual_cone_product_prox(fos, oracle):
+    """cones.jl:122-142 on a mixed product: Zero + NonNeg + SOC + SOC + SDP rows, Free + NonNeg vars."""
+    from fos_b200 import problems
+    rng = np.random.default_rng(4)
+    c1 = [("Zero", 7), ("NonNeg", 20), ("SOC", 9), ("SOC", 3), ("SDP", 10), ("NonPos", 4), ("Free", 3)]
+    m = sum(l for _, l in c1)
+    c2 = [("Free", 11), ("NonNeg", 6)]
+    n = sum(l for _, l in c2)
+    A = sp.random(m, n, density=0.3, random_state=rng, data_rvs=rng.standard_normal).tocsc()
+    P = problems.ConicProblem(rng.standard_normal(n), A, rng.standard_normal(m), c1, c2)
+    O = oracle.OracleConic(P.c, P.A, P.b, P.constr_cones, P.var_cones)
+    H = load_conic(fos, P)
+    for _ in range(4):
+        z = rng.standard_normal(2 * (m + n + 1)) * 2
+        assert rel_err(H.cone_prox(z), O.cone_prox(z)) < 1e-12
+
+
+def test_errors_are_loud(fos):
+    from fos_b200 import problems
+    H = fos.Handle(0)
+    with pytest.raises(fos.FosError):
+        H.get_iterate()                      # nothing loaded
+    with pytest.raises(fos.FosError):
+        H.prox_cone("ExpPrimal", np.ones(3))  # outside the hot-path scope -> FOS_ERR_UNSUPPORTED
+    P = problems.nnls_conic(4, 5, 1)
+    P.constr_cones = [("SOC", 5)]            # does not cover 1:m
+    with pytest.raises((fos.FosError, AssertionError)):
+        load_conic(fos, P)
