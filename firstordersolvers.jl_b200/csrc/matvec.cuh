@@ -69,10 +69,13 @@ inline K1Plan k1_make_plan(int64_t m_local, int64_t n, int G_req)
         int64_t kc = (b == P.NB - 1) ? P.kc_last : K1_KC;
         return (int64_t)P.RT * K1_KC * b + rt * kc;
     };
+    // every CTA gets a non-empty, contiguous range (G <= units): the slot of a CTA inside a band is
+    // its distance from the band's first CTA, which needs the owners of a band to be consecutive.
     int64_t u = 0;
     for (int g = 0; g < G; g++) {
         int64_t target = (Wt * g + G - 1) / G;  // ceil
-        while (u < units && pre(u) < target) u++;
+        while (u < units - (G - g) && pre(u) < target) u++;
+        if (g > 0 && u <= P.cta_unit_begin[g - 1]) u = P.cta_unit_begin[g - 1] + 1;
         P.cta_unit_begin[g] = (int32_t)u;
     }
     P.cta_unit_begin[G] = (int32_t)units;

@@ -133,7 +133,10 @@ class _Handle:
         self.ck(self.L.fos_set_option(self.h, key.encode(), float(value)))
 
     def n(self):
-        return int(self.L.fos_iterate_length(self.h))
+        n = int(self.L.fos_iterate_length(self.h))
+        if n < 0:
+            raise _lib.FosError(-1, "no problem loaded on this handle")
+        return n
 
     def set_algorithm(self, alg: FOSAlgorithm):
         code, a, a1, a2, b, ip = alg._params()

@@ -34,11 +34,13 @@ class ConicProblem:
         return self.A.shape[1]
 
 
-def nnls_conic(rows=40, cols=50, seed=1) -> ConicProblem:
+def nnls_conic(rows=40, cols=50, seed=1, scale=1.0) -> ConicProblem:
     """C1 / C5: minimise ||D x - d|| s.t. x >= 0 as  min t  s.t. (t, Dx-d) in SOC, x in NonNeg.
-    ξ = (t, x);  m = rows + 1 + cols,  n = cols + 1  (40x50 -> m = 91, n = 51)."""
+    ξ = (t, x);  m = rows + 1 + cols,  n = cols + 1  (40x50 -> m = 91, n = 51).
+    `scale` multiplies D (scale << 1 gives a KKT matrix with eigenvalues near +-1, on which the
+    reference's CG does not amplify rounding: used by the strict lock-step parity tests)."""
     rng = np.random.default_rng(seed)
-    D = rng.standard_normal((rows, cols))
+    D = rng.standard_normal((rows, cols)) * scale
     d = rng.standard_normal(rows)
     n = cols + 1
     top = sp.hstack([sp.csr_matrix(([-1.0], ([0], [0])), shape=(1, 1)), sp.csr_matrix((1, cols))])
@@ -79,17 +81,17 @@ def _sample_in_cone(rng, cones, dual=False):
     return np.concatenate(parts) if parts else np.zeros(0)
 
 
-def random_feasible_conic(m, n, constr_cones, seed=2, density=None, dense=True) -> ConicProblem:
+def random_feasible_conic(m, n, constr_cones, seed=2, density=None, dense=True, scale=1.0) -> ConicProblem:
     """C2-style: A = randn(m,n)/sqrt(n); primal and dual strictly feasible by construction
     (b = A ξ* + s*, s* in K1;  c = -A' y*, y* in K1*), variables free."""
     rng = np.random.default_rng(seed)
     if density is None:
-        A = rng.standard_normal((m, n)) / np.sqrt(n)
+        A = rng.standard_normal((m, n)) / np.sqrt(n) * scale
         Aop = A
         A_out = A if dense else sp.csc_matrix(A)
     else:
         A_out = sp.random(m, n, density=density, random_state=rng, data_rvs=rng.standard_normal, format="csc")
-        A_out = A_out / np.sqrt(max(density * n, 1.0))
+        A_out = A_out / np.sqrt(max(density * n, 1.0)) * scale
         Aop = A_out
     xi = rng.standard_normal(n)
     s = _sample_in_cone(rng, constr_cones)
@@ -100,16 +102,16 @@ def random_feasible_conic(m, n, constr_cones, seed=2, density=None, dense=True) 
                         f"rand{m}x{n}")
 
 
-def lasso_like(m=200, n=400, seed=2, dense=True) -> ConicProblem:
+def lasso_like(m=200, n=400, seed=2, dense=True, scale=1.0) -> ConicProblem:
     """C2 at test scale: rows split K1 = Zero(m/2) + NonNeg(m - m/2), DR(0.5)."""
     h = m // 2
-    return random_feasible_conic(m, n, [("Zero", h), ("NonNeg", m - h)], seed=seed, dense=dense)
+    return random_feasible_conic(m, n, [("Zero", h), ("NonNeg", m - h)], seed=seed, dense=dense, scale=scale)
 
 
-def soc_constrained_ls(md=300, nx=60, seed=3, rho=None) -> ConicProblem:
+def soc_constrained_ls(md=300, nx=60, seed=3, rho=None, scale=1.0) -> ConicProblem:
     """C3: min t s.t. ||D x - d|| <= t, ||x|| <= rho.  ξ = (t, x); K1 = SOC(md+1) + SOC(nx+1)."""
     rng = np.random.default_rng(seed)
-    D = rng.standard_normal((md, nx)) / np.sqrt(nx)
+    D = rng.standard_normal((md, nx)) / np.sqrt(nx) * scale
     x0 = rng.standard_normal(nx)
     d = D @ x0 + 0.1 * rng.standard_normal(md)
     if rho is None:

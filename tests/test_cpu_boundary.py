@@ -97,7 +97,8 @@ def test_history_container(fos):
 
 
 @pytest.mark.parametrize("m,n,G", [(20000, 40000, 148), (1, 1, 148), (16, 2048, 148), (17, 2049, 7),
-                                   (100000, 20000, 148), (5000, 300, 148), (33, 100000, 148), (12500, 20000, 296)])
+                                   (100000, 20000, 148), (5000, 300, 148), (33, 100000, 148), (12500, 20000, 296),
+                                   (700, 4500, 148), (91, 51, 148), (2600, 2100, 148), (40, 5000, 148), (641, 6200, 148)])
 def test_k1_work_partition(fos, m, n, G):
     """Every row group is owned by exactly one CTA, CTAs are balanced by tile count, and the
     column-partial slots enumerate exactly the (band, CTA) incidences."""
@@ -111,7 +112,7 @@ def test_k1_work_partition(fos, m, n, G):
     assert lib.fos_k1_plan(m, n, G, dims, ub, g + 1, sb, fc, NB + 1) == 0
     ub, sb, fc = list(ub), list(sb), list(fc)
     assert RT == -(-m // 16) and NB == -(-n // 2048)
-    assert ub[0] == 0 and ub[-1] == NB * RT and all(a <= b for a, b in zip(ub, ub[1:]))
+    assert ub[0] == 0 and ub[-1] == NB * RT and all(a < b for a, b in zip(ub, ub[1:])), "empty CTA"
     assert g == min(G, NB * RT)
     # balance by tiles
     def tiles(u0, u1):
@@ -124,7 +125,7 @@ def test_k1_work_partition(fos, m, n, G):
     loads = [tiles(ub[k], ub[k + 1]) for k in range(g)]
     total = sum(loads)
     assert total == RT * 4 * (NB - 1) + RT * kc_last
-    assert max(loads) - min(loads) <= 2 * 4 + 1 or max(loads) <= 1.02 * total / g + 8
+    assert max(loads) <= total / g + 8
     # slots
     count = 0
     for b in range(NB):
