@@ -3,7 +3,7 @@
 "Dense LASSO via HSDE, A 20000x40000 FP64, DR(0.5) with CG affine projection, 1 B200".
 
 A "step" is one outer DR iteration of the hot path (affine projection by CG on the KKT operator
-= k+2 passes over A, cone projection, relaxation).  The timed region is exactly
+= k+1 passes over A with the fused right-hand side, cone projection, relaxation).  The timed region is exactly
 `--steps` consecutive iterations after `--warmup` untimed ones; A (6.4 GB) does not fit L2, so
 every pass streams it from HBM ("inputs larger than L2", no flush needed).
 
@@ -44,47 +44,71 @@ def peaks():
 # clocks sampling during the timed region (B200_PROFILING.md recipe)
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons of one GPU, polled every 20 ms through NVML while the timed
+    region runs (nvidia-smi -lms 200 is too coarse for a ~0.5 s region); nvidia-smi as fallback."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
-        self.proc = None
-        self.lines = []
+        self.samples = []
+        self.reasons = set()
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.smax = None
+        self.how = "nvml"
+
+    def _loop_nvml(self):
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+        try:
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.smax = None
+        while not self.stop_flag.is_set():
+            try:
+                self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def _loop_smi(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.gpu)], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                self.samples.append(float(f[0]))
+                self.smax = float(f[1])
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                     f[2:6]):
+                    if val.lower().startswith("active"):
+                        self.reasons.add(name)
+            except Exception:
+                pass
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.gpu), "-lms", "200"], stdout=subprocess.PIPE, text=True)
-            threading.Thread(target=self._pump, daemon=True).start()
+            import pynvml  # noqa: F401
+            target = self._loop_nvml
         except Exception:
-            self.proc = None
-
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            target, self.how = self._loop_smi, "nvidia-smi"
+        self.thread = threading.Thread(target=target, daemon=True)
+        self.thread.start()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
-        self.proc.terminate()
-        sm, smax, reasons = [], [], set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                smax.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self.stop_flag.set()
+        if self.thread is not None:
+            self.thread.join(timeout=6)
+        sm = self.samples
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.smax,
+                "reasons": sorted(self.reasons), "samples": len(sm), "how": self.how}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -152,7 +176,7 @@ def cpu_reference_rate(m_full, n_full, steps, warmup, seed=2, sample_div=10):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--m", type=int, default=20000)
@@ -265,24 +289,37 @@ def main():
     assert done == K, f"solver stopped after {done} of {K} timed iterations (status {st}); lower --steps"
     launches = H.info("launches") - launches0
     cg_iters = H.info("total_cg") - cg0
-    passes = H.info("total_passes") - passes0
+    passes = H.info("total_passes") - passes0   # executed passes over A (predicated no-op launches excluded)
     mv2_ms, mv2_n = H.info("mv2_ms"), H.info("mv2_n")
     mv1_ms, mv1_n = H.info("mv1_ms"), H.info("mv1_n")
     bytes_pass = H.info("bytes_per_pass")
     H.set_option("profile_matvec", 0)
     value = K / (ms_total / 1e3)
 
-    # ---- e2e: the same iterations through the C ABI with HOST buffers ------------------------------
-    # every step: iterate in from host memory (H2D), one iteration, iterate + residual record out (D2H)
-    z = H.get_iterate()
+    # ---- e2e: the SAME iterations W+1..W+K through the C ABI with HOST buffers ---------------------
+    # A second handle on the same device matrix replays the solve; every step moves the iterate in
+    # from host memory (H2D), runs one iteration with a residual check and reads the iterate and the
+    # p/d/g record back (D2H), all inside the timed region.
+    H2 = fos.Handle(local_rank)
+    H2.set_option("matvec_impl", args.matvec_impl)
+    if world > 1:
+        cid2 = parallel.exchange_comm_id(rank, parallel.nccl_unique_id, dist)
+        parallel.init_comm(H2, rank, world, cid2)
+    H2.ck(H2.L.fos_load_conic_dense(H2.h, m, n, C.c_void_p(A_loc.data_ptr()), n, 1, r0, cnt, _d(b), _d(c), len(t1),
+                                    _i32p(t1), _i64p(l1), len(t2), _i32p(t2), _i64p(l2)))
+    H2.set_algorithm(fos.DR(0.5))
+    H2.set_initial_iterate()
+    H2.ck(H2.L.fos_begin_solve(H2.h))
+    if W > 0:
+        H2.run(1, W, 100, 1e-5)
+    z = H2.get_iterate()
     N = z.size
     barrier()
     t0 = time.perf_counter()
-    i_next = W + K + 1
     for k in range(K):
-        H.set_iterate(z)
-        H.run(i_next + k, 1, 1, 1e-5)      # checki = 1: the p/d/g record of this step comes back too
-        z = H.get_iterate()
+        H2.set_iterate(z)
+        H2.run(W + 1 + k, 1, 1, 1e-5)      # checki = 1: the p/d/g record of this step comes back too
+        z = H2.get_iterate()
     barrier()
     e2e_s = time.perf_counter() - t0
     if world > 1:
@@ -291,8 +328,9 @@ def main():
         e2e_s = float(tt.item())
     e2e = {"value": K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(N * 8),
            "d2h_bytes_per_step": int(N * 8 + 10 * 8),
-           "note": "fos_set_iterate + fos_run(1 iteration, checki=1) + fos_get_iterate per step; these later "
-                   "iterations run more CG iterations per step than the timed ones (tolerance schedule)"}
+           "note": "per step: fos_set_iterate (host->device) + fos_run(1 iteration, checki=1: one extra pass over A "
+                   "for the residual check) + fos_get_iterate (device->host); same iterations as the timed region"}
+    del H2
 
     if rank != 0:
         if world > 1:
@@ -318,7 +356,7 @@ def main():
                 "whole_iteration_frac": bytes_pass * passes / (ms_total / 1e3) / 1e9 / peak}
     cb = None
     if not args.no_cpu_baseline and world == 1:
-        cb = cpu_reference_rate(m, n, min(K, 20), W, args.seed)
+        cb = cpu_reference_rate(m, n, min(K, 40), W, args.seed)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": config, "roofline": roofline, "cpu_baseline": cb,

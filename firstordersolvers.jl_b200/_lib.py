@@ -54,6 +54,7 @@ SIGNATURES = {
     "fos_q_mul": (C.c_int32, [_h, _dp, _dp, C.c_int32]),
     "fos_kkt_mul": (C.c_int32, [_h, _dp, _dp]),
     "fos_affine_prox": (C.c_int32, [_h, _dp, _dp]),
+    "fos_hsdematrix_prox": (C.c_int32, [_h, _dp, _dp]),
     "fos_cone_prox": (C.c_int32, [_h, _dp, _dp]),
     "fos_cg_dense": (C.c_int32, [_h, C.c_int64, _dp, _dp, _dp, C.c_double, C.c_int64, _i64p]),
     "fos_prox_cone": (C.c_int32, [_h, C.c_int32, C.c_int32, _dp, _dp, C.c_int64]),

@@ -92,6 +92,8 @@ int32_t fos_set_option(fos_handle_t hh, const char *key, double value)
         h.grid_ctas = (int)value;
     } else if (k == "cg_batch") {
         h.cg_batch = (int)value;
+    } else if (k == "fuse_rhs") {
+        h.fuse_rhs = value != 0;
     } else if (k == "profile_matvec") {
         h.A.profile = value != 0;
         h.A.prof_reset();
@@ -485,6 +487,32 @@ int32_t fos_affine_prox(fos_handle_t hh, const double *x, double *y)
     h.s1_prox(h.w1.p);
     h.sol_scaled_to(h.w2.p);
     h.unpack_to_host(h.w2.p, y);
+    FOS_API_END(hh)
+}
+
+int32_t fos_hsdematrix_prox(fos_handle_t hh, const double *x, double *y)
+{
+    FOS_API_BEGIN(hh)
+    Handle &h = hh->h;
+    h.require_loaded();
+    FOS_REQUIRE(h.L.form == 0 && x && y, "fos_hsdematrix_prox needs the conic form");
+    const size_t bytes = (size_t)h.L.NP * 8;
+    // borrow S1's CG buffers; keep its warm start, rhs and counters intact
+    FOS_CUDA(cudaMemcpyAsync(h.w3.p, h.sol.p, bytes, cudaMemcpyDeviceToDevice, h.stream));
+    const int64_t keep_cgiter = h.cgiter;
+    const int64_t keep_total = h.stats.total_cg;
+    h.pack_from_host(x, h.rhs.p);                                                              // rhs = x
+    FOS_CUDA(cudaMemcpyAsync(h.sol.p, h.rhs.p, bytes, cudaMemcpyDeviceToDevice, h.stream));   // :109-114 first run
+    h.cgiter = 1;
+    h.cg_solve((double)h.N * 2.220446049250313e-16, 1000);                                     // :106, :116
+    FOS_CUDA(cudaMemcpyAsync(h.w2.p, h.sol.p, bytes, cudaMemcpyDeviceToDevice, h.stream));
+    h.q_mul(h.sol.p, h.w2.p + h.L.LP, false);                                                  // :120-124  v = Q u
+    h.unpack_to_host(h.w2.p, y);
+    FOS_CUDA(cudaMemcpyAsync(h.sol.p, h.w3.p, bytes, cudaMemcpyDeviceToDevice, h.stream));
+    FOS_CUDA(cudaMemsetAsync(h.rhs.p, 0, bytes, h.stream));  // HSDE: rhs2 = b = 0 (HSDE.jl:22); rhs1 is rebuilt per prox
+    FOS_CUDA(cudaStreamSynchronize(h.stream));
+    h.cgiter = keep_cgiter;
+    h.stats.total_cg = keep_total;
     FOS_API_END(hh)
 }
 

@@ -265,6 +265,29 @@ k2_rhs_plain(Lay L, MVView V, const double *__restrict__ xin, const double *__re
         rhs[e] = sub_(add_(mul_(beta, mv_atw(V, 0, e)), xin[e]), qv[e]);
 }
 
+// Fused right-hand side (option "fuse_rhs"): by linearity the initial CG residual
+//     r0 = rhs - KKT*x0,   rhs = [beta*Op'x2 + x1 - q ; b]      (affinepluslinear.jl:94-95, cg :32-33)
+// equals   rhs' - KKT*d   with  d = [x0_1 ; x0_2 - beta*x2]  and  rhs' = [x1 - q ; b + beta*x2],
+// which needs ONE pass over A instead of two (the rhs pass disappears).  HSDE: q = b = 0, beta = 1,
+// so rhs' is the input vector itself.  d is written to `dvec`; for the plain operator rhs' to `rhsp`.
+static __global__ void __launch_bounds__(VBLOCK)
+k_fuse_prep(Lay L, const double *__restrict__ x0, const double *__restrict__ xin, double beta,
+            const double *__restrict__ qv, const double *__restrict__ bhat, double *__restrict__ dvec,
+            double *__restrict__ rhsp)
+{
+    const int64_t p2 = L.form == 0 ? L.LP : L.n_pad;
+    for (int64_t e = (int64_t)blockIdx.x * VBLOCK + threadIdx.x; e < L.NP; e += (int64_t)gridDim.x * VBLOCK) {
+        if (e < p2) {
+            dvec[e] = x0[e];
+            if (L.form == 1) rhsp[e] = sub_(xin[e], qv[e]);
+        } else {
+            const double bx2 = mul_(beta, xin[e]);
+            dvec[e] = sub_(x0[e], bx2);
+            if (L.form == 1) rhsp[e] = add_(bhat[e - p2], bx2);
+        }
+    }
+}
+
 // =======================================================================================
 // K3: CG updates (conjugategradients.jl:40-51)
 // =======================================================================================

@@ -274,7 +274,7 @@ MVView MatOp::run_t(const double *const *X, const double *const *W, const int32_
         if (stats) stats->launches += 2;
         V = view_full(NV, full_ax.p, full_atw.p);
     }
-    if (stats) stats->total_passes++;
+    if (stats && skip == nullptr) stats->total_passes++;  // predicated CG launches are counted by cg_solve
     if (nranks > 1) {
         // fold the local partials into the exchange buffer, all-reduce over NVLink, hand out
         // a complete view.  Rows owned by other ranks are zero in the local contribution.

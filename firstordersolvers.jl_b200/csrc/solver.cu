@@ -340,6 +340,7 @@ void Handle::load_affine(int64_t am, int64_t an, const double *b, const double *
     std::vector<double> hb((size_t)L.m_pad, 0.0);
     for (int64_t i = 0; i < am; i++) hb[(size_t)i] = b ? b[i] : 0.0;
     FOS_CUDA(cudaMemcpy(rhs.p + L.n_pad, hb.data(), (size_t)L.m_pad * 8, cudaMemcpyHostToDevice));
+    d_bhat.upload(hb);
 }
 
 // =======================================================================================
@@ -398,19 +399,21 @@ void Handle::cg_enqueue_iteration()
 // conjugategradient!(sol, KKT, rhs, r, p, Ap; tol, max_iters) (conjugategradients.jl:31-55).
 // Iterations are enqueued in batches; every kernel of a batch returns at once when the
 // device-side stop test has fired, so the host synchronises once per batch, not per iteration.
-void Handle::cg_solve(double tol, int max_iters)
+void Handle::cg_solve(double tol, int max_iters, const double *x0, const double *rhs_)
 {
+    // r = rhs_ - KKT*x0 ; p = r ; rn = r.r   (x0/rhs_ default to sol/rhs; the fused path passes d/rhs')
+    if (!x0) x0 = sol.p;
+    if (!rhs_) rhs_ = rhs.p;
     FOS_LAUNCH(this, k_cg_begin, 1, 1, 0, d_ctrl.p, tol, max_iters);
-    MVView V = kkt_pass(sol.p, nullptr);
+    MVView V = kkt_pass(x0, nullptr);
     if (L.form == 0)
-        FOS_LAUNCH(this, k2_kkt_hsde<K2_RESID>, vgrid(L.LP), VBLOCK, 0, L, V, sol.p, d_c.p, d_b.p, nullptr, rhs.p,
-                   r.p, p.p, d_ctrl.p, rb, 0);
+        FOS_LAUNCH(this, k2_kkt_hsde<K2_RESID>, vgrid(L.LP), VBLOCK, 0, L, V, x0, d_c.p, d_b.p, nullptr, rhs_, r.p,
+                   p.p, d_ctrl.p, rb, 0);
     else if (L.form == 1)
-        FOS_LAUNCH(this, k2_kkt_plain<K2_RESID>, vgrid(L.NP), VBLOCK, 0, L, V, sol.p, nullptr, rhs.p, r.p, p.p,
-                   d_ctrl.p, rb, 0);
+        FOS_LAUNCH(this, k2_kkt_plain<K2_RESID>, vgrid(L.NP), VBLOCK, 0, L, V, x0, nullptr, rhs_, r.p, p.p, d_ctrl.p,
+                   rb, 0);
     else
-        FOS_LAUNCH(this, k2_spd<K2_RESID>, vgrid(L.NP), VBLOCK, 0, L, V, sol.p, nullptr, rhs.p, r.p, p.p, d_ctrl.p, rb,
-                   0);
+        FOS_LAUNCH(this, k2_spd<K2_RESID>, vgrid(L.NP), VBLOCK, 0, L, V, x0, nullptr, rhs_, r.p, p.p, d_ctrl.p, rb, 0);
     int64_t enq = 0;
     int batch = cg_batch > 0 ? cg_batch : (int)std::max<int64_t>(1, cgiter);  // adaptive: last solve's count
     for (;;) {
@@ -425,12 +428,30 @@ void Handle::cg_solve(double tol, int max_iters)
     }
     cgiter = h_ctrl->iter;
     stats.total_cg += cgiter;
+    stats.total_passes += cgiter;  // one pass over A per executed CG iteration
     if (h_ctrl->warn_maxit) warn_maxit = true;
 }
 
 // prox!(y, S::AffinePlusLinear, x) (affinepluslinear.jl:83-126).  Result: sol (= xinit).
 void Handle::s1_prox(const double *xin)
 {
+    const double an_ = (double)(L.form == 0 ? (L.n + L.m + 1) : L.n);
+    if (fuse_rhs) {
+        // one pass fewer per projection: see k_fuse_prep.  Same mathematics, different association of
+        // the sums than affinepluslinear.jl:94-95 + conjugategradients.jl:32-33 (set "fuse_rhs" = 0 to
+        // build rhs exactly in the reference's order).
+        if (firstrun) {  // :101-104
+            FOS_CUDA(cudaMemcpyAsync(sol.p, xin, (size_t)L.NP * 8, cudaMemcpyDeviceToDevice, stream));
+            firstrun = false;
+        }
+        FOS_LAUNCH(this, k_fuse_prep, vgrid(L.NP), VBLOCK, 0, L, sol.p, xin, beta, d_q.p, d_bhat.p, Ap.p, rhs.p);
+        const double floor2 = an_ * 2.220446049250313e-16;
+        double tol2 = floor2;
+        if (decreasing) tol2 = std::max(std::pow(0.2, std::sqrt((double)s1_calls)), floor2);  // :108-112
+        s1_calls += 1;                                                                        // :114
+        cg_solve(tol2, 1000, Ap.p, L.form == 0 ? xin : rhs.p);
+        return;
+    }
     if (L.form == 0) {
         const double *X[1] = {xin + L.LP};
         const double *W[1] = {xin + L.LP + L.n_pad};
@@ -441,6 +462,7 @@ void Handle::s1_prox(const double *xin)
         const double *W[1] = {xin + L.n_pad};
         MVView V = A.run(1, X, W, nullptr, stream);
         FOS_LAUNCH(this, k2_rhs_plain, vgrid(L.n), VBLOCK, 0, L, V, xin, d_q.p, beta, rhs.p);
+        FOS_CUDA(cudaMemcpyAsync(rhs.p + L.n_pad, d_bhat.p, (size_t)L.m_pad * 8, cudaMemcpyDeviceToDevice, stream));
     }
     if (firstrun) {  // :101-104
         FOS_CUDA(cudaMemcpyAsync(sol.p, xin, (size_t)L.NP * 8, cudaMemcpyDeviceToDevice, stream));

@@ -165,14 +165,14 @@ struct Handle {
     int num_sms = 148;
     std::string err;
     // options
-    int matvec_impl = 0, grid_ctas = 0, cg_batch = 0;
+    int matvec_impl = 0, grid_ctas = 0, cg_batch = 0, fuse_rhs = 1;
     // problem
     bool loaded = false;
     Lay L{};
     SegMap seg{};
     int64_t N = 0;
     MatOp A;
-    DevBuf<double> d_b, d_c, d_q;  // HSDE: b (m_pad), c (n_pad).  plain: q (n_pad)
+    DevBuf<double> d_b, d_c, d_q, d_bhat;  // HSDE: b (m_pad), c (n_pad).  plain: q (n_pad), b (m_pad)
     double nb = 0, ncn = 0;
     double beta = 1.0;
     bool decreasing = true;
@@ -228,7 +228,7 @@ struct Handle {
     void kkt_mul(const double *in, double *out);
     void q_mul(const double *Bp, double *Yp, bool transpose);
     void s1_prox(const double *xin);
-    void cg_solve(double tol, int max_iters);
+    void cg_solve(double tol, int max_iters, const double *x0 = nullptr, const double *rhs_ = nullptr);
     void cg_enqueue_iteration();
     void sol_scaled_to(double *dst);
     void cone_project(ConeSet &K, const double *in, double *projbuf, int epi, const EpiArgs &E);

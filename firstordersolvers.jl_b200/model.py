@@ -220,6 +220,9 @@ class _Handle:
     def affine_prox(self, x):
         return self._vec_call(self.L.fos_affine_prox, x)
 
+    def hsdematrix_prox(self, x):
+        return self._vec_call(self.L.fos_hsdematrix_prox, x)
+
     def cone_prox(self, x):
         return self._vec_call(self.L.fos_cone_prox, x)
 

@@ -96,6 +96,9 @@ const char *fos_last_error(fos_handle_t h);
  *   "matvec_impl"  0 = TMA-staged fused kernel (default), 1 = plain two-kernel reference path
  *   "grid_ctas"    number of persistent CTAs of the fused kernel (default = #SMs)
  *   "cg_batch"     CG iterations enqueued per host synchronisation (default adaptive = 0)
+ *   "fuse_rhs"     1 (default) = fold the right-hand-side product of the affine projection into the
+ *                  initial CG residual (k+1 passes over A per projection instead of k+2; same
+ *                  mathematics, sums associated differently); 0 = build rhs in the reference's order
  *   "profile_matvec" 1 = CUDA events around every mat-vec launch (read back with fos_get_info)
  *   "use_graphs"   reserved                                                                */
 int32_t fos_set_option(fos_handle_t h, const char *key, double value);
@@ -205,6 +208,10 @@ int32_t fos_kkt_mul(fos_handle_t h, const double *x, double *y);
 /* y = prox of S1 at x (affinepluslinear.jl:83-126), including every side effect (S1.i,
  * warm start, cgiter). */
 int32_t fos_affine_prox(fos_handle_t h, const double *x, double *y);
+/* y = HSDEMatrix.prox!(x) (problemforms/HSDE/HSDEAffine.jl:105-126): CG on [I Q'; Q -I] y = x with
+ * the fixed tolerance 2l*eps, then v <- Q u.  Tested by the reference (test/HSDEAffine.jl:71-81)
+ * but not used by its solver path; runs on a fresh CG state and leaves S1 untouched. */
+int32_t fos_hsdematrix_prox(fos_handle_t h, const double *x, double *y);
 /* y = prox of S2 at x (DualConeProduct cones.jl:122-142 / ConeProduct cones.jl:89-94). */
 int32_t fos_cone_prox(fos_handle_t h, const double *x, double *y);
 /* conjugategradient!(x, A, b, r, p, Ap; tol, max_iters) (conjugategradients.jl:31-55) on a

@@ -80,6 +80,9 @@ def test_affine_plus_linear_prox_matches_dense_solve(fos, oracle, beta):
     H = load_affine(fos, A, b, q, beta, [("Free", 30)])
     O = oracle.OracleFeasibility(A, b, q, beta, [("Free", 30)])
     xin = np.concatenate([x0, z0])
+    H0 = load_affine(fos, A, b, q, beta, [("Free", 30)], fuse_rhs=0)   # reference-order rhs
+    assert rel_err(H0.affine_prox(xin), H.affine_prox(xin)) < CG_TOL
+    H = load_affine(fos, A, b, q, beta, [("Free", 30)])
     y = H.affine_prox(xin)
     if beta == 1:
         M = np.block([[np.eye(20), A.T], [A, -np.eye(10)]])
@@ -102,20 +105,56 @@ def test_hsde_affine_prox_sequence(fos, oracle, m, n, path):
     from fos_b200 import problems
     h = m // 2
     P = problems.random_feasible_conic(m, n, [("Zero", h), ("NonNeg", m - h)], seed=21, scale=0.1)
+    for fuse in (0, 1):
+        O = oracle.OracleConic(P.c, P.A, P.b, P.constr_cones, P.var_cones)
+        H = load_conic(fos, P, storage=path, fuse_rhs=fuse)
+        rng = np.random.default_rng(2)
+        for k in range(3):
+            xin = rng.standard_normal(2 * (m + n + 1))
+            yo = O.affine_prox(xin)
+            # lock-step: same warm start and call counter on both sides
+            if k > 0:
+                H.set_info("s1_calls", O.s1_calls - 1)
+            yg = H.affine_prox(xin)
+            assert H.info("cgiter") == O.cgiter, f"CG iteration count differs at call {k}"
+            assert rel_err(yg, yo) < CG_TOL
+            if not fuse:  # the reference-order path materialises rhs (affinepluslinear.jl:94-95)
+                assert rel_err(H.get_state("rhs"), O.get_state("rhs")) < OP_TOL
+            H.set_state("xinit", O.get_state("xinit"))
+        # fused: k+1 passes per projection, reference order: k+2
+        assert H.info("total_passes") == H.info("total_cg") + (3 if fuse else 6)
+
+
+def test_hsdematrix_prox_matches_dense_solve(fos, oracle):
+    """test/HSDEAffine.jl:71-81: HSDEMatrix.prox! == dense M\\b with v <- Q u == projection onto {Qu = v}."""
+    from fos_b200 import problems
+    m, n = 40, 70
+    P = problems.random_feasible_conic(m, n, [("Free", m)], seed=1)
+    A = np.asarray(P.A)
+    l = m + n + 1
+    Q = np.zeros((l, l))
+    Q[:n, n:n + m] = A.T
+    Q[:n, -1] = P.c
+    Q[n:n + m, :n] = -A
+    Q[n:n + m, -1] = P.b
+    Q[-1, :n] = -P.c
+    Q[-1, n:n + m] = -P.b
+    M1 = np.block([[np.eye(l), Q.T], [Q, -np.eye(l)]])
+    H = load_conic(fos, P)
     O = oracle.OracleConic(P.c, P.A, P.b, P.constr_cones, P.var_cones)
-    H = load_conic(fos, P, storage=path)
-    rng = np.random.default_rng(2)
-    for k in range(3):
-        xin = rng.standard_normal(2 * (m + n + 1))
-        yo = O.affine_prox(xin)
-        # lock-step: same warm start and call counter on both sides
-        if k > 0:
-            H.set_info("s1_calls", O.s1_calls - 1)
-        yg = H.affine_prox(xin)
-        assert H.info("cgiter") == O.cgiter, f"CG iteration count differs at call {k}"
-        assert rel_err(yg, yo) < CG_TOL
-        assert rel_err(H.get_state("rhs"), O.get_state("rhs")) < OP_TOL
-        H.set_state("xinit", O.get_state("xinit"))
+    bb = np.random.default_rng(3).standard_normal(2 * l)
+    y = H.hsdematrix_prox(bb)
+    y3 = np.linalg.solve(M1, bb)
+    y3[l:] = Q @ y3[:l]
+    np.testing.assert_allclose(y, y3, rtol=1e-8, atol=1e-8)
+    B = np.hstack([Q, -np.eye(l)])
+    y1 = bb - B.T @ np.linalg.solve(B @ B.T, B @ bb)          # IndAffine([Q -I], 0)
+    np.testing.assert_allclose(y, y1, rtol=1e-8, atol=1e-8)
+    np.testing.assert_allclose(y, O.hsdematrix_prox(bb), rtol=1e-8, atol=1e-8)
+    # S1's own state is untouched
+    assert H.info("s1_calls") == 1 and H.info("cgiter") == 0
+    v = np.random.default_rng(4).standard_normal(2 * l)
+    assert rel_err(H.affine_prox(v), O.affine_prox(v)) < 1e-6
 
 
 def test_cg_dense_spd(fos, oracle):
