@@ -721,19 +721,25 @@ k_unpack(SegMap M, const double *__restrict__ padded, double *__restrict__ logic
     }
 }
 
-// multi-GPU: fold the local partials into the exchange buffer [NV][n_pad] | [NV][m_pad]
+// multi-GPU: fold the local partials into the exchange buffer [NV][n_pad] | [NV][m_pad].  Rows owned
+// by other ranks (and all padding) are written as zeros on every pass: the all-reduce is in place, so
+// the buffer still holds the previous pass's global sums.
 template <int NV>
 __global__ void __launch_bounds__(VBLOCK)
 k1_finalize_local(MVView V, int64_t n, int64_t n_pad, int64_t m_local, int64_t row_begin, int64_t m_pad,
                   double *__restrict__ xbuf, const int32_t *skip_flag)
 {
     if (skip_flag != nullptr && *skip_flag != 0) return;
-    const int64_t total = n + m_local;
+    const int64_t total = n_pad + m_pad;
     for (int64_t e = (int64_t)blockIdx.x * VBLOCK + threadIdx.x; e < total; e += (int64_t)gridDim.x * VBLOCK) {
 #pragma unroll
         for (int v = 0; v < NV; v++) {
-            if (e < n) xbuf[(size_t)v * n_pad + e] = mv_atw(V, v, e);
-            else xbuf[(size_t)NV * n_pad + (size_t)v * m_pad + row_begin + (e - n)] = mv_ax(V, v, e - n);
+            if (e < n_pad) {
+                xbuf[(size_t)v * n_pad + e] = e < n ? mv_atw(V, v, e) : 0.0;
+            } else {
+                const int64_t row = e - n_pad, lr = row - row_begin;
+                xbuf[(size_t)NV * n_pad + (size_t)v * m_pad + row] = (lr >= 0 && lr < m_local) ? mv_ax(V, v, lr) : 0.0;
+            }
         }
     }
 }

@@ -278,7 +278,7 @@ MVView MatOp::run_t(const double *const *X, const double *const *W, const int32_
     if (nranks > 1) {
         // fold the local partials into the exchange buffer, all-reduce over NVLink, hand out
         // a complete view.  Rows owned by other ranks are zero in the local contribution.
-        const int64_t total = n + m_local;
+        const int64_t total = n_pad + m_pad;
         int grid = (int)std::min<int64_t>((total + VBLOCK - 1) / VBLOCK, 4 * (int64_t)num_sms);
         k1_finalize_local<NV><<<grid, VBLOCK, 0, st>>>(V, n, n_pad, m_local, row_begin, m_pad, xbuf.p, skip);
         if (stats) stats->launches++;

@@ -44,7 +44,12 @@ def exchange_comm_id(rank: int, make_id, dist=None):
     buf = torch.zeros(_lib.FOS_COMM_ID_BYTES, dtype=torch.uint8)
     if rank == 0:
         buf.copy_(torch.from_numpy(np.frombuffer(make_id(), dtype=np.uint8).copy()))
-    dist.broadcast(buf, src=0)
+    if dist.get_backend() == "nccl":  # NCCL process groups only move device tensors
+        dbuf = buf.cuda()
+        dist.broadcast(dbuf, src=0)
+        buf = dbuf.cpu()
+    else:
+        dist.broadcast(buf, src=0)
     return bytes(buf.numpy().tobytes())
 
 
