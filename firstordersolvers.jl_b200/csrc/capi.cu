@@ -647,4 +647,45 @@ int32_t fos_time_matvec(fos_handle_t hh, int32_t nvec, int32_t reps, double *ms_
     FOS_API_END(hh)
 }
 
+int32_t fos_time_psd(fos_handle_t hh, int64_t d, int64_t ncones, const double *x, double *y, int32_t reps,
+                     double *ms_per_call, int32_t *sweeps)
+{
+    FOS_API_BEGIN(hh)
+    Handle &h = hh->h;
+    FOS_REQUIRE(d >= 1 && d <= 1024 && ncones >= 1 && ncones <= 4096 && reps >= 1 && x, "bad arguments");
+    const int64_t plen = d * (d + 1) / 2, seglen = ru(plen, PAD);
+    const int64_t NP = seglen * ncones;
+    ConeSet K;
+    std::vector<ConeSeg> segs;
+    for (int64_t k = 0; k < ncones; k++) segs.push_back(ConeSeg{FOS_CONE_SDP, 0, k * seglen, plen});
+    K.build(NP, segs);
+    DevBuf<double> din, dout;
+    din.alloc((size_t)NP);
+    dout.alloc((size_t)NP);
+    FOS_CUDA(cudaMemcpy2D(din.p, (size_t)seglen * 8, x, (size_t)plen * 8, (size_t)plen * 8, (size_t)ncones,
+                          cudaMemcpyHostToDevice));
+    auto project = [&]() {
+        if (!K.psd.empty()) psd_project(&h, K, din.p, dout.p);
+        if (!K.psd_large.empty()) psd_project_large(&h, K, din.p, dout.p);
+    };
+    cudaEvent_t e0, e1;
+    FOS_CUDA(cudaEventCreate(&e0));
+    FOS_CUDA(cudaEventCreate(&e1));
+    project();  // warm-up
+    FOS_CUDA(cudaEventRecord(e0, h.stream));
+    for (int r = 0; r < reps; r++) project();
+    FOS_CUDA(cudaEventRecord(e1, h.stream));
+    FOS_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    FOS_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (ms_per_call) *ms_per_call = (double)ms / reps;
+    if (sweeps) *sweeps = K.psd_large.empty() ? 0 : psd_large_last_sweeps(&h, K);
+    if (y)
+        FOS_CUDA(cudaMemcpy2D(y, (size_t)plen * 8, dout.p, (size_t)seglen * 8, (size_t)plen * 8, (size_t)ncones,
+                              cudaMemcpyDeviceToHost));
+    FOS_API_END(hh)
+}
+
 }  // extern "C"

@@ -7,8 +7,8 @@
 //
 // Eigendecomposition = parallel two-sided (symmetric) Jacobi with round-robin pair ordering:
 // each of the D-1 steps of a sweep applies D/2 disjoint plane rotations at once
-// (S <- J' S J, V <- V J).  One CTA per cone; S and V live in shared memory when
-// 2*d*d*8 bytes fit (d <= 112), otherwise in a global workspace (L2 resident).
+// (S <- J' S J, V <- V J).  One CTA per cone; S and V live in shared memory (2*d*d*8 bytes, d <= 112).
+// Larger cones take the cooperative multi-CTA path of psd_large.cu.
 #include <algorithm>
 
 #include "solver.cuh"
@@ -16,7 +16,6 @@
 namespace fos {
 
 constexpr int PSD_THREADS = 512;
-constexpr int PSD_SMEM_MAX_D = 112;
 constexpr int PSD_MAX_SWEEPS = 40;
 
 __device__ __forceinline__ void rr_pair(int s, int k, int D, int &a, int &b)
@@ -174,16 +173,8 @@ void psd_project(Handle *h, ConeSet &K, const double *in, double *projbuf)
     const int d = K.psd_max_d;
     const int D = (d + 1) & ~1;
     const size_t need = ((size_t)2 * d * d + (size_t)D) * sizeof(double);
-    const int use_smem = d <= PSD_SMEM_MAX_D ? 1 : 0;
-    int64_t stride = 0;
-    if (!use_smem) {
-        stride = (int64_t)2 * d * d + D;
-        if (K.psd_work.n < (size_t)stride * nc) K.psd_work.alloc((size_t)stride * nc);
-    }
-    if (use_smem)
-        FOS_CUDA(cudaFuncSetAttribute(k5_psd_jacobi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
-    FOS_LAUNCH(h, k5_psd_jacobi, nc, PSD_THREADS, use_smem ? need : 0, K.d_psd.p, in, projbuf, K.psd_work.p, stride,
-               use_smem);
+    FOS_CUDA(cudaFuncSetAttribute(k5_psd_jacobi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+    FOS_LAUNCH(h, k5_psd_jacobi, nc, PSD_THREADS, need, K.d_psd.p, in, projbuf, (double *)nullptr, (int64_t)0, 1);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) throw Error(FOS_ERR_CUDA, std::string("PSD projection launch failed: ") + cudaGetErrorString(e));
 }

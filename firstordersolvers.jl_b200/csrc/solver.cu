@@ -114,6 +114,7 @@ void ConeSet::build(int64_t NP_, const std::vector<ConeSeg> &segs)
     std::vector<SocCone> h_soc;
     std::vector<int32_t> h_chunk_cone;
     psd.clear();
+    psd_large.clear();
     psd_max_d = 0;
     for (const ConeSeg &s : segs) {
         FOS_REQUIRE(s.off >= 0 && s.off + s.len <= NP && s.len >= 0, "cone segment out of range");
@@ -151,8 +152,13 @@ void ConeSet::build(int64_t NP_, const std::vector<ConeSeg> &segs)
             pc.off = s.off;
             pc.d = (int32_t)d;
             pc.dual = s.dual;
-            psd.push_back(pc);
-            psd_max_d = std::max<int>(psd_max_d, (int)d);
+            if (d <= PSD_SMEM_MAX_D) {
+                psd.push_back(pc);
+                psd_max_d = std::max<int>(psd_max_d, (int)d);
+            } else {
+                FOS_REQUIRE(d <= 1024, "SDP cones larger than 1024 x 1024 are not supported");
+                psd_large.push_back(pc);
+            }
             for (int64_t k = 0; k < s.len; k++) h_ops[(size_t)(s.off + k)] = OP_PRE;
             continue;
         }
@@ -174,6 +180,7 @@ void ConeSet::build(int64_t NP_, const std::vector<ConeSeg> &segs)
     }
     counter.alloc(1);
     if (!psd.empty()) d_psd.upload(psd);
+    if (!psd_large.empty()) d_psd_large.upload(psd_large);
 }
 
 void Handle::cone_project(ConeSet &K, const double *in, double *projbuf, int epi, const EpiArgs &E)
@@ -182,6 +189,7 @@ void Handle::cone_project(ConeSet &K, const double *in, double *projbuf, int epi
         FOS_LAUNCH(this, k4_soc_norms, K.nchunks, VBLOCK, 0, in, K.soc.p, K.nsoc, K.chunk_cone.p, K.chunk_sum.p,
                    K.soc_scale.p, K.counter.p);
     if (!K.psd.empty()) psd_project(this, K, in, projbuf);
+    if (!K.psd_large.empty()) psd_project_large(this, K, in, projbuf);
     const int g = vgrid(K.NP);
 #define CONE_CASE(EPI)                                                                                            \
     case EPI:                                                                                                     \

@@ -152,9 +152,11 @@ struct ConeSet {
     DevBuf<double> chunk_sum;
     DevBuf<unsigned int> counter;
     int nsoc = 0, nchunks = 0;
-    std::vector<PsdCone> psd;
-    DevBuf<PsdCone> d_psd;
+    std::vector<PsdCone> psd;        // d <= PSD_SMEM_MAX_D: one CTA per cone, two-sided Jacobi in shared memory
+    std::vector<PsdCone> psd_large;  // larger: cooperative one-sided block Jacobi (psd_large.cu)
+    DevBuf<PsdCone> d_psd, d_psd_large;
     DevBuf<double> psd_work;
+    DevBuf<uint8_t> psd_ctl;
     int psd_max_d = 0;
     void build(int64_t NP_, const std::vector<ConeSeg> &segs);
 };
@@ -251,6 +253,9 @@ struct Handle {
         (h)->stats.launches++;                                         \
     } while (0)
 
-void psd_project(Handle *h, ConeSet &K, const double *in, double *projbuf);  // K5, psd.cu
+constexpr int PSD_SMEM_MAX_D = 112;  // largest cone whose S and V fit one SM's shared memory
+void psd_project(Handle *h, ConeSet &K, const double *in, double *projbuf);        // K5, psd.cu
+void psd_project_large(Handle *h, ConeSet &K, const double *in, double *projbuf);  // K5, psd_large.cu
+int psd_large_last_sweeps(Handle *h, ConeSet &K);
 
 }  // namespace fos

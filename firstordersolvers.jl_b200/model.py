@@ -252,6 +252,17 @@ class _Handle:
         self.ck(self.L.fos_get_stream(self.h, C.byref(out)))
         return int(out.value)
 
+    def time_psd(self, X, reps=5):
+        """X: (ncones, d(d+1)/2) packed matrices -> (projections, ms per call, Jacobi sweeps)."""
+        X = np.ascontiguousarray(np.atleast_2d(X), dtype=np.float64)
+        nc, plen = X.shape
+        d = int(round(np.sqrt(0.25 + 2 * plen) - 0.5))
+        Y = np.empty_like(X)
+        ms = C.c_double(0)
+        sw = C.c_int32(0)
+        self.ck(self.L.fos_time_psd(self.h, d, nc, _d(X), _d(Y), int(reps), C.byref(ms), C.byref(sw)))
+        return Y, ms.value, int(sw.value)
+
     def time_matvec(self, nvec=2, reps=10):
         ms = C.c_double(0)
         by = C.c_double(0)

@@ -238,6 +238,13 @@ int32_t fos_get_stream(fos_handle_t h, uint64_t *stream_out);
  * direction) on the loaded matrix with CUDA events on the library's stream; returns the
  * average milliseconds per launch and the algorithmic bytes one launch streams. */
 int32_t fos_time_matvec(fos_handle_t h, int32_t nvec, int32_t reps, double *ms_per_launch, double *bytes_per_launch);
+/* Times `reps` projections of `ncones` packed symmetric matrices of order d (x: ncones * d(d+1)/2
+ * doubles, host) onto the PSD cone (IndPSD(scaling=true), cones.jl:11) with CUDA events on the library's
+ * stream; returns the average milliseconds per projection call (all cones in one launch), the number
+ * of Jacobi sweeps of the last call (cone 0; 0 for the small-cone kernel) and, when y != NULL, the
+ * projections.  Stand-alone: needs no loaded problem. */
+int32_t fos_time_psd(fos_handle_t h, int64_t d, int64_t ncones, const double *x, double *y, int32_t reps,
+                     double *ms_per_call, int32_t *sweeps);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -219,7 +219,7 @@ def test_psd_literal_known_answer(fos):
     np.testing.assert_allclose(Pd, P_PSD_YS, rtol=1e-10, atol=1e-14)
 
 
-@pytest.mark.parametrize("d", [1, 2, 3, 5, 16, 33, 64, 100, 130])
+@pytest.mark.parametrize("d", [1, 2, 3, 5, 16, 33, 64, 100, 112, 113, 130, 200, 256, 300, 512])
 @pytest.mark.parametrize("dual", [False, True])
 def test_psd_projection_vs_lapack(fos, d, dual):
     from oracle import np_oracle as npo
@@ -237,6 +237,37 @@ def test_psd_projection_vs_lapack(fos, d, dual):
         S = (G * lam) @ G.T
         got = problems.smat(H.prox_cone("SDP", problems.svec(S)))
         np.testing.assert_allclose(got, (G * np.maximum(lam, 0)) @ G.T, atol=1e-12)
+
+
+@pytest.mark.parametrize("d,nc", [(512, 2), (129, 5), (640, 1), (1024, 1)])
+def test_psd_large_batched_cones(fos, d, nc):
+    """Several large cones in one cooperative launch (config 4: the primal and the dual SDP(512) cone of
+    DualConeProduct are projected together); spectra: random, low rank + noise, all negative, zero."""
+    from oracle import np_oracle as npo
+    from fos_b200 import problems
+    H = fos.Handle(0)
+    rng = np.random.default_rng(d + nc)
+    plen = d * (d + 1) // 2
+    X = rng.standard_normal((nc, plen))
+    if nc >= 2:
+        U = rng.standard_normal((d, 3))
+        X[1] = problems.svec(U @ U.T - 0.2 * np.eye(d)) + 1e-6 * rng.standard_normal(plen)
+    if nc >= 3:
+        G = rng.standard_normal((d, d))
+        X[2] = problems.svec(-(G @ G.T) - np.eye(d))
+    if nc >= 4:
+        X[3] = 0.0
+    Y, ms, sweeps = H.time_psd(X, reps=1)
+    for k in range(nc):
+        ref = npo.prox_cone("SDP", X[k])
+        den = max(np.abs(ref).max(), np.abs(X[k]).max(), 1e-300)
+        assert np.abs(Y[k] - ref).max() / den < 1e-12, (k, np.abs(Y[k] - ref).max() / den)
+    assert 1 <= sweeps <= 40
+    # idempotence and Moreau decomposition x = P_K(x) - P_K(-x) (size-independent properties)
+    Y2, _, _ = H.time_psd(Y, reps=1)
+    assert np.abs(Y2 - Y).max() <= 1e-12 * max(np.abs(Y).max(), 1.0)
+    Yn, _, _ = H.time_psd(-X, reps=1)
+    assert np.abs(Y - Yn - X).max() <= 1e-12 * np.abs(X).max()
 
 
 def test_dual_cone_product_prox(fos, oracle):
