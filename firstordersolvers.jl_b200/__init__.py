@@ -10,7 +10,7 @@ of src/FOSSolverInterface.jl with the ``!`` dropped.
 from .algorithms import AP, DR, FISTA, GAP, GAPA, GAPP, Dykstra, FOSAlgorithm
 from .model import (AffinePlusLinear, ConeProduct, ConicModel, Feasibility, FeasibilityModel, FeasibilitySolution,
                     FOSMathProgModel, MVHistory, Solution, getobjval, getsolution, loadproblem, numconstr, numvar,
-                    optimize, solve, status, supportedcones)
+                    optimize, solve, solve_batch, status, supportedcones)
 from .model import _Handle as Handle
 from ._lib import FosError, lib_path, load as load_library
 from . import build as _build
@@ -20,5 +20,5 @@ build_library = _build.build
 
 __all__ = ["AP", "DR", "FISTA", "GAP", "GAPA", "GAPP", "Dykstra", "FOSAlgorithm", "AffinePlusLinear", "ConeProduct",
            "ConicModel", "Feasibility", "FeasibilityModel", "FeasibilitySolution", "FOSMathProgModel", "MVHistory",
-           "Solution", "getobjval", "getsolution", "loadproblem", "numconstr", "numvar", "optimize", "solve", "status",
+           "Solution", "getobjval", "getsolution", "loadproblem", "numconstr", "numvar", "optimize", "solve", "solve_batch", "status",
            "supportedcones", "Handle", "FosError", "lib_path", "load_library", "build_library", "problems"]

@@ -50,6 +50,21 @@ SIGNATURES = {
     "fos_finish": (C.c_int32, [_h, _dp, C.c_int64, _dp, _i64p, _i32p]),
     "fos_solve": (C.c_int32, [_h, C.c_int64, C.c_int64, C.c_double, _dp, C.c_int64, _i64p, _i32p, _dp, C.c_int64,
                               _i64p]),
+    "fos_load_conic_dense_batch": (C.c_int32, [_h, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64,
+                                               C.c_int32, _dp, _dp, C.c_int64, _i32p, _i64p, C.c_int64, _i32p,
+                                               _i64p]),
+    "fos_batch_size": (C.c_int64, [_h]),
+    "fos_set_iterate_batch": (C.c_int32, [_h, _dp]),
+    "fos_get_iterate_batch": (C.c_int32, [_h, _dp]),
+    "fos_get_state_batch": (C.c_int32, [_h, C.c_int32, _dp]),
+    "fos_set_state_batch": (C.c_int32, [_h, C.c_int32, _dp]),
+    "fos_get_info_batch": (C.c_int32, [_h, C.c_int32, _dp]),
+    "fos_set_info_batch": (C.c_int32, [_h, C.c_int32, _dp]),
+    "fos_begin_solve_batch": (C.c_int32, [_h]),
+    "fos_run_batch": (C.c_int32, [_h, C.c_int64, C.c_int64, C.c_int64, C.c_double, _i64p, _i32p, _dp, C.c_int64,
+                                  _i64p]),
+    "fos_finish_batch": (C.c_int32, [_h, _dp, _dp, _i64p, _i32p]),
+    "fos_solve_batch": (C.c_int32, [_h, C.c_int64, C.c_int64, C.c_double, _dp, _i64p, _i32p, _dp, C.c_int64, _i64p]),
     "fos_a_mul": (C.c_int32, [_h, _dp, _dp, C.c_int32]),
     "fos_q_mul": (C.c_int32, [_h, _dp, _dp, C.c_int32]),
     "fos_kkt_mul": (C.c_int32, [_h, _dp, _dp]),

@@ -14,8 +14,8 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libfos_b200.so"
-SOURCES = ["capi.cu", "solver.cu", "matop.cu", "psd.cu", "psd_large.cu"]
-HEADERS = ["common.cuh", "kernels.cuh", "matvec.cuh", "solver.cuh", "../../include/fos_b200.h"]
+SOURCES = ["capi.cu", "solver.cu", "matop.cu", "psd.cu", "psd_large.cu", "batch.cu"]
+HEADERS = ["common.cuh", "kernels.cuh", "matvec.cuh", "solver.cuh", "batch.cuh", "../../include/fos_b200.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

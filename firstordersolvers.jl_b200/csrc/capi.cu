@@ -97,6 +97,9 @@ int32_t fos_set_option(fos_handle_t hh, const char *key, double value)
     } else if (k == "profile_matvec") {
         h.A.profile = value != 0;
         h.A.prof_reset();
+    } else if (k == "batch_ctas") {
+        h.batch_ctas = (int)value;
+        if (h.batch) h.batch->grid_ctas = (int)value;
     } else if (k == "use_graphs") {
         // reserved
     } else {
@@ -226,14 +229,16 @@ int32_t fos_set_algorithm(fos_handle_t hh, int32_t alg, double alpha, double alp
                           int64_t iproj)
 {
     FOS_API_BEGIN(hh)
-    hh->h.require_loaded();
+    FOS_REQUIRE(hh->h.loaded || (hh->h.batch && hh->h.batch->loaded), "no problem loaded on this handle");
     hh->h.set_algorithm(alg, alpha, alpha1, alpha2, beta, iproj);
     FOS_API_END(hh)
 }
 
 int64_t fos_iterate_length(fos_handle_t hh)
 {
-    if (!hh || !hh->h.loaded) return -1;
+    if (!hh) return -1;
+    if (hh->h.batch && hh->h.batch->loaded) return hh->h.batch->N;
+    if (!hh->h.loaded) return -1;
     return hh->h.N;
 }
 
@@ -414,6 +419,186 @@ int32_t fos_solve(fos_handle_t hh, int64_t max_iters, int64_t checki, double eps
     if (iters_done) *iters_done = done;
     if (n_rec) *n_rec = nr1 + nr2;
     if (status) *status = h.status == FOS_STATUS_CONTINUE ? FOS_STATUS_INDETERMINATE : h.status;
+    FOS_API_END(hh)
+}
+
+// ---- batch mode -----------------------------------------------------------------------------
+static BatchSolver &batch_of(Handle &h)
+{
+    FOS_REQUIRE(h.batch && h.batch->loaded, "the handle is not in batch mode (fos_load_conic_dense_batch)");
+    return *h.batch;
+}
+static int batch_vec_of(int32_t which, bool for_set)
+{
+    switch (which) {
+    case 0: return BV_X;
+    case 1: FOS_REQUIRE(!for_set, "this state vector cannot be set"); return BV_TMP1;
+    case 2: FOS_REQUIRE(!for_set, "this state vector cannot be set"); return BV_TMP2;
+    case 3: return BV_SOL;
+    case 5: FOS_REQUIRE(!for_set, "this state vector cannot be set"); return BV_PROJ;
+    case 6: return BV_FY;
+    case 7: return BV_DP;
+    case 8: return BV_DQ;
+    default: throw Error(FOS_ERR_INVALID, "unknown state selector");
+    }
+}
+
+int32_t fos_load_conic_dense_batch(fos_handle_t hh, int64_t nprob, int64_t m, int64_t n, const double *A, int64_t lda,
+                                   int64_t pstride, int32_t a_location, const double *b, const double *c,
+                                   int64_t ncones1, const int32_t *cone_type1, const int64_t *cone_len1,
+                                   int64_t ncones2, const int32_t *cone_type2, const int64_t *cone_len2)
+{
+    FOS_API_BEGIN(hh)
+    Handle &h = hh->h;
+    FOS_REQUIRE(A && b && c, "null problem data");
+    FOS_REQUIRE(lda >= n && pstride >= (m - 1) * lda + n, "bad leading dimension / problem stride");
+    FOS_REQUIRE(a_location == FOS_MEM_HOST || a_location == FOS_MEM_DEVICE, "bad a_location");
+    FOS_REQUIRE(h.nranks == 1, "batch mode is split across GPUs by the caller (one handle per rank), not row-sharded");
+    h.loaded = false;
+    h.batch.reset(new BatchSolver());
+    h.batch->grid_ctas = h.batch_ctas;
+    h.batch->load(&h, nprob, m, n, A, lda, pstride, a_location, b, c, ncones1, cone_type1, cone_len1, ncones2,
+                  cone_type2, cone_len2);
+    h.alg = FOS_ALG_GAP;
+    h.alpha = 0.8;
+    h.alpha1 = 1.8;
+    h.alpha2 = 1.8;
+    h.betaA = 0.0;
+    FOS_API_END(hh)
+}
+
+int64_t fos_batch_size(fos_handle_t hh)
+{
+    if (!hh || !hh->h.batch || !hh->h.batch->loaded) return -1;
+    return hh->h.batch->B;
+}
+
+int32_t fos_set_iterate_batch(fos_handle_t hh, const double *z)
+{
+    FOS_API_BEGIN(hh)
+    BatchSolver &bs = batch_of(hh->h);
+    if (z) bs.set_vector(BV_X, z, 0, bs.B);
+    else bs.set_initial_iterate();
+    FOS_API_END(hh)
+}
+
+int32_t fos_get_iterate_batch(fos_handle_t hh, double *z)
+{
+    FOS_API_BEGIN(hh)
+    BatchSolver &bs = batch_of(hh->h);
+    FOS_REQUIRE(z != nullptr, "null output");
+    bs.get_vector(BV_X, z, 0, bs.B);
+    FOS_API_END(hh)
+}
+
+int32_t fos_get_state_batch(fos_handle_t hh, int32_t which, double *buf)
+{
+    FOS_API_BEGIN(hh)
+    BatchSolver &bs = batch_of(hh->h);
+    FOS_REQUIRE(buf != nullptr, "null output");
+    bs.get_vector(batch_vec_of(which, false), buf, 0, bs.B);
+    FOS_API_END(hh)
+}
+
+int32_t fos_set_state_batch(fos_handle_t hh, int32_t which, const double *buf)
+{
+    FOS_API_BEGIN(hh)
+    BatchSolver &bs = batch_of(hh->h);
+    FOS_REQUIRE(buf != nullptr, "null input");
+    bs.set_vector(batch_vec_of(which, true), buf, 0, bs.B);
+    if (which == 3) {  // restoring the CG warm start clears S1's first-run flag (affinepluslinear.jl:101-104)
+        std::vector<BatchCtl> hc((size_t)bs.B);
+        FOS_CUDA(cudaMemcpy(hc.data(), bs.dctl.p, hc.size() * sizeof(BatchCtl), cudaMemcpyDeviceToHost));
+        for (BatchCtl &c : hc) c.firstrun = 0;
+        FOS_CUDA(cudaMemcpy(bs.dctl.p, hc.data(), hc.size() * sizeof(BatchCtl), cudaMemcpyHostToDevice));
+    }
+    FOS_API_END(hh)
+}
+
+int32_t fos_get_info_batch(fos_handle_t hh, int32_t which, double *out)
+{
+    FOS_API_BEGIN(hh)
+    BatchSolver &bs = batch_of(hh->h);
+    FOS_REQUIRE(out != nullptr, "null output");
+    FOS_CUDA(cudaStreamSynchronize(hh->h.stream));
+    std::vector<BatchCtl> hc((size_t)bs.B);
+    FOS_CUDA(cudaMemcpy(hc.data(), bs.dctl.p, hc.size() * sizeof(BatchCtl), cudaMemcpyDeviceToHost));
+    for (int64_t p = 0; p < bs.B; p++) {
+        const BatchCtl &c = hc[(size_t)p];
+        switch (which) {
+        case 0: out[p] = (double)c.s1_calls; break;
+        case 1: out[p] = (double)c.cgiter; break;
+        case 2: out[p] = c.alpha12; break;
+        case 3: out[p] = c.fista_t; break;
+        case 4: out[p] = (double)c.warn_maxit; break;
+        case 5: out[p] = (double)c.total_cg; break;
+        case 6: out[p] = (double)c.total_passes; break;
+        default: throw Error(FOS_ERR_INVALID, "unknown info selector");
+        }
+    }
+    FOS_API_END(hh)
+}
+
+int32_t fos_set_info_batch(fos_handle_t hh, int32_t which, const double *values)
+{
+    FOS_API_BEGIN(hh)
+    BatchSolver &bs = batch_of(hh->h);
+    FOS_REQUIRE(values != nullptr, "null input");
+    FOS_CUDA(cudaStreamSynchronize(hh->h.stream));
+    std::vector<BatchCtl> hc((size_t)bs.B);
+    FOS_CUDA(cudaMemcpy(hc.data(), bs.dctl.p, hc.size() * sizeof(BatchCtl), cudaMemcpyDeviceToHost));
+    for (int64_t p = 0; p < bs.B; p++) {
+        BatchCtl &c = hc[(size_t)p];
+        switch (which) {
+        case 0: c.s1_calls = (int64_t)values[p]; break;
+        case 2: c.alpha12 = values[p]; break;
+        case 3: c.fista_t = values[p]; break;
+        default: throw Error(FOS_ERR_INVALID, "this scalar cannot be set");
+        }
+    }
+    FOS_CUDA(cudaMemcpy(bs.dctl.p, hc.data(), hc.size() * sizeof(BatchCtl), cudaMemcpyHostToDevice));
+    FOS_API_END(hh)
+}
+
+int32_t fos_begin_solve_batch(fos_handle_t hh)
+{
+    FOS_API_BEGIN(hh)
+    batch_of(hh->h).begin_solve();
+    FOS_API_END(hh)
+}
+
+int32_t fos_run_batch(fos_handle_t hh, int64_t i_start, int64_t n_iters, int64_t checki, double eps,
+                      int64_t *iters_done, int32_t *status, double *records, int64_t rec_cap, int64_t *n_rec)
+{
+    FOS_API_BEGIN(hh)
+    BatchSolver &bs = batch_of(hh->h);
+    bs.launch(i_start, n_iters, checki, eps, true, false);
+    bs.collect(iters_done, status, records, records ? rec_cap : 0, n_rec, nullptr);
+    FOS_API_END(hh)
+}
+
+int32_t fos_finish_batch(fos_handle_t hh, double *guess, double *record, int64_t *n_rec, int32_t *status)
+{
+    FOS_API_BEGIN(hh)
+    BatchSolver &bs = batch_of(hh->h);
+    bs.launch(0, 0, 1 << 30, bs.last_eps, false, true);
+    bs.collect(nullptr, status, record, record ? 1 : 0, n_rec, nullptr);
+    if (guess) bs.get_vector(BV_PROJ, guess, 0, bs.B);
+    FOS_API_END(hh)
+}
+
+int32_t fos_solve_batch(fos_handle_t hh, int64_t max_iters, int64_t checki, double eps, double *guess,
+                        int64_t *iters_done, int32_t *status, double *records, int64_t rec_cap, int64_t *n_rec)
+{
+    FOS_API_BEGIN(hh)
+    BatchSolver &bs = batch_of(hh->h);
+    bs.begin_solve();
+    bs.launch(1, max_iters, checki, eps, true, true);
+    bs.collect(iters_done, status, records, records ? rec_cap : 0, n_rec, nullptr);
+    if (status)
+        for (int64_t p = 0; p < bs.B; p++)
+            if (status[p] == FOS_STATUS_CONTINUE) status[p] = FOS_STATUS_INDETERMINATE;  // HSDE.jl:56-59
+    if (guess) bs.get_vector(BV_PROJ, guess, 0, bs.B);
     FOS_API_END(hh)
 }
 

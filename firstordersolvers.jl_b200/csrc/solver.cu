@@ -530,6 +530,7 @@ void Handle::set_algorithm(int alg_, double a, double a1, double a2, double bA, 
     betaA = bA;
     iproj = ip;
     fista_t = 1.0;  // fista.jl:24
+    if (batch && batch->loaded) batch->set_algorithm();
     if (loaded) {
         const size_t bytes = (size_t)L.NP * 8;
         FOS_CUDA(cudaMemsetAsync(fy.p, 0, bytes, stream));

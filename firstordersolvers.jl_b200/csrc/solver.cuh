@@ -12,6 +12,7 @@
 #include "common.cuh"
 #include "kernels.cuh"
 #include "matvec.cuh"
+#include "batch.cuh"
 
 namespace fos {
 
@@ -161,13 +162,49 @@ struct ConeSet {
     void build(int64_t NP_, const std::vector<ConeSeg> &segs);
 };
 
+struct Handle;
+
+// batch mode (batch.cu): B problems of identical shape, one persistent CTA per problem
+struct BatchSolver {
+    Handle *h = nullptr;
+    bool loaded = false;
+    int64_t B = 0, N = 0;
+    Lay L{};
+    SegMap seg{};
+    int64_t lda = 0, a_stride = 0;
+    int ntiles = 0, S = 0, CW = 0, KP = 1, ctas_per_sm = 1;
+    size_t smem_bytes = 0;
+    int grid_ctas = 0;
+    DevBuf<double> dA, db, dc, dnb, dncn, vec, drecs, dtol;
+    DevBuf<BatchCtl> dctl;
+    DevBuf<unsigned int> counter;
+    ConeSet cones;
+    int rec_cap = 0, tol_n = 0;
+    double tol_floor = 0.0;
+    double last_eps = 1e-5;  // eps of the last run (the forced final check of finish uses it)
+
+    void load(Handle *h_, int64_t B_, int64_t m, int64_t n, const double *A, int64_t lda_src, int64_t pstride_src,
+              int location, const double *b, const double *c, int64_t nc1, const int32_t *t1, const int64_t *l1,
+              int64_t nc2, const int32_t *t2, const int64_t *l2);
+    void ensure_recs(int cap);
+    void set_algorithm();
+    void begin_solve();
+    void set_initial_iterate();
+    void set_vector(int which, const double *z, int64_t pb0, int64_t count);
+    void get_vector(int which, double *z, int64_t pb0, int64_t count);
+    void launch(int64_t i_start, int64_t n_iters, int64_t checki, double eps, bool do_run, bool do_finish);
+    void collect(int64_t *iters_done, int32_t *status, double *records, int64_t rec_cap_host, int64_t *n_rec,
+                 int64_t *cgiter_total);
+    double bytes_per_pass() const;
+};
+
 struct Handle {
     int device = 0;
     cudaStream_t stream = nullptr;
     int num_sms = 148;
     std::string err;
     // options
-    int matvec_impl = 0, grid_ctas = 0, cg_batch = 0, fuse_rhs = 1;
+    int matvec_impl = 0, grid_ctas = 0, cg_batch = 0, fuse_rhs = 1, batch_ctas = 0;
     // problem
     bool loaded = false;
     Lay L{};
@@ -210,6 +247,8 @@ struct Handle {
     // run parameters remembered for finish()
     int64_t cur_i = 0, cur_checki = 100;
     double cur_eps = 1e-5;
+    // batch mode
+    std::unique_ptr<BatchSolver> batch;
 
     ~Handle();
     void create(int dev);

@@ -111,6 +111,7 @@ class _Handle:
 
     def __init__(self, device=0):
         self.L = _lib.load()
+        self._B = 0
         self.h = C.c_void_p()
         rc = self.L.fos_create(C.byref(self.h), int(device))
         if rc != 0:
@@ -206,6 +207,96 @@ class _Handle:
         self.ck(self.L.fos_solve(self.h, max_iters, checki, eps, _d(guess), guess.size, C.byref(done), C.byref(st),
                                  _d(rec), cap, C.byref(nrec)))
         return int(done.value), int(st.value), rec[:min(nrec.value, cap)], guess
+
+    # -- batch mode (fos_*_batch): every array has a leading batch dimension -----------------------
+    def load_conic_batch(self, A, b, c, constr_cones, var_cones, device_ptr=None):
+        """A: (B, m, n) ndarray (or its shape when ``device_ptr=(ptr, lda, pstride)`` hands over
+        matrices already on the GPU); b: (B, m); c: (B, n); cones shared by all problems."""
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        c = np.ascontiguousarray(c, dtype=np.float64)
+        B, m = b.shape
+        n = c.shape[1]
+        t1, l1 = _cone_arrays(constr_cones, m, "constraint")
+        t2, l2 = _cone_arrays(var_cones, n, "variable")
+        if device_ptr is not None:
+            ptr, lda, pstride = device_ptr
+            loc = 1
+            keep = None
+        else:
+            keep = np.ascontiguousarray(A, dtype=np.float64)
+            assert keep.shape == (B, m, n), (keep.shape, (B, m, n))
+            ptr, lda, pstride, loc = keep.ctypes.data, n, m * n, 0
+        self.ck(self.L.fos_load_conic_dense_batch(self.h, B, m, n, C.c_void_p(int(ptr)), int(lda), int(pstride), loc,
+                                                  _d(b), _d(c), len(t1), _i32p(t1), _i64p(l1), len(t2), _i32p(t2),
+                                                  _i64p(l2)))
+        self._B = B
+
+    def batch_size(self):
+        return int(self.L.fos_batch_size(self.h))
+
+    def set_iterate_batch(self, z=None):
+        if z is None:
+            self.ck(self.L.fos_set_iterate_batch(self.h, None))
+        else:
+            z = np.ascontiguousarray(z, dtype=np.float64)
+            assert z.shape == (self._B, self.n())
+            self.ck(self.L.fos_set_iterate_batch(self.h, _d(z)))
+
+    def get_iterate_batch(self):
+        z = np.empty((self._B, self.n()))
+        self.ck(self.L.fos_get_iterate_batch(self.h, _d(z)))
+        return z
+
+    def get_state_batch(self, which):
+        z = np.empty((self._B, self.n()))
+        self.ck(self.L.fos_get_state_batch(self.h, self._STATE[which], _d(z)))
+        return z
+
+    def set_state_batch(self, which, z):
+        z = np.ascontiguousarray(z, dtype=np.float64)
+        assert z.shape == (self._B, self.n())
+        self.ck(self.L.fos_set_state_batch(self.h, self._STATE[which], _d(z)))
+
+    def info_batch(self, which):
+        out = np.empty(self._B)
+        self.ck(self.L.fos_get_info_batch(self.h, self._INFO[which], _d(out)))
+        return out
+
+    def set_info_batch(self, which, values):
+        v = np.ascontiguousarray(np.broadcast_to(np.asarray(values, dtype=np.float64), (self._B,)))
+        self.ck(self.L.fos_set_info_batch(self.h, self._INFO[which], _d(v)))
+
+    def run_batch(self, i_start, n_iters, checki, eps):
+        B = self._B
+        cap = n_iters // max(checki, 1) + 2
+        rec = np.zeros((B, cap, REC_LEN))
+        done = np.zeros(B, dtype=np.int64)
+        st = np.zeros(B, dtype=np.int32)
+        nrec = np.zeros(B, dtype=np.int64)
+        self.ck(self.L.fos_run_batch(self.h, i_start, n_iters, checki, eps, _i64p(done), _i32p(st), _d(rec), cap,
+                                     _i64p(nrec)))
+        return done, st, [rec[p, :min(nrec[p], cap)] for p in range(B)]
+
+    def finish_batch(self):
+        B = self._B
+        guess = np.empty((B, self.n()))
+        rec = np.zeros((B, REC_LEN))
+        nrec = np.zeros(B, dtype=np.int64)
+        st = np.zeros(B, dtype=np.int32)
+        self.ck(self.L.fos_finish_batch(self.h, _d(guess), _d(rec), _i64p(nrec), _i32p(st)))
+        return guess, [rec[p:p + 1][:nrec[p]] for p in range(B)], st
+
+    def solve_batch(self, max_iters, checki, eps):
+        B = self._B
+        cap = max_iters // max(checki, 1) + 2
+        rec = np.zeros((B, cap, REC_LEN))
+        guess = np.empty((B, self.n()))
+        done = np.zeros(B, dtype=np.int64)
+        st = np.zeros(B, dtype=np.int32)
+        nrec = np.zeros(B, dtype=np.int64)
+        self.ck(self.L.fos_solve_batch(self.h, max_iters, checki, eps, _d(guess), _i64p(done), _i32p(st), _d(rec), cap,
+                                       _i64p(nrec)))
+        return done, st, [rec[p, :min(nrec[p], cap)] for p in range(B)], guess
 
     # unit level
     def _vec_call(self, fn, x, n_out=None, *extra):
@@ -524,6 +615,61 @@ def optimize(model: FOSMathProgModel, out=None):
     model.slack = sol.s
     model.obj_val = float(np.dot(model.c, model.primal_sol))  # :20
     return model
+
+
+# =============================================================================================
+# batch of conic models (config 5: many independent problems of one shape)
+# =============================================================================================
+def solve_batch(alg: FOSAlgorithm, cs, As, bs, constr_cones, var_cones, device=0, device_ptr=None):
+    """``[solve!(model_j) for j in 1:B]`` for B models that share (m, n, cones) -- loadproblem! +
+    optimize! (FOSSolverInterface.jl:8-64) with the whole batch resident on one GPU and one persistent
+    CTA per problem.  Options (max_iters, eps, checki, debug) come from ``alg.options`` as for
+    ``ConicModel``.  Returns a list of ``FOSMathProgModel`` with solve_stat / primal_sol / dual_sol /
+    slack / obj_val / history filled in, in input order."""
+    alg._check_supported()
+    opts = dict(alg.options)
+    max_iters = int(opts.get("max_iters", 10000))
+    eps = float(opts.get("eps", 1e-5))
+    checki = int(opts.get("checki", 100))
+    debug = int(opts.get("debug", 1))
+    bs = np.ascontiguousarray(bs, dtype=np.float64)
+    cs = np.ascontiguousarray(cs, dtype=np.float64)
+    B, m = bs.shape
+    n = cs.shape[1]
+    H = _Handle(device)
+    if "batch_ctas" in opts:
+        H.set_option("batch_ctas", opts["batch_ctas"])
+    H.load_conic_batch(As, bs, cs, constr_cones, var_cones, device_ptr=device_ptr)
+    H.set_algorithm(alg)
+    if "initx" in opts:
+        H.set_iterate_batch(np.broadcast_to(np.asarray(opts["initx"], dtype=np.float64), (B, H.n())))
+    t0 = time.perf_counter_ns()
+    done, st, recs, guess = H.solve_batch(max_iters, checki, eps)
+    t = time.perf_counter_ns() - t0
+    if H.info("cg_warned"):
+        warnings.warn("CG reached max iterations, result may be inaccurate")  # conjugategradients.jl:53
+    models = []
+    l = n + m + 1
+    for j in range(B):
+        mod = FOSMathProgModel(alg, **alg.options)
+        mod.input_numconstr, mod.input_numvar = m, n
+        mod.K1, mod.K2 = tuple(constr_cones), tuple(var_cones)
+        mod.b, mod.c = bs[j], cs[j]
+        mod.last_iteration = int(done[j])
+        if debug > 0:
+            for r in recs[j]:
+                for key, v in (("p", r[1]), ("d", r[2]), ("g", r[3]), ("ctx", r[4]), ("bty", r[5]), ("κ", r[6]),
+                               ("τ", r[7]), ("t", t)):
+                    mod.history.push(key, int(r[0]), v)
+                mod.history.push("cgiter", int(r[0]), int(r[8]))
+        g = guess[j]
+        tau = g[l - 1]
+        with np.errstate(all="ignore"):
+            mod.primal_sol, mod.dual_sol, mod.slack = g[:n] / tau, g[n:n + m] / tau, g[l + n:l + n + m] / tau
+        mod.solve_stat = STATUS_SYMBOLS[int(st[j])]
+        mod.obj_val = float(np.dot(cs[j], mod.primal_sol))
+        models.append(mod)
+    return models
 
 
 # =============================================================================================

@@ -100,6 +100,7 @@ const char *fos_last_error(fos_handle_t h);
  *                  initial CG residual (k+1 passes over A per projection instead of k+2; same
  *                  mathematics, sums associated differently); 0 = build rhs in the reference's order
  *   "profile_matvec" 1 = CUDA events around every mat-vec launch (read back with fos_get_info)
+ *   "batch_ctas"   persistent CTAs of the batch kernel (default = #SMs)
  *   "use_graphs"   reserved                                                                */
 int32_t fos_set_option(fos_handle_t h, const char *key, double value);
 
@@ -195,6 +196,43 @@ int32_t fos_finish(fos_handle_t h, double *guess, int64_t len, double *record, i
  * i = 1, finish.  Status Continue is reported as Indeterminate (HSDE.jl:56-59). */
 int32_t fos_solve(fos_handle_t h, int64_t max_iters, int64_t checki, double eps, double *guess, int64_t len,
                   int64_t *iters_done, int32_t *status, double *records, int64_t rec_cap, int64_t *n_rec);
+
+/* ====================================================================================== */
+/* batch mode: B independent conic problems of identical shape (same m, n, cone layout;  */
+/* different A, b, c), one persistent CTA per problem, no host round trips (new; the     */
+/* reference solves one model at a time -- SURVEY.md 8b "fos_load_conic_batch /         */
+/* fos_run_batch", 8e batch split).  Every per-problem array has a leading batch          */
+/* dimension.  The algorithm is chosen with fos_set_algorithm (GAP/DR/AP, GAPA, FISTA,    */
+/* Dykstra); a handle is either in batch mode or in single-problem mode.                  */
+/* ====================================================================================== */
+/* A: B matrices, m x n row-major, leading dimension lda, problem stride pstride (elements), on the host
+ * or on the device; b: B x m, c: B x n (host).  Cones as in fos_load_conic_csc (SDP not offered). */
+int32_t fos_load_conic_dense_batch(fos_handle_t h, int64_t nprob, int64_t m, int64_t n, const double *A, int64_t lda,
+                                   int64_t pstride, int32_t a_location, const double *b, const double *c,
+                                   int64_t ncones1, const int32_t *cone_type1, const int64_t *cone_len1,
+                                   int64_t ncones2, const int32_t *cone_type2, const int64_t *cone_len2);
+int64_t fos_batch_size(fos_handle_t h); /* number of problems; <0 when the handle is not in batch mode */
+/* z: B x fos_iterate_length, or NULL for the initial value of every problem (HSDE.jl:40-47). */
+int32_t fos_set_iterate_batch(fos_handle_t h, const double *z);
+int32_t fos_get_iterate_batch(fos_handle_t h, double *z);
+/* Same selectors as fos_get_state / fos_set_state (0 x, 1 tmp1, 2 tmp2, 3 xinit, 5 last unrelaxed S2
+ * projection, 6 FISTA y, 7/8 Dykstra p/q); buf: B x fos_iterate_length. */
+int32_t fos_get_state_batch(fos_handle_t h, int32_t which, double *buf);
+int32_t fos_set_state_batch(fos_handle_t h, int32_t which, const double *buf);
+/* Per-problem scalars, B values.  which: 0 S1.i, 1 S1.cgiter, 2 alpha12, 3 FISTA t (settable: 0, 2, 3);
+ * read-only: 5 total CG iterations, 6 total passes over A. */
+int32_t fos_get_info_batch(fos_handle_t h, int32_t which, double *out);
+int32_t fos_set_info_batch(fos_handle_t h, int32_t which, const double *values);
+int32_t fos_begin_solve_batch(fos_handle_t h);
+/* fos_run for every problem: iterations i_start .. i_start+n_iters-1, each problem stopping on its own
+ * when a check sets its status.  iters_done, status, n_rec: B entries; records: B x rec_cap x FOS_REC_LEN. */
+int32_t fos_run_batch(fos_handle_t h, int64_t i_start, int64_t n_iters, int64_t checki, double eps,
+                      int64_t *iters_done, int32_t *status, double *records, int64_t rec_cap, int64_t *n_rec);
+/* fos_finish for every problem: guess B x fos_iterate_length, record B x FOS_REC_LEN, n_rec / status B. */
+int32_t fos_finish_batch(fos_handle_t h, double *guess, double *record, int64_t *n_rec, int32_t *status);
+/* solve!(model) for every problem in ONE kernel launch: begin, iterations 1..max_iters, getsol, final check. */
+int32_t fos_solve_batch(fos_handle_t h, int64_t max_iters, int64_t checki, double eps, double *guess,
+                        int64_t *iters_done, int32_t *status, double *records, int64_t rec_cap, int64_t *n_rec);
 
 /* ====================================================================================== */
 /* unit-level entry points (drive the restated unit tests of the reference)  */

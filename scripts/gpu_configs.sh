@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests/test_gpu_batch.py -m gpu -q --timeout 300 > gpurun_out/pytest_batch.log 2>&1; echo "pytest rc=$?"
+tail -15 gpurun_out/pytest_batch.log
+timeout 900 python scripts/config_runs.py c5 --nprob 1024 --iters 100 --cpu > gpurun_out/c5.jsonl 2> gpurun_out/c5.err; echo "c5 rc=$?"; cat gpurun_out/c5.jsonl; tail -5 gpurun_out/c5.err
+timeout 900 python scripts/config_runs.py c4 --iters 30 --cpu > gpurun_out/c4.jsonl 2> gpurun_out/c4.err; echo "c4 rc=$?"; cat gpurun_out/c4.jsonl; tail -5 gpurun_out/c4.err
+timeout 900 python scripts/config_runs.py c3 --iters 30 > gpurun_out/c3.jsonl 2> gpurun_out/c3.err; echo "c3 rc=$?"; cat gpurun_out/c3.jsonl; tail -5 gpurun_out/c3.err
+timeout 600 python scripts/psd_probe.py > gpurun_out/psd_probe.jsonl 2> gpurun_out/psd_probe.err; echo "probe rc=$?"; cat gpurun_out/psd_probe.jsonl; tail -5 gpurun_out/psd_probe.err
