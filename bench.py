@@ -184,6 +184,8 @@ def main():
     ap.add_argument("--seed", type=int, default=2)
     ap.add_argument("--matvec-impl", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: fused peer-memory exchange kernel (default) or fold + ncclAllReduce")
     args = ap.parse_args()
     W = max(args.warmup, 0)
     K = max(args.steps, 1)
@@ -196,7 +198,9 @@ def main():
                           f"CG affine projection with the reference's 0.2^sqrt(i) tolerance schedule",
               "m": m, "n": n, "algorithm": "DR(0.5)", "iterations_timed": f"{W + 1}..{W + K}",
               "l2": "inputs larger than L2 (A is streamed from HBM every pass; no flush needed)",
-              "parallelism": "single GPU" if world == 1 else f"A row-sharded over {world} GPUs, NCCL all-reduce"}
+              "parallelism": "single GPU" if world == 1 else
+              f"A row-sharded over {world} GPUs, " + ("fused peer-memory (NVLink, CUDA IPC) exchange kernel"
+                                                      if args.exchange == "p2p" else "NCCL all-reduce")}
 
     if args.impl == "reference":
         if rank != 0:
@@ -252,6 +256,8 @@ def main():
     t2, l2 = _cone_arrays([("Free", n)], n, "variable")
     H.ck(H.L.fos_load_conic_dense(H.h, m, n, C.c_void_p(A_loc.data_ptr()), n, 1, r0, cnt, _d(b), _d(c), len(t1),
                                   _i32p(t1), _i64p(l1), len(t2), _i32p(t2), _i64p(l2)))
+    if world > 1 and args.exchange == "p2p":
+        parallel.enable_p2p_exchange(H, rank, world, dist)
     H.set_algorithm(fos.DR(0.5))
     H.set_initial_iterate()
     H.ck(H.L.fos_begin_solve(H.h))
@@ -293,6 +299,7 @@ def main():
     mv2_ms, mv2_n = H.info("mv2_ms"), H.info("mv2_n")
     mv1_ms, mv1_n = H.info("mv1_ms"), H.info("mv1_n")
     bytes_pass = H.info("bytes_per_pass")
+    tail_ms, tail_n = H.info("tail_ms"), H.info("tail_n")
     H.set_option("profile_matvec", 0)
     value = K / (ms_total / 1e3)
 
@@ -307,6 +314,8 @@ def main():
         parallel.init_comm(H2, rank, world, cid2)
     H2.ck(H2.L.fos_load_conic_dense(H2.h, m, n, C.c_void_p(A_loc.data_ptr()), n, 1, r0, cnt, _d(b), _d(c), len(t1),
                                     _i32p(t1), _i64p(l1), len(t2), _i32p(t2), _i64p(l2)))
+    if world > 1 and args.exchange == "p2p":
+        parallel.enable_p2p_exchange(H2, rank, world, dist)
     H2.set_algorithm(fos.DR(0.5))
     H2.set_initial_iterate()
     H2.ck(H2.L.fos_begin_solve(H2.h))
@@ -361,6 +370,7 @@ def main():
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": config, "roofline": roofline, "cpu_baseline": cb,
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "cg_tail_avg_launch_us": (1e3 * tail_ms / tail_n) if tail_n else None,
             "cg_iterations_per_step": cg_iters / K, "passes_over_A_per_step": passes / K,
             "wall_ms_per_step": t_wall * 1e3 / K, "status_after_timed": int(st)}
     print(json.dumps(line))

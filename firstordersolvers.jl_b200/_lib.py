@@ -19,6 +19,7 @@ _h = C.c_void_p
 
 FOS_REC_LEN = 10
 FOS_COMM_ID_BYTES = 128
+FOS_IPC_HANDLE_BYTES = 64
 
 # name -> (restype, argtypes); mirrors include/fos_b200.h one to one
 SIGNATURES = {
@@ -29,6 +30,8 @@ SIGNATURES = {
     "fos_set_option": (C.c_int32, [_h, C.c_char_p, C.c_double]),
     "fos_comm_unique_id": (C.c_int32, [_u8p]),
     "fos_comm_init": (C.c_int32, [_h, C.c_int32, C.c_int32, _u8p]),
+    "fos_comm_p2p_export": (C.c_int32, [_h, _u8p]),
+    "fos_comm_p2p_import": (C.c_int32, [_h, _u8p]),
     "fos_load_conic_csc": (C.c_int32, [_h, C.c_int64, C.c_int64, _i64p, _i64p, _dp, C.c_int64, _dp, _dp,
                                        C.c_int64, _i32p, _i64p, C.c_int64, _i32p, _i64p, C.c_int32]),
     "fos_load_conic_dense": (C.c_int32, [_h, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int64,

@@ -94,9 +94,15 @@ int32_t fos_set_option(fos_handle_t hh, const char *key, double value)
         h.cg_batch = (int)value;
     } else if (k == "fuse_rhs") {
         h.fuse_rhs = value != 0;
+    } else if (k == "fuse_tail") {
+        h.fuse_tail = value != 0;
     } else if (k == "profile_matvec") {
         h.A.profile = value != 0;
         h.A.prof_reset();
+    } else if (k == "exchange_impl") {
+        FOS_REQUIRE(value == 0 || value == 1, "exchange_impl must be 0 (NCCL) or 1 (peer memory)");
+        FOS_REQUIRE(value == 0 || h.A.p2p.nranks > 1, "exchange_impl = 1 needs fos_comm_p2p_import first");
+        h.A.p2p_on = value != 0;
     } else if (k == "batch_ctas") {
         h.batch_ctas = (int)value;
         if (h.batch) h.batch->grid_ctas = (int)value;
@@ -144,6 +150,27 @@ int32_t fos_comm_init(fos_handle_t hh, int32_t rank, int32_t nranks, const uint8
     h.nranks = nranks;
     h.A.rank = rank;
     h.A.nranks = nranks;
+    FOS_API_END(hh)
+}
+
+int32_t fos_comm_p2p_export(fos_handle_t hh, uint8_t *handle_out)
+{
+    FOS_API_BEGIN(hh)
+    Handle &h = hh->h;
+    h.require_loaded();
+    FOS_REQUIRE(handle_out != nullptr, "null handle buffer");
+    FOS_CUDA(cudaStreamSynchronize(h.stream));
+    h.A.p2p_export(handle_out);
+    FOS_API_END(hh)
+}
+
+int32_t fos_comm_p2p_import(fos_handle_t hh, const uint8_t *handles)
+{
+    FOS_API_BEGIN(hh)
+    Handle &h = hh->h;
+    h.require_loaded();
+    FOS_REQUIRE(handles != nullptr, "null handle table");
+    h.A.p2p_import(handles);
     FOS_API_END(hh)
 }
 
@@ -368,6 +395,8 @@ int32_t fos_get_info(fos_handle_t hh, int32_t which, double *out)
     case 13: *out = (double)h.A.prof_skipped; break;
     case 14: *out = h.A.bytes_per_pass(); break;
     case 15: *out = (double)h.num_sms; break;
+    case 16: *out = h.A.prof_ms[0]; break;
+    case 17: *out = (double)h.A.prof_n[0]; break;
     default: throw Error(FOS_ERR_INVALID, "unknown info selector");
     }
     FOS_API_END(hh)

@@ -743,6 +743,428 @@ k1_finalize_local(MVView V, int64_t n, int64_t n_pad, int64_t m_local, int64_t r
         }
     }
 }
+
+// ---------------------------------------------------------------------------------------
+// K7, fused exchange over NVLink peer memory (one process per GPU, CUDA IPC): replaces
+// k1_finalize_local + ncclAllReduce with ONE kernel.
+//   phase 1  every block folds its slice of the local K1 partials into this rank's exchange slot
+//            buf[parity] = [NV][n_pad] A' partial sums | [NV][m_pad] own rows of A X;
+//            the last block to finish publishes the epoch in every peer's flag array (st.release.sys).
+//   phase 2  every block waits until all ranks have published the epoch (ld.acquire.sys on its OWN
+//            flag array), then gathers its slice straight from the peers' slots: column entries are
+//            summed over ranks in rank order (identical bits on every rank -> identical stop tests),
+//            row entries are copied from their owner.  Result: complete A X / A' W in xbuf.
+// Slots are double buffered by epoch parity: a slot is rewritten two exchanges later, after every
+// peer has passed the intermediate exchange (which it enters only after finishing this one's reads).
+// ---------------------------------------------------------------------------------------
+constexpr int P2P_MAX_RANKS = 16;
+constexpr int P2P_FLAG_STRIDE = 32;  // uint32 per rank slot (128 B apart)
+constexpr int P2P_MAX_BLOCKS = 512;  // grid limit of k_cg_tail_hsde<true>
+struct P2PHeader {  // first bytes of every rank's region
+    int64_t row_begin, m_local;
+    int64_t reserved[14];
+};
+struct P2PView {
+    unsigned char *peer[P2P_MAX_RANKS];  // base of every rank's region (own region included), mapped here
+    int64_t row_begin[P2P_MAX_RANKS], m_local[P2P_MAX_RANKS];
+    int32_t nranks, rank;
+    int64_t flags_off, buf_off, slot_doubles;  // byte offsets inside a region; doubles per slot
+    int64_t bflags_off;      // per-block flags [nranks][P2P_MAX_BLOCKS] of the fused CG tail
+    unsigned int *epoch;     // local: exchanges completed so far
+    unsigned int *tickets;   // local: [0] phase-1 ticket, [1] exit ticket
+};
+
+__device__ __forceinline__ double ld_sys_f64(const double *p)
+{
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys_u32(const unsigned int *p)
+{
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u32(unsigned int *p, unsigned int v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Sum over ranks (rank order) of NV entries `off + v*vstride` of every rank's slot.  All remote loads of a
+// group of eight ranks are issued before the first add, so the NVLink round trips overlap instead of
+// queueing behind each other (an in-order `acc += load` chain costs nranks round trips).
+template <int NV>
+__device__ __forceinline__ void p2p_gather_sum(const P2PView &X, int par, int64_t off, int64_t vstride, double (&acc)[NV])
+{
+#pragma unroll
+    for (int v = 0; v < NV; v++) acc[v] = 0.0;
+    for (int r0 = 0; r0 < X.nranks; r0 += 8) {
+        double t[8][NV];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if (r0 + k < X.nranks) {
+                const double *src =
+                    reinterpret_cast<const double *>(X.peer[r0 + k] + X.buf_off) + (size_t)par * X.slot_doubles + off;
+#pragma unroll
+                for (int v = 0; v < NV; v++) t[k][v] = ld_sys_f64(src + (size_t)v * vstride);
+            } else {
+#pragma unroll
+                for (int v = 0; v < NV; v++) t[k][v] = 0.0;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+#pragma unroll
+            for (int v = 0; v < NV; v++) acc[v] += t[k][v];
+    }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(VBLOCK)
+k1_exchange_p2p(MVView V, P2PView X, int64_t n, int64_t n_pad, int64_t m_pad, double *__restrict__ xbuf,
+                const int32_t *skip_flag)
+{
+    if (skip_flag != nullptr && *skip_flag != 0) return;
+    __shared__ bool s_last;
+    const unsigned int epoch = *X.epoch + 1u;
+    const int par = (int)(epoch & 1u);
+    const int64_t total = n_pad + m_pad;
+    double *mine = reinterpret_cast<double *>(X.peer[X.rank] + X.buf_off) + (size_t)par * X.slot_doubles;
+    const int64_t rb = X.row_begin[X.rank], ml = X.m_local[X.rank];
+    // ---- phase 1: local fold ----
+    for (int64_t e = (int64_t)blockIdx.x * VBLOCK + threadIdx.x; e < total; e += (int64_t)gridDim.x * VBLOCK) {
+#pragma unroll
+        for (int v = 0; v < NV; v++) {
+            if (e < n_pad) {
+                mine[(size_t)v * n_pad + e] = e < n ? mv_atw(V, v, e) : 0.0;
+            } else {
+                const int64_t row = e - n_pad, lr = row - rb;
+                if (lr >= 0 && lr < ml) mine[(size_t)NV * n_pad + (size_t)v * m_pad + row] = mv_ax(V, v, lr);
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();  // cumulative: publishes the whole block's slot writes
+        const unsigned int t = atomicAdd(&X.tickets[0], 1u);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence_system();
+        if (threadIdx.x < X.nranks)
+            st_release_sys_u32(reinterpret_cast<unsigned int *>(X.peer[threadIdx.x] + X.flags_off) +
+                                   (size_t)X.rank * P2P_FLAG_STRIDE,
+                               epoch);
+    }
+    // ---- phase 2: wait for every rank, gather ----
+    if (threadIdx.x < X.nranks) {
+        const unsigned int *f = reinterpret_cast<const unsigned int *>(X.peer[X.rank] + X.flags_off) +
+                                (size_t)threadIdx.x * P2P_FLAG_STRIDE;
+        while ((int)(ld_acquire_sys_u32(f) - epoch) < 0) {
+        }
+    }
+    __syncthreads();
+    for (int64_t e = (int64_t)blockIdx.x * VBLOCK + threadIdx.x; e < total; e += (int64_t)gridDim.x * VBLOCK) {
+        if (e < n_pad) {
+            double acc[NV];
+            p2p_gather_sum<NV>(X, par, e, n_pad, acc);
+#pragma unroll
+            for (int v = 0; v < NV; v++) xbuf[(size_t)v * n_pad + e] = acc[v];
+        } else {
+            const int64_t row = e - n_pad;
+            int owner = -1;
+            for (int r = 0; r < X.nranks; r++)
+                if (row >= X.row_begin[r] && row < X.row_begin[r] + X.m_local[r]) owner = r;
+#pragma unroll
+            for (int v = 0; v < NV; v++) {
+                double val = 0.0;
+                if (owner >= 0) {
+                    const double *src =
+                        reinterpret_cast<const double *>(X.peer[owner] + X.buf_off) + (size_t)par * X.slot_doubles;
+                    val = ld_sys_f64(src + (size_t)NV * n_pad + (size_t)v * m_pad + row);
+                }
+                xbuf[(size_t)NV * n_pad + (size_t)v * m_pad + row] = val;
+            }
+        }
+    }
+    // ---- exit: the last block advances the epoch and re-arms the tickets ----
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int t = atomicAdd(&X.tickets[1], 1u);
+        if (t == gridDim.x - 1) {
+            X.tickets[0] = 0u;
+            X.tickets[1] = 0u;
+            *X.epoch = epoch;
+            __threadfence();
+        }
+    }
+}
+
+// =======================================================================================
+// Fused CG tail (HSDE form): everything of one CG iteration after the pass over A, in ONE
+// cooperative kernel --  [peer exchange]  ->  Ap = KKT p, <Ap,p>  ->  alpha  ->  x += alpha p,
+// r -= alpha Ap, ||r||  ->  stop test, beta  ->  p = beta p + r  (conjugategradients.jl:38-51 on
+// top of affinepluslinear.jl:37-49 / HSDEAffine.jl:41-65).  Replaces k1_exchange_p2p + k2_kkt_hsde<K2_AP>
+// + k3_cg_update + k3_cg_dir: one launch instead of four, the vectors make one trip through the
+// SMs instead of three, and the two dot products are grid reductions (fixed tree, bitwise
+// reproducible) separated by grid barriers instead of kernel boundaries.
+// Every thread owns the same entries e, LP+e in all phases, so the only cross-thread traffic is
+// the reductions.  With P2P the gathered A X / A' W entries are read straight from the peers'
+// exchange slots (see k1_exchange_p2p for the slot protocol, shared with this kernel).
+// =======================================================================================
+struct GridBar {
+    unsigned int *count;  // arrivals since the handle was created (monotonic)
+    unsigned int *flag;   // last completed barrier target, on its own cache line
+    unsigned int *base;   // value of *count when the current launch started
+    unsigned int *exit_ticket;
+    double *part;         // [2][gridDim.x][8] block partials of the two reductions
+};
+__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int *p)
+{
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned int ld_relaxed_gpu_u32(const unsigned int *p)
+{
+    unsigned int v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// Arrivals are counted with one atomic per block on `count`; the last arriver publishes the target in
+// `flag`, which lives on its own cache line: the waiting blocks poll that line (plain reads, with a
+// short sleep) and never compete with the arriving atomics for the counter's line.
+__device__ __forceinline__ void grid_barrier(const GridBar &gb, unsigned int &k, unsigned int base)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        k++;
+        const unsigned int target = base + k * gridDim.x;
+        __threadfence();
+        const unsigned int old = atomicAdd(gb.count, 1u);
+        if (old + 1u == target) {
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(gb.flag), "r"(target) : "memory");
+        } else {
+            while ((int)(ld_relaxed_gpu_u32(gb.flag) - target) < 0) __nanosleep(32);
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+// block partials -> part[blockIdx.x][0..NQ), grid barrier, every block adds all partials in block order
+template <int NQ>
+__device__ __forceinline__ void grid_allreduce(double (&q)[NQ], double *part, const GridBar &gb, unsigned int &k,
+                                               unsigned int base)
+{
+    __shared__ double s_w[8][VBLOCK / 32];
+    __shared__ double s_tot[8];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NQ; i++) {
+        const double v = warp_sum(q[i]);
+        if (lane == 0) s_w[i][w] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < NQ) {
+        double s = 0.0;
+        for (int j = 0; j < VBLOCK / 32; j++) s += s_w[threadIdx.x][j];
+        part[(size_t)blockIdx.x * 8 + threadIdx.x] = s;
+    }
+    grid_barrier(gb, k, base);
+    // fixed tree: thread t adds blocks t, t+VBLOCK, ...; warp shuffle tree; 8 warp sums in order
+    {
+        double acc[NQ];
+#pragma unroll
+        for (int i = 0; i < NQ; i++) acc[i] = 0.0;
+        for (unsigned int bidx = threadIdx.x; bidx < gridDim.x; bidx += VBLOCK) {
+            double t[NQ];
+#pragma unroll
+            for (int i = 0; i < NQ; i++) t[i] = __ldcg(part + (size_t)bidx * 8 + i);  // all in flight together
+#pragma unroll
+            for (int i = 0; i < NQ; i++) acc[i] += t[i];
+        }
+#pragma unroll
+        for (int i = 0; i < NQ; i++) {
+            const double v = warp_sum(acc[i]);
+            if (lane == 0) s_w[i][w] = v;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < NQ) {
+        double s = 0.0;
+        for (int j = 0; j < VBLOCK / 32; j++) s += s_w[threadIdx.x][j];
+        s_tot[threadIdx.x] = s;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NQ; i++) q[i] = s_tot[i];
+    __syncthreads();
+}
+
+template <bool P2P>
+__global__ void __launch_bounds__(VBLOCK)
+k_cg_tail_hsde(Lay L, MVView V, P2PView X, const double *__restrict__ c, const double *__restrict__ b,
+               double *__restrict__ sol, double *__restrict__ r, double *__restrict__ p, double *__restrict__ Ap,
+               Ctrl *ctrl, GridBar gb)
+{
+    if (cg_skip(ctrl)) return;
+    const unsigned int base = *gb.base;
+    unsigned int nbar = 0;
+    const int64_t LP = L.LP, oy = L.n_pad, ot = L.n_pad + L.m_pad;
+    const int64_t stride = (int64_t)gridDim.x * VBLOCK, e0 = (int64_t)blockIdx.x * VBLOCK + threadIdx.x;
+    const double rn = ctrl->rn, tol = ctrl->tol;
+    const int iter = ctrl->iter, max_iters = ctrl->max_iters;
+    unsigned int epoch = 0;
+    int par = 0;
+    if (P2P) {
+        // ---- exchange, phase 1: fold the local partials into this rank's slot, publish, wait for the peers ----
+        epoch = *X.epoch + 1u;
+        par = (int)(epoch & 1u);
+        double *mine = reinterpret_cast<double *>(X.peer[X.rank] + X.buf_off) + (size_t)par * X.slot_doubles;
+        const int64_t rb = X.row_begin[X.rank], ml = X.m_local[X.rank];
+        for (int64_t e = e0; e < ot; e += stride) {
+#pragma unroll
+            for (int v = 0; v < 2; v++) {
+                if (e < oy) {
+                    mine[(size_t)v * L.n_pad + e] = e < L.n ? mv_atw(V, v, e) : 0.0;
+                } else {
+                    const int64_t row = e - oy, lr = row - rb;
+                    if (lr >= 0 && lr < ml) mine[(size_t)2 * L.n_pad + (size_t)v * L.m_pad + row] = mv_ax(V, v, lr);
+                }
+            }
+        }
+        // Block i of every rank owns the same entries, so the hand-shake is block to block: publish this
+        // block's part of the slot to every peer, wait for the same block of every peer.
+        __syncthreads();
+        if (threadIdx.x == 0) __threadfence_system();  // cumulative: the whole block's slot writes
+        __syncthreads();
+        if (threadIdx.x < X.nranks) {
+            st_release_sys_u32(reinterpret_cast<unsigned int *>(X.peer[threadIdx.x] + X.bflags_off) +
+                                   (size_t)X.rank * P2P_MAX_BLOCKS + blockIdx.x,
+                               epoch);
+            const unsigned int *f = reinterpret_cast<const unsigned int *>(X.peer[X.rank] + X.bflags_off) +
+                                    (size_t)threadIdx.x * P2P_MAX_BLOCKS + blockIdx.x;
+            while ((int)(ld_acquire_sys_u32(f) - epoch) < 0) {
+            }
+        }
+        __syncthreads();
+    }
+    // ---- Ap = [I Q'; Q -I] p and the dot products (k2_kkt_hsde<K2_AP>) ----
+    const double tau1 = p[ot], tau2 = p[LP + ot];
+    double q[5] = {0, 0, 0, 0, 0};
+    for (int64_t e = e0; e < ot; e += stride) {
+        double o1 = 0.0, o2 = 0.0;
+        const double i1 = p[e], i2 = p[LP + e];
+        if (e < oy) {
+            if (e < L.n) {
+                double w0, w1;
+                if (P2P) {
+                    double acc[2];
+                    p2p_gather_sum<2>(X, par, e, L.n_pad, acc);
+                    w0 = acc[0];
+                    w1 = acc[1];
+                } else {
+                    w0 = mv_atw(V, 0, e);
+                    w1 = mv_atw(V, 1, e);
+                }
+                const double cj = c[e];
+                const double q1 = add_(w0, mul_(tau1, cj));
+                const double q2 = add_(w1, mul_(tau2, cj));
+                o1 = add_(-q2, i1);
+                o2 = sub_(q1, i2);
+                q[0] = fma(cj, i1, q[0]);
+                q[2] = fma(cj, i2, q[2]);
+            }
+        } else {
+            const int64_t i = e - oy;
+            if (i < L.m) {
+                double a0, a1;
+                if (P2P) {
+                    int owner = 0;
+                    for (int rk = 0; rk < X.nranks; rk++)
+                        if (i >= X.row_begin[rk] && i < X.row_begin[rk] + X.m_local[rk]) owner = rk;
+                    const double *src =
+                        reinterpret_cast<const double *>(X.peer[owner] + X.buf_off) + (size_t)par * X.slot_doubles;
+                    a0 = ld_sys_f64(src + 2 * L.n_pad + i);
+                    a1 = ld_sys_f64(src + 2 * L.n_pad + L.m_pad + i);
+                } else {
+                    a0 = mv_ax(V, 0, i);
+                    a1 = mv_ax(V, 1, i);
+                }
+                const double bi = b[i];
+                const double q1 = -sub_(a0, mul_(tau1, bi));
+                const double q2 = -sub_(a1, mul_(tau2, bi));
+                o1 = add_(-q2, i1);
+                o2 = sub_(q1, i2);
+                q[1] = fma(bi, i1, q[1]);
+                q[3] = fma(bi, i2, q[3]);
+            }
+        }
+        Ap[e] = o1;
+        Ap[LP + e] = o2;
+        q[4] = fma(o1, i1, q[4]);
+        q[4] = fma(o2, i2, q[4]);
+    }
+    grid_allreduce<5>(q, gb.part, gb, nbar, base);
+    const double q1t = sub_(-q[0], q[1]);  // HSDEAffine.jl:57
+    const double q2t = sub_(-q[2], q[3]);
+    const double o1t = add_(-q2t, tau1);
+    const double o2t = sub_(q1t, tau2);
+    const double pAp = q[4] + o1t * tau1 + o2t * tau2;
+    const double alpha = rn / pAp;  // cg :39
+    // ---- x += alpha p ; r -= alpha Ap ; ||r||  (k3_cg_update) ----
+    double q2r[1] = {0.0};
+    for (int64_t e = e0; e < LP; e += stride) {
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int64_t g = e + h * LP;
+            double ape = Ap[g];
+            if (e == ot) ape = h == 0 ? o1t : o2t;
+            sol[g] = add_(sol[g], mul_(alpha, p[g]));
+            const double re = sub_(r[g], mul_(alpha, ape));
+            r[g] = re;
+            q2r[0] = fma(re, re, q2r[0]);
+        }
+    }
+    grid_allreduce<1>(q2r, gb.part + (size_t)gridDim.x * 8, gb, nbar, base);
+    const double rr = q2r[0];
+    const double rnorm = sqrt(rr);
+    const bool stop = rnorm <= tol || iter >= max_iters;  // cg :42
+    const double beta = rr / rn;
+    if (!stop)
+        for (int64_t e = e0; e < LP; e += stride) {  // p = beta p + r  (:49-50)
+            p[e] = add_(mul_(beta, p[e]), r[e]);
+            p[LP + e] = add_(mul_(beta, p[LP + e]), r[LP + e]);
+        }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        Ap[ot] = o1t;
+        Ap[LP + ot] = o2t;
+        ctrl->alpha = alpha;
+        ctrl->rnorm = rnorm;
+        if (stop) {
+            ctrl->done = 1;
+            if (iter >= max_iters) ctrl->warn_maxit = 1;  // :53
+        } else {
+            ctrl->rn = rr;
+            ctrl->beta = beta;
+            ctrl->iter = iter + 1;
+        }
+    }
+    // ---- exit: the last block re-arms the barrier base (and the exchange epoch / tickets) ----
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(gb.exit_ticket, 1u) == gridDim.x - 1) {
+            *gb.exit_ticket = 0u;
+            *gb.base = base + nbar * gridDim.x;
+            if (P2P) *X.epoch = epoch;
+            __threadfence();
+        }
+    }
+}
 #endif  // __CUDACC__
 
 }  // namespace fos

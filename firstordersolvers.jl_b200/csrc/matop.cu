@@ -147,6 +147,79 @@ void MatOp::init_sparse(int64_t m_, int64_t n_, const int64_t *colptr, const int
 MatOp::~MatOp()
 {
     for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
+    p2p_close();
+}
+
+// ---------------------------------------------------------------------------------------
+// fused exchange over peer memory: region = header | flags[nranks] | slot[2]
+// ---------------------------------------------------------------------------------------
+static int64_t p2p_flags_off() { return (int64_t)sizeof(P2PHeader); }
+static int64_t p2p_bflags_off(int nranks) { return ru(p2p_flags_off() + (int64_t)nranks * P2P_FLAG_STRIDE * 4, 256); }
+static int64_t p2p_buf_off(int nranks)
+{
+    return ru(p2p_bflags_off(nranks) + (int64_t)nranks * P2P_MAX_BLOCKS * 4, 256);
+}
+
+void MatOp::p2p_export(uint8_t *handle_out)
+{
+    FOS_REQUIRE(kind == 1 && nranks > 1, "the peer-memory exchange needs a row-sharded dense problem (fos_comm_init + "
+                                         "fos_load_conic_dense)");
+    FOS_REQUIRE(nranks <= P2P_MAX_RANKS, "too many ranks for the peer-memory exchange");
+    static_assert(sizeof(cudaIpcMemHandle_t) == FOS_IPC_HANDLE_BYTES, "IPC handle size");
+    p2p_close();
+    const int64_t slot = 2 * (n_pad + m_pad);
+    const size_t bytes = (size_t)p2p_buf_off(nranks) + (size_t)2 * slot * 8;
+    p2p_region.alloc(bytes);  // zeroed
+    P2PHeader hd;
+    memset(&hd, 0, sizeof(hd));
+    hd.row_begin = row_begin;
+    hd.m_local = m_local;
+    FOS_CUDA(cudaMemcpy(p2p_region.p, &hd, sizeof(hd), cudaMemcpyHostToDevice));
+    p2p_local.alloc(4);
+    cudaIpcMemHandle_t hdl;
+    FOS_CUDA(cudaIpcGetMemHandle(&hdl, p2p_region.p));
+    memcpy(handle_out, &hdl, sizeof(hdl));
+}
+
+void MatOp::p2p_import(const uint8_t *handles)
+{
+    FOS_REQUIRE(p2p_region.p != nullptr, "fos_comm_p2p_export must precede fos_comm_p2p_import");
+    memset(&p2p, 0, sizeof(p2p));
+    p2p.nranks = nranks;
+    p2p.rank = rank;
+    p2p.flags_off = p2p_flags_off();
+    p2p.buf_off = p2p_buf_off(nranks);
+    p2p.bflags_off = p2p_bflags_off(nranks);
+    p2p.slot_doubles = 2 * (n_pad + m_pad);
+    p2p.epoch = p2p_local.p;
+    p2p.tickets = p2p_local.p + 1;
+    for (int r = 0; r < nranks; r++) {
+        void *base = nullptr;
+        if (r == rank) {
+            base = p2p_region.p;
+        } else {
+            cudaIpcMemHandle_t hdl;
+            memcpy(&hdl, handles + (size_t)r * FOS_IPC_HANDLE_BYTES, sizeof(hdl));
+            cudaError_t e = cudaIpcOpenMemHandle(&base, hdl, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess)
+                throw Error(FOS_ERR_COMM, std::string("cudaIpcOpenMemHandle (rank ") + std::to_string(r) +
+                                              ") failed: " + cudaGetErrorString(e));
+            p2p_opened.push_back(base);
+        }
+        p2p.peer[r] = reinterpret_cast<unsigned char *>(base);
+        P2PHeader hd;
+        FOS_CUDA(cudaMemcpy(&hd, base, sizeof(hd), cudaMemcpyDeviceToHost));
+        p2p.row_begin[r] = hd.row_begin;
+        p2p.m_local[r] = hd.m_local;
+    }
+    p2p_on = true;
+}
+
+void MatOp::p2p_close()
+{
+    for (void *p : p2p_opened) cudaIpcCloseMemHandle(p);
+    p2p_opened.clear();
+    p2p_on = false;
 }
 void MatOp::prof_begin(int NV, cudaStream_t st)
 {
@@ -177,6 +250,13 @@ void MatOp::prof_collect()
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, ev_pool[k], ev_pool[k + 1]) != cudaSuccess) continue;
         const int nv = ev_nv[k / 2];
+        if (nv == 0) {  // fused CG tail: predicated no-ops take ~2 us
+            if (ms > 0.004f) {
+                prof_ms[0] += ms;
+                prof_n[0]++;
+            }
+            continue;
+        }
         if ((double)ms < min_ms) {
             prof_skipped++;
             continue;
@@ -220,7 +300,8 @@ MVView MatOp::view_full(int NV, const double *ax, const double *atw) const
 }
 
 template <int NV>
-MVView MatOp::run_t(const double *const *X, const double *const *W, const int32_t *skip, cudaStream_t st)
+MVView MatOp::run_t(const double *const *X, const double *const *W, const int32_t *skip, cudaStream_t st,
+                    bool defer_exchange)
 {
     K1Args<NV> a;
     for (int v = 0; v < NV; v++) {
@@ -275,7 +356,17 @@ MVView MatOp::run_t(const double *const *X, const double *const *W, const int32_
         V = view_full(NV, full_ax.p, full_atw.p);
     }
     if (stats && skip == nullptr) stats->total_passes++;  // predicated CG launches are counted by cg_solve
-    if (nranks > 1) {
+    if (nranks > 1 && p2p_on && defer_exchange) {
+        // the consumer (k_cg_tail_hsde<true>) folds, publishes and gathers itself
+    } else if (nranks > 1 && p2p_on) {
+        // ONE kernel: fold the local partials, publish, gather from the peers over NVLink (k1_exchange_p2p).
+        // Its blocks wait for each other and for the peers, so the grid must be co-resident.
+        const int64_t total = n_pad + m_pad;
+        int grid = (int)std::min<int64_t>((total + VBLOCK - 1) / VBLOCK, 2 * (int64_t)num_sms);
+        k1_exchange_p2p<NV><<<grid, VBLOCK, 0, st>>>(V, p2p, n, n_pad, m_pad, xbuf.p, skip);
+        if (stats) stats->launches++;
+        V = view_full(NV, xbuf.p + (size_t)NV * n_pad, xbuf.p);
+    } else if (nranks > 1) {
         // fold the local partials into the exchange buffer, all-reduce over NVLink, hand out
         // a complete view.  Rows owned by other ranks are zero in the local contribution.
         const int64_t total = n_pad + m_pad;
@@ -290,11 +381,12 @@ MVView MatOp::run_t(const double *const *X, const double *const *W, const int32_
     return V;
 }
 
-MVView MatOp::run(int NV, const double *const *X, const double *const *W, const int32_t *skip, cudaStream_t st)
+MVView MatOp::run(int NV, const double *const *X, const double *const *W, const int32_t *skip, cudaStream_t st,
+                  bool defer_exchange)
 {
     FOS_REQUIRE(kind != 0, "matrix not loaded");
     prof_begin(NV, st);
-    MVView V = (NV == 1) ? run_t<1>(X, W, skip, st) : run_t<2>(X, W, skip, st);
+    MVView V = (NV == 1) ? run_t<1>(X, W, skip, st, defer_exchange) : run_t<2>(X, W, skip, st, defer_exchange);
     prof_end(st);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) throw Error(FOS_ERR_CUDA, std::string("mat-vec launch failed: ") + cudaGetErrorString(e));

@@ -31,8 +31,11 @@ constexpr int PL_TILE = 64;
 constexpr int PL_JC = 32;  // columns of W per shared-memory chunk of the final product
 
 struct PsdLargeCtl {  // one per cone, zeroed before every launch
-    unsigned int bar;
+    unsigned int bar;   // arrival counter of the group barrier
     int sweeps;
+    unsigned int pad0_[30];
+    unsigned int flag;  // last completed barrier target, on its own cache line (the waiters poll this one)
+    unsigned int pad1_[31];
     unsigned long long maxcos[PL_MAX_SWEEPS];  // bit pattern of the largest |cos| seen in sweep k
 };
 
@@ -71,16 +74,23 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p)
     return v;
 }
 
-// barrier among the CT CTAs of one cone: monotonically increasing arrival counter
-__device__ __forceinline__ void group_barrier(unsigned int *bar, unsigned int &epoch, unsigned int CT)
+// barrier among the CT CTAs of one cone: one atomic per CTA on the arrival counter; the last arriver
+// publishes the target on a separate cache line, which the others poll with relaxed loads
+__device__ __forceinline__ void group_barrier(PsdLargeCtl *ctl, unsigned int &epoch, unsigned int CT)
 {
     __syncthreads();
     if (threadIdx.x == 0) {
         epoch++;
-        __threadfence();
-        atomicAdd(bar, 1u);
         const unsigned int target = epoch * CT;
-        while (ld_acquire_u32(bar) < target) {
+        __threadfence();
+        const unsigned int old = atomicAdd(&ctl->bar, 1u);
+        if (old + 1u == target) {
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&ctl->flag), "r"(target) : "memory");
+        } else {
+            unsigned int v;
+            do {
+                asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(&ctl->flag) : "memory");
+            } while (v < target);
         }
         __threadfence();
     }
@@ -96,10 +106,12 @@ __device__ __forceinline__ void bulk_store_1d(void *gdst, const void *ssrc, uint
 
 template <int DK>
 struct PLCfg {
-    static constexpr int BS = DK <= 8 ? 16 : 8;  // columns per block == warps per CTA
+    static constexpr int BS = 8;                 // columns per block == warps per CTA
     static constexpr int THREADS = 32 * BS;
     static constexpr int DS = 64 * DK;           // padded column length
-    static constexpr size_t SMEM = (size_t)2 * BS * DS * sizeof(double);
+    static constexpr size_t COLS_BYTES = (size_t)2 * BS * DS * sizeof(double);
+    static constexpr size_t PROD_BYTES = (size_t)2 * 32 * 64 * sizeof(double);  // Wi / Wk chunks of the final product
+    static constexpr size_t SMEM = COLS_BYTES > PROD_BYTES ? COLS_BYTES : PROD_BYTES;
 };
 
 // one warp: orthogonalise columns P and Q (shared memory, DS doubles each).  n2p / n2q hold the squared
@@ -145,6 +157,46 @@ __device__ __forceinline__ void rotate_pair(double *__restrict__ cp, double *__r
         *n2p = fma(-t, ga, al);
         *n2q = fma(t, ga, be);
     }
+}
+
+// Same rotation with column P held in REGISTERS by its warp for all BS rounds of a step (shared memory
+// bandwidth, not FP64, bounds the sweep: this halves the LDS/STS traffic).  al = ||P||^2 travels with it.
+template <int DK>
+__device__ __forceinline__ void rotate_pair_reg(double2 (&P)[DK], double &al, double *__restrict__ cq, double *n2q,
+                                                int lane, double tiny2, double &lmax2)
+{
+    double2 Q[DK];
+    double g0 = 0.0, g1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < DK; k++) {
+        Q[k] = *reinterpret_cast<const double2 *>(cq + 64 * k + 2 * lane);
+        g0 = fma(P[k].x, Q[k].x, g0);
+        g1 = fma(P[k].y, Q[k].y, g1);
+    }
+    const double ga = warp_sum(g0 + g1);
+    const double be = *n2q;
+    const double ab = al * be;
+    if (!(ab > tiny2)) return;
+    const double g2 = ga * ga;
+    lmax2 = fmax(lmax2, g2 / ab);
+    if (!(g2 > 1e-30 * ab)) return;
+    const double delta = be - al;
+    const double hyp = sqrt(fma(delta, delta, 4.0 * g2));
+    const double t = (delta >= 0.0 ? 2.0 : -2.0) * ga / (fabs(delta) + hyp);
+    const double c = rsqrt(fma(t, t, 1.0));
+    const double s = c * t;
+#pragma unroll
+    for (int k = 0; k < DK; k++) {
+        double2 pn, qn;
+        pn.x = fma(-s, Q[k].x, c * P[k].x);
+        pn.y = fma(-s, Q[k].y, c * P[k].y);
+        qn.x = fma(s, P[k].x, c * Q[k].x);
+        qn.y = fma(s, P[k].y, c * Q[k].y);
+        P[k] = pn;
+        *reinterpret_cast<double2 *>(cq + 64 * k + 2 * lane) = qn;
+    }
+    if (lane == 0) *n2q = fma(t, ga, be);
+    al = fma(-t, ga, al);
 }
 
 template <int DK>
@@ -221,7 +273,7 @@ __global__ void __launch_bounds__(PLCfg<DK>::THREADS, 1) k5_psd_hestenes(const P
             G[(size_t)j * DS + i] = (i == j && i < d) ? v + sigma : v;
         }
     }
-    group_barrier(&ctl->bar, epoch, a.CT);
+    group_barrier(ctl, epoch, a.CT);
 
     // ---- phase 2: block Jacobi sweeps ----
     constexpr uint32_t BLK_BYTES = (uint32_t)(BS * DS * sizeof(double));
@@ -265,10 +317,20 @@ __global__ void __launch_bounds__(PLCfg<DK>::THREADS, 1) k5_psd_hestenes(const P
                     __syncthreads();
                 }
             }
-            for (int r = 0; r < BS; r++) {
-                const int q = BS + ((warp + r) & (BS - 1));
-                rotate_pair<DK>(cols + (size_t)warp * DS, cols + (size_t)q * DS, s_n2 + warp, s_n2 + q, lane, tiny2, lmax);
-                __syncthreads();
+            {
+                // cross pairs: warp w keeps column w of the first block in registers through the BS rounds
+                double2 P[DK];
+                double *cp = cols + (size_t)warp * DS;
+#pragma unroll
+                for (int k = 0; k < DK; k++) P[k] = *reinterpret_cast<const double2 *>(cp + 64 * k + 2 * lane);
+                double al = s_n2[warp];
+                for (int r = 0; r < BS; r++) {
+                    const int q = BS + ((warp + r) & (BS - 1));
+                    rotate_pair_reg<DK>(P, al, cols + (size_t)q * DS, s_n2 + q, lane, tiny2, lmax);
+                    __syncthreads();
+                }
+#pragma unroll
+                for (int k = 0; k < DK; k++) *reinterpret_cast<double2 *>(cp + 64 * k + 2 * lane) = P[k];
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncthreads();
@@ -290,7 +352,7 @@ __global__ void __launch_bounds__(PLCfg<DK>::THREADS, 1) k5_psd_hestenes(const P
                     atomicMax(&ctl->maxcos[sweep], (unsigned long long)__double_as_longlong(mx));
                 }
             }
-            group_barrier(&ctl->bar, epoch, a.CT);
+            group_barrier(ctl, epoch, a.CT);
         }
         sweeps_done = sweep + 1;
         const double mx = __longlong_as_double((long long)*((volatile unsigned long long *)&ctl->maxcos[sweep]));
@@ -369,14 +431,14 @@ __global__ void __launch_bounds__(PLCfg<DK>::THREADS, 1) k5_psd_hestenes(const P
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
             asm volatile("fence.proxy.async;" ::: "memory");
         }
-        group_barrier(&ctl->bar, epoch, a.CT);
+        group_barrier(ctl, epoch, a.CT);
     }
 
     // ---- phase 4: P = W W' over the columns with lambda > 0 ----
     if (warp == 0) {
         int cnt = 0;
         for (int base = 0; base < a.d_pad; base += 32) {
-            const bool pos = lam_g[base + lane] > 0.0;
+            const bool pos = base + lane < a.d_pad && lam_g[base + lane] > 0.0;
             const unsigned int m = __ballot_sync(0xffffffffu, pos);
             if (pos) s_plist[cnt + __popc(m & ((1u << lane) - 1u))] = base + lane;
             cnt += __popc(m);
@@ -477,7 +539,7 @@ void psd_project_large(Handle *h, ConeSet &K, const double *in, double *projbuf)
         }
     if (DK == 0)
         throw Error(FOS_ERR_UNSUPPORTED, "SDP cone of order " + std::to_string(dmax) + " exceeds the supported 1024");
-    const int bs = DK <= 8 ? 16 : 8;
+    const int bs = 8;
     const int dS = 64 * DK;
     PsdLargeArgs a;
     a.d_pad = (int)ru(dmax, 2 * bs);

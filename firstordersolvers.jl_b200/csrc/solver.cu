@@ -35,6 +35,13 @@ void Handle::create(int dev)
     rb.counter = red_counter.p;
     A.num_sms = num_sms;
     A.stats = &stats;
+    gb_ctr.alloc(96);
+    gb_part.alloc((size_t)2 * 2 * num_sms * 8);
+    gbar.count = gb_ctr.p;
+    gbar.base = gb_ctr.p + 1;
+    gbar.exit_ticket = gb_ctr.p + 2;
+    gbar.flag = gb_ctr.p + 64;
+    gbar.part = gb_part.p;
 }
 
 Handle::~Handle()
@@ -355,12 +362,12 @@ void Handle::load_affine(int64_t am, int64_t an, const double *b, const double *
 // operators
 // =======================================================================================
 // one pass over A feeding the KKT product of v
-MVView Handle::kkt_pass(const double *v, const int32_t *skip)
+MVView Handle::kkt_pass(const double *v, const int32_t *skip, bool defer_exchange)
 {
     if (L.form == 0) {
         const double *X[2] = {v, v + L.LP};
         const double *W[2] = {v + L.n_pad, v + L.LP + L.n_pad};
-        return A.run(2, X, W, skip, stream);
+        return A.run(2, X, W, skip, stream, defer_exchange);
     }
     const double *X[1] = {v};
     const double *W[1] = {L.form == 2 ? v : v + L.n_pad};
@@ -390,6 +397,24 @@ void Handle::q_mul(const double *Bp, double *Yp, bool transpose)
 void Handle::cg_enqueue_iteration()
 {
     const int32_t *skip = &d_ctrl.p->done;
+    if (L.form == 0 && fuse_tail) {
+        // K1 + ONE cooperative kernel for the rest of the iteration (k_cg_tail_hsde)
+        const bool p2p = A.nranks > 1 && A.p2p_on;
+        MVView V = kkt_pass(p.p, skip, /*defer_exchange=*/p2p);
+        // identical on every rank (block i of all ranks owns the same entries); co-resident by construction
+        const int grid = (int)std::min<int64_t>((L.LP + VBLOCK - 1) / VBLOCK, std::min<int64_t>((int64_t)num_sms, P2P_MAX_BLOCKS));
+        const double *cptr = d_c.p, *bptr = d_b.p;
+        double *solp = sol.p, *rp = r.p, *pp = p.p, *App = Ap.p;
+        Ctrl *cp = d_ctrl.p;
+        void *args[] = {(void *)&L, (void *)&V, (void *)&A.p2p, (void *)&cptr, (void *)&bptr, (void *)&solp,
+                        (void *)&rp,  (void *)&pp, (void *)&App, (void *)&cp, (void *)&gbar};
+        const void *fn = p2p ? (const void *)k_cg_tail_hsde<true> : (const void *)k_cg_tail_hsde<false>;
+        A.prof_begin(0, stream);
+        FOS_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(VBLOCK), args, 0, stream));
+        A.prof_end(stream);
+        stats.launches++;
+        return;
+    }
     MVView V = kkt_pass(p.p, skip);
     if (L.form == 0)
         FOS_LAUNCH(this, k2_kkt_hsde<K2_AP>, vgrid(L.LP), VBLOCK, 0, L, V, p.p, d_c.p, d_b.p, Ap.p, nullptr, nullptr,

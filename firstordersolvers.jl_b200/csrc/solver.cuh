@@ -98,6 +98,15 @@ struct MatOp {
     int nranks = 1, rank = 0;
     void *comm = nullptr;
     DevBuf<double> xbuf;
+    // fused exchange over NVLink peer memory (CUDA IPC, one process per GPU): k1_exchange_p2p
+    DevBuf<unsigned char> p2p_region;
+    DevBuf<unsigned int> p2p_local;  // [0] epoch, [1..2] tickets
+    P2PView p2p{};
+    bool p2p_on = false;
+    std::vector<void *> p2p_opened;
+    void p2p_export(uint8_t *handle_out);
+    void p2p_import(const uint8_t *handles);
+    void p2p_close();
 
     int impl = 0;  // 0 TMA, 1 plain
     int num_sms = 148;
@@ -122,10 +131,14 @@ struct MatOp {
                      int64_t base, cudaStream_t st);
     double bytes_per_pass() const;
     // Runs one pass; X[v] have n_pad entries, W[v] have m_pad entries (global rows).
-    MVView run(int NV, const double *const *X, const double *const *W, const int32_t *skip, cudaStream_t st);
+    // defer_exchange: with the peer-memory exchange enabled, return the LOCAL partial view and leave the
+    // exchange to the consumer kernel (k_cg_tail_hsde<true>)
+    MVView run(int NV, const double *const *X, const double *const *W, const int32_t *skip, cudaStream_t st,
+               bool defer_exchange = false);
 
     template <int NV>
-    MVView run_t(const double *const *X, const double *const *W, const int32_t *skip, cudaStream_t st);
+    MVView run_t(const double *const *X, const double *const *W, const int32_t *skip, cudaStream_t st,
+                 bool defer_exchange);
     MVView view_full(int NV, const double *ax, const double *atw) const;
 };
 
@@ -204,7 +217,7 @@ struct Handle {
     int num_sms = 148;
     std::string err;
     // options
-    int matvec_impl = 0, grid_ctas = 0, cg_batch = 0, fuse_rhs = 1, batch_ctas = 0;
+    int matvec_impl = 0, grid_ctas = 0, cg_batch = 0, fuse_rhs = 1, batch_ctas = 0, fuse_tail = 1;
     // problem
     bool loaded = false;
     Lay L{};
@@ -233,6 +246,10 @@ struct Handle {
     DevBuf<double> red_partials;
     DevBuf<unsigned int> red_counter;
     RedBuf rb{};
+    DevBuf<unsigned int> gb_ctr;  // fused CG tail: grid-barrier counters {count, base, exit ticket}
+    DevBuf<double> gb_part;
+    GridBar gbar{};
+    int tail_grid = 0;
     DevBuf<double> d_recs;
     int rec_cap = 0;
     DevBuf<double> d_stage;
@@ -265,7 +282,7 @@ struct Handle {
     void pack_from_host(const double *z, double *dst);
     void unpack_to_host(const double *src, double *z);
     // operators
-    MVView kkt_pass(const double *v, const int32_t *skip);
+    MVView kkt_pass(const double *v, const int32_t *skip, bool defer_exchange = false);
     void kkt_mul(const double *in, double *out);
     void q_mul(const double *Bp, double *Yp, bool transpose);
     void s1_prox(const double *xin);

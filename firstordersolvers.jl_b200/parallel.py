@@ -66,3 +66,24 @@ def init_comm(handle, rank: int, nranks: int, comm_id: bytes):
     """fos_comm_init on a ``Handle`` (before loading the problem)."""
     arr = (C.c_uint8 * _lib.FOS_COMM_ID_BYTES).from_buffer_copy(comm_id)
     handle.ck(handle.L.fos_comm_init(handle.h, rank, nranks, arr))
+
+
+def enable_p2p_exchange(handle, rank: int, nranks: int, dist=None):
+    """After ``fos_load_conic_dense`` on every rank: export this rank's CUDA-IPC exchange slot,
+    all-gather the 64-byte handles through ``torch.distributed`` (plumbing only) and import the
+    table -- from then on every pass over A uses the fused peer-memory exchange kernel instead of
+    fold + ncclAllReduce."""
+    import torch
+    if dist is None:
+        import torch.distributed as dist
+    arr = (C.c_uint8 * _lib.FOS_IPC_HANDLE_BYTES)()
+    handle.ck(handle.L.fos_comm_p2p_export(handle.h, arr))
+    mine = torch.from_numpy(np.frombuffer(bytes(arr), dtype=np.uint8).copy())
+    if dist.get_backend() == "nccl":
+        mine = mine.cuda()
+    table = [torch.empty_like(mine) for _ in range(nranks)]
+    dist.all_gather(table, mine)
+    flat = np.concatenate([t.cpu().numpy() for t in table]).astype(np.uint8)
+    buf = (C.c_uint8 * (nranks * _lib.FOS_IPC_HANDLE_BYTES)).from_buffer_copy(flat.tobytes())
+    handle.ck(handle.L.fos_comm_p2p_import(handle.h, buf))
+    dist.barrier()

@@ -99,6 +99,10 @@ const char *fos_last_error(fos_handle_t h);
  *   "fuse_rhs"     1 (default) = fold the right-hand-side product of the affine projection into the
  *                  initial CG residual (k+1 passes over A per projection instead of k+2; same
  *                  mathematics, sums associated differently); 0 = build rhs in the reference's order
+ *   "fuse_tail"    1 (default) = conic form: everything of a CG iteration after the pass over A (peer
+ *                  exchange, KKT epilogue, both dot products, x/r/p updates, stop test) runs in ONE
+ *                  cooperative kernel; 0 = one kernel per step (K2, K3 update, K3 direction)
+ *   "exchange_impl" multi-GPU: 1 = fused peer-memory exchange (after fos_comm_p2p_import), 0 = NCCL
  *   "profile_matvec" 1 = CUDA events around every mat-vec launch (read back with fos_get_info)
  *   "batch_ctas"   persistent CTAs of the batch kernel (default = #SMs)
  *   "use_graphs"   reserved                                                                */
@@ -111,6 +115,14 @@ int32_t fos_set_option(fos_handle_t h, const char *key, double value);
 #define FOS_COMM_ID_BYTES 128
 int32_t fos_comm_unique_id(uint8_t *id_out /* FOS_COMM_ID_BYTES */);
 int32_t fos_comm_init(fos_handle_t h, int32_t rank, int32_t nranks, const uint8_t *id /* FOS_COMM_ID_BYTES */);
+/* Fused exchange over NVLink peer memory (optional, after fos_load_conic_dense on every rank): replaces
+ * the fold kernel + ncclAllReduce of every pass over A by ONE kernel that publishes this rank's partial
+ * sums in a CUDA-IPC-shared slot and gathers the peers' slots with direct loads over NVLink, summing
+ * in rank order (bitwise identical results on every rank).  Each rank exports a 64-byte handle, the
+ * caller all-gathers them (rank order) and hands the table to every rank.  One process per GPU. */
+#define FOS_IPC_HANDLE_BYTES 64
+int32_t fos_comm_p2p_export(fos_handle_t h, uint8_t *handle_out /* FOS_IPC_HANDLE_BYTES */);
+int32_t fos_comm_p2p_import(fos_handle_t h, const uint8_t *handles /* nranks * FOS_IPC_HANDLE_BYTES */);
 
 /* ====================================================================================== */
 /* problem loading -- replaces loadproblem! (FOSSolverInterface.jl:27-64) + HSDE()        */
@@ -169,7 +181,7 @@ int32_t fos_set_state(fos_handle_t h, int32_t which, const double *buf, int64_t 
  * 7 kernel launches so far, 8 GAPP alpha_best of the last projected step; with the option
  * "profile_matvec" = 1: 9 / 10 summed milliseconds / count of 2-RHS mat-vec launches, 11 / 12 the
  * same for 1-RHS launches, 13 predicated no-op launches; 14 algorithmic bytes of one pass over A,
- * 15 number of SMs. */
+ * 15 number of SMs, 16 / 17 summed milliseconds / count of executed fused CG-tail launches. */
 int32_t fos_get_info(fos_handle_t h, int32_t which, double *out);
 /* Restores a scalar: which = 0 (S1.i), 2 (alpha12) or 3 (FISTA t). */
 int32_t fos_set_info(fos_handle_t h, int32_t which, double value);

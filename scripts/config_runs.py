@@ -144,35 +144,69 @@ def run_c4(args):
 
 
 def run_c3(args):
+    """C3: min t s.t. ||D x - d|| <= t, ||x|| <= rho, D md x nx dense; K1 = SOC(md+1) + SOC(nx+1); GAPA().
+    Under torchrun the (md+nx+2) x (nx+1) matrix is row-sharded over the ranks."""
     import ctypes as C
+    import os
     import torch
     import fos_b200 as fos
+    from fos_b200 import parallel
     from fos_b200.model import _cone_arrays, _d, _i32p, _i64p
-    dev = torch.device("cuda", 0)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
     md, nx = args.md, args.nx
     m, n = md + 1 + nx + 1, nx + 1
-    g = torch.Generator(device=dev)
-    g.manual_seed(3)
-    A = torch.zeros((m, n), dtype=torch.float64, device=dev)
-    A[0, 0] = -1.0
-    blk = 10000
-    for r0 in range(0, md, blk):
-        r1 = min(md, r0 + blk)
-        A[1 + r0:1 + r1, 1:] = -torch.randn((r1 - r0, nx), dtype=torch.float64, device=dev, generator=g) / np.sqrt(nx)
-    idx = torch.arange(nx, device=dev)
-    A[md + 2 + idx, 1 + idx] = -1.0
-    x0 = torch.randn(nx, dtype=torch.float64, device=dev, generator=g)
-    dvec = (-A[1:md + 1, 1:]) @ x0 + 0.1 * torch.randn(md, dtype=torch.float64, device=dev, generator=g)
+    r0, cnt = parallel.row_shard(m, rank, world)
+    A = torch.zeros((cnt, n), dtype=torch.float64, device=dev)
+    BLK = 1000
+    x0 = torch.randn(nx, dtype=torch.float64, device=dev, generator=torch.Generator(device=dev).manual_seed(33))
+    dloc = torch.zeros(m, dtype=torch.float64, device=dev)   # D x0 on the D rows owned here
+    for gi in range(r0, r0 + cnt):
+        pass  # (rows are filled block-wise below)
+    # global row 0: [-1 0]; rows 1..md: [0 -D]; row md+1: zeros; rows md+2..: [0 -I]
+    lo, hi = max(r0, 1), min(r0 + cnt, md + 1)      # D rows in this shard (global indices)
+    b0 = ((lo - 1) // BLK) * BLK
+    while lo < hi and b0 < hi - 1:
+        g = torch.Generator(device=dev)
+        g.manual_seed(3 * 1000003 + b0 // BLK)
+        blk = torch.randn((BLK, nx), dtype=torch.float64, device=dev, generator=g) / np.sqrt(nx)
+        s, e = max(b0, lo - 1), min(b0 + BLK, hi - 1)   # D-row indices (0-based inside D)
+        if e > s:
+            A[s + 1 - r0:e + 1 - r0, 1:] = -blk[s - b0:e - b0]
+            dloc[s + 1:e + 1] = blk[s - b0:e - b0] @ x0
+        b0 += BLK
+    if r0 == 0 and cnt > 0:
+        A[0, 0] = -1.0
+    lo2, hi2 = max(r0, md + 2), min(r0 + cnt, m)
+    if hi2 > lo2:
+        gi = torch.arange(lo2, hi2, device=dev)
+        A[gi - r0, 1 + (gi - (md + 2))] = -1.0
+    if world > 1:
+        dist.all_reduce(dloc)
+    noise = torch.randn(md, dtype=torch.float64, device=dev, generator=torch.Generator(device=dev).manual_seed(34))
+    dvec = dloc[1:md + 1] + 0.1 * noise
     rho = 0.5 * float(torch.linalg.norm(x0))
     b = np.concatenate([[0.0], -dvec.cpu().numpy(), [rho], np.zeros(nx)])
     c = np.zeros(n)
     c[0] = 1.0
     cones1, cones2 = [("SOC", md + 1), ("SOC", nx + 1)], [("Free", n)]
-    H = fos.Handle(0)
+    H = fos.Handle(local)
+    if world > 1:
+        cid = parallel.exchange_comm_id(rank, parallel.nccl_unique_id, dist)
+        parallel.init_comm(H, rank, world, cid)
     t1, l1 = _cone_arrays(cones1, m, "constraint")
     t2, l2 = _cone_arrays(cones2, n, "variable")
-    H.ck(H.L.fos_load_conic_dense(H.h, m, n, C.c_void_p(A.data_ptr()), n, 1, 0, m, _d(b), _d(c), len(t1), _i32p(t1),
+    H.ck(H.L.fos_load_conic_dense(H.h, m, n, C.c_void_p(A.data_ptr()), n, 1, r0, cnt, _d(b), _d(c), len(t1), _i32p(t1),
                                   _i64p(l1), len(t2), _i32p(t2), _i64p(l2)))
+    if world > 1 and args.exchange == "p2p":
+        parallel.enable_p2p_exchange(H, rank, world, dist)
     H.set_algorithm(fos.GAPA())
     H.set_initial_iterate()
     H.ck(H.L.fos_begin_solve(H.h))
@@ -180,16 +214,28 @@ def run_c3(args):
     W, K = args.warmup, args.iters
     H.run(1, W, 100, 1e-5)
     p0, cg0 = H.info("total_passes"), H.info("total_cg")
+    if world > 1:
+        dist.barrier()
     ms, (done, st, rec, _) = timed(torch, stream, lambda: H.run(W + 1, K, 100, 1e-5))
+    if world > 1:
+        tt = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
     passes, cgs = H.info("total_passes") - p0, H.info("total_cg") - cg0
     peak, peak_src = peak_hbm()
-    bytes_pass = H.info("bytes_per_pass")
+    bytes_pass = 8.0 * m * n
     gbs = passes * bytes_pass / (ms / 1e3) / 1e9
-    print(json.dumps({"config": "C3", "algorithm": "GAPA()", "m": m, "n": n, "matrix_gb": bytes_pass / 1e9,
-                      "iterations_timed": int(done), "ms_per_iteration": ms / max(done, 1),
-                      "iterations_per_s": done / (ms / 1e3), "cg_iterations_per_step": cgs / max(done, 1),
-                      "passes_over_A_per_step": passes / max(done, 1), "achieved_gbs": gbs, "peak_gbs": peak,
-                      "frac": gbs / peak, "peak_source": peak_src, "status": int(st)}), flush=True)
+    if rank == 0:
+        print(json.dumps({"config": "C3", "algorithm": "GAPA()", "n_gpus": world, "exchange": args.exchange if world > 1 else None,
+                          "m": m, "n": n, "matrix_gb": bytes_pass / 1e9,
+                          "iterations_timed": int(done), "ms_per_iteration": ms / max(done, 1),
+                          "iterations_per_s": done / (ms / 1e3), "cg_iterations_per_step": cgs / max(done, 1),
+                          "passes_over_A_per_step": passes / max(done, 1), "aggregate_gbs": gbs,
+                          "per_gpu_gbs": gbs / world, "peak_gbs_per_gpu": peak, "frac_per_gpu": gbs / world / peak,
+                          "peak_source": peak_src, "status": int(st),
+                          "last_p_d_g": [float(x) for x in rec[-1][1:4]] if len(rec) else None}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def main():
@@ -202,6 +248,7 @@ def main():
     ap.add_argument("--md", type=int, default=100000)
     ap.add_argument("--nx", type=int, default=20000)
     ap.add_argument("--cpu", action="store_true")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"])
     args = ap.parse_args()
     {"c3": run_c3, "c4": run_c4, "c5": run_c5}[args.config](args)
 

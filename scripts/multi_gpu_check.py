@@ -36,7 +36,10 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ok = True
-    for (m, n, scale, tol, alg) in ((1000, 2500, 0.1, 1e-10, "DR"), (2000, 1300, 1.0, 1e-4, "GAPA")):
+    cases = [(m, n, scale, tol, alg, ex) for ex in ("nccl", "p2p")
+             for (m, n, scale, tol, alg) in ((1000, 2500, 0.1, 1e-10, "DR"), (2000, 1300, 1.0, 1e-4, "GAPA"),
+                                             (333, 4100, 0.1, 1e-10, "FISTA"))]
+    for (m, n, scale, tol, alg, ex) in cases:
         P = problems.lasso_like(m, n, seed=7, scale=scale)
         A = np.asarray(P.A)
         r0, cnt = parallel.row_shard(m, rank, world)
@@ -44,10 +47,12 @@ def main():
         cid = parallel.exchange_comm_id(rank, parallel.nccl_unique_id, dist)
         parallel.init_comm(Hs, rank, world, cid)
         load_dense(Hs, P, A[r0:r0 + cnt], r0, cnt)
+        if ex == "p2p":  # fused peer-memory exchange kernel instead of fold + ncclAllReduce
+            parallel.enable_p2p_exchange(Hs, rank, world, dist)
         H1 = fos.Handle(local)  # unsharded reference on the same device
         load_dense(H1, P, A, 0, m)
         for H in (Hs, H1):
-            H.set_algorithm(fos.DR(0.5) if alg == "DR" else fos.GAPA())
+            H.set_algorithm({"DR": fos.DR(0.5), "GAPA": fos.GAPA(), "FISTA": fos.FISTA()}[alg])
             H.set_initial_iterate()
             H.ck(H.L.fos_begin_solve(H.h))
         v = np.random.default_rng(1).standard_normal(2 * (m + n + 1))
@@ -61,14 +66,29 @@ def main():
             Hs.set_info("s1_calls", H1.info("s1_calls"))
             if alg == "GAPA":
                 Hs.set_info("alpha12", H1.info("alpha12"))
+            if alg == "FISTA":
+                Hs.set_state("fista_y", H1.get_state("fista_y"))
+                Hs.set_info("fista_t", H1.info("fista_t"))
             H1.run(i, 1, 5, 1e-9)
             _, _, rec, _ = Hs.run(i, 1, 5, 1e-9)
             flips += Hs.info("cgiter") != H1.info("cgiter")
             worst = max(worst, rel_err(Hs.get_iterate(), H1.get_iterate()))
         good = e_kkt < 1e-12 and worst < tol and flips <= 2
         ok = ok and good
-        print(f"rank {rank}/{world} {m}x{n} {alg}: kkt_mul err {e_kkt:.2e}, worst lock-step deviation {worst:.2e}, "
+        print(f"rank {rank}/{world} {m}x{n} {alg} [{ex}]: kkt_mul err {e_kkt:.2e}, worst lock-step deviation {worst:.2e}, "
               f"CG count flips {flips} -> {'ok' if good else 'FAIL'}", flush=True)
+        # free-running: every rank must take identical decisions (replicated scalars from identical sums)
+        Hs.set_initial_iterate()
+        Hs.ck(Hs.L.fos_begin_solve(Hs.h))
+        done, st, rec, _ = Hs.run(1, 60, 10, 1e-7)
+        sig = torch.tensor([float(done), float(st), float(Hs.info("total_cg")), float(np.sum(Hs.get_iterate()))],
+                           dtype=torch.float64, device="cuda")
+        sigs = [torch.empty_like(sig) for _ in range(world)]
+        dist.all_gather(sigs, sig)
+        same = all(torch.equal(sigs[0], t) for t in sigs)
+        if not same:
+            ok = False
+            print(f"rank {rank}: free-running state differs across ranks [{ex}] {sigs}", flush=True)
         del Hs, H1
     flag = torch.tensor([0 if ok else 1], device="cuda")
     dist.all_reduce(flag)

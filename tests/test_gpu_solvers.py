@@ -179,6 +179,31 @@ def test_free_running_solve(fos, oracle, kind, alg, eps, max_iters):
     assert rel_err(xg, xo) < 1e-4
 
 
+@pytest.mark.parametrize("kind,alg", [("lasso", "DR"), ("nnls", "GAPA"), ("socls", "FISTA")])
+def test_fused_cg_tail_matches_kernel_per_step_path(fos, oracle, kind, alg):
+    """"fuse_tail" = 1 (one cooperative kernel per CG iteration after the pass over A) against
+    "fuse_tail" = 0 (K2 / K3 update / K3 direction as separate kernels): same CG iteration counts, iterates
+    equal up to the association of the two dot products; both in lock-step with the oracle at 1e-10."""
+    from fos_b200 import problems
+    P = _problem(problems, kind, WELL[kind])
+    O = oracle.OracleConic(P.c, P.A, P.b, P.constr_cones, P.var_cones)
+    Hs = [load_conic(fos, P, storage="dense", fuse_tail=f) for f in (1, 0)]
+    for H in Hs:
+        set_alg_both(fos, H, O, alg)
+        H.ck(H.L.fos_begin_solve(H.h))
+    O.set_iterate(O.initial_value())
+    for i in range(1, 26):
+        for H in Hs:
+            sync_state_from_oracle(H, O, alg)
+        O.run(i, 1, checki=5, eps=1e-12)
+        for H in Hs:
+            H.run(i, 1, 5, 1e-12)
+            assert H.info("cgiter") == O.cgiter
+            assert rel_err(H.get_iterate(), O.get_state("x")) < STEP_TOL
+        assert rel_err(Hs[0].get_iterate(), Hs[1].get_iterate()) < 1e-11
+    assert Hs[0].info("launches") < Hs[1].info("launches")
+
+
 def test_solve_tail_forced_check_and_getsol_side_effects(fos, oracle):
     """a-Q 1-3: forced final check iff the last iteration was not a check iteration; getsol runs one
     more CG solve that advances S1.i; a second solve! continues the tolerance schedule."""
