@@ -28,7 +28,7 @@ namespace {
 struct BK {
     const BatchArgs *a;
     int ct, NT, warp, lane;
-    double *tiles, *s_ax, *s_atw, *s_x, *s_red;
+    double *tiles, *s_ax, *s_atw, *s_x, *s_wv, *s_red;
     SocScale *s_soc;
     uint64_t *full, *empty;
     uint32_t t;  // tiles consumed so far by this CTA
@@ -88,6 +88,10 @@ __device__ __forceinline__ void bt_pass(BK &k, const double *X0, const double *X
         k.s_x[e] = X0[e];
         k.s_x[n_pad + e] = X1[e];
     }
+    for (int64_t e = k.ct; e < m_pad; e += k.NT) {  // W rides in shared memory too: 16 broadcast reads per tile
+        k.s_wv[e] = W0[e];
+        k.s_wv[m_pad + e] = W1[e];
+    }
     double2 ca[KP][2];
 #pragma unroll
     for (int kk = 0; kk < KP; kk++) ca[kk][0] = ca[kk][1] = make_double2(0.0, 0.0);
@@ -98,7 +102,7 @@ __device__ __forceinline__ void bt_pass(BK &k, const double *X0, const double *X
         const int row0 = tile * BT_TR;
 #pragma unroll
         for (int r = 0; r < BT_TR; r++) {
-            const double w0 = W0[row0 + r], w1 = W1[row0 + r];
+            const double w0 = k.s_wv[row0 + r], w1 = k.s_wv[m_pad + row0 + r];
 #pragma unroll
             for (int kk = 0; kk < KP; kk++) {
                 const int cp = k.ct + kk * k.NT;
@@ -114,6 +118,7 @@ __device__ __forceinline__ void bt_pass(BK &k, const double *X0, const double *X
         for (int r = k.warp; r < BT_TR; r += CW) {
             const double *rowp = tp + (size_t)r * lda;
             double a0x = 0.0, a0y = 0.0, a1x = 0.0, a1y = 0.0;
+#pragma unroll 3
             for (int cp = k.lane; cp < npairs; cp += 32) {
                 const double2 e = *reinterpret_cast<const double2 *>(rowp + 2 * cp);
                 const double2 x0 = *reinterpret_cast<const double2 *>(k.s_x + 2 * cp);
@@ -507,7 +512,8 @@ __global__ void __launch_bounds__(MAXT, MINB) k_batch_solve(const BatchArgs a)
     double *s_ax = tiles + (size_t)a.S * tile_elems;
     double *s_atw = s_ax + 2 * a.L.m_pad;
     double *s_x = s_atw + 2 * a.L.n_pad;
-    double *s_red = s_x + 2 * a.L.n_pad;
+    double *s_wv = s_x + 2 * a.L.n_pad;
+    double *s_red = s_wv + 2 * a.L.m_pad;
     SocScale *s_soc = reinterpret_cast<SocScale *>(s_red + 8 * 16);
     uint64_t *full = reinterpret_cast<uint64_t *>(s_soc + BT_MAX_SOC);
     uint64_t *empty = full + BT_MAX_STAGES;
@@ -571,6 +577,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_batch_solve(const BatchArgs a)
     k.s_ax = s_ax;
     k.s_atw = s_atw;
     k.s_x = s_x;
+    k.s_wv = s_wv;
     k.s_red = s_red;
     k.s_soc = s_soc;
     k.full = full;
@@ -783,7 +790,7 @@ void BatchSolver::load(Handle *h_, int64_t B_, int64_t m, int64_t n, const doubl
     if ((int64_t)KP * 32 * BT_MAX_CW < npairs) throw Error(FOS_ERR_UNSUPPORTED, "batch mode: n too large");
     CW = std::max(4, (npairs + KP * 32 - 1) / (KP * 32));
     const size_t tile_bytes = (size_t)BT_TR * lda * 8;
-    const size_t fixed = (size_t)(2 * L.m_pad + 4 * L.n_pad + 8 * 16) * 8 + BT_MAX_SOC * sizeof(SocScale) +
+    const size_t fixed = (size_t)(4 * L.m_pad + 4 * L.n_pad + 8 * 16) * 8 + BT_MAX_SOC * sizeof(SocScale) +
                          2 * BT_MAX_STAGES * 8 + 64;
     // two CTAs (= two problems) per SM when they fit: one CTA's vector phases overlap the other's pass
     ctas_per_sm = 1;

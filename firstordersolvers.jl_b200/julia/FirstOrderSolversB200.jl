@@ -125,3 +125,60 @@ function iterate(alg::FOSAlgorithm, data::B200Data, status::HSDEStatus, x, max_i
     end
     return guess
 end
+
+# ---------------------------------------------------------------------------------------------
+# Batch mode (config 5): `[solve!(m) for m in models]` for models that share (m, n, cones), solved
+# by ONE kernel launch -- one persistent CTA per problem, no host round trips (fos_*_batch).
+#   As :: Array{Float64,3} of size (n, m, B): Julia is column-major, so As[:, :, j] is the ROW-major
+#   m x n matrix of problem j that the library expects (lda = n, problem stride = m*n);
+#   bs :: (m, B), cs :: (n, B).
+# Returns (guess (2(m+n+1), B), status::Vector{Symbol}, iterations, records (10, ncheck, B)).
+# ---------------------------------------------------------------------------------------------
+function solve_batch_b200(alg::FOSAlgorithm, cs::Matrix{Float64}, As::Array{Float64,3}, bs::Matrix{Float64},
+                          constr_cones, var_cones; device = 0)
+    n, m, B = size(As)
+    opts = Dict{Symbol,Any}(alg.options)
+    max_iters = get(opts, :max_iters, 10000); eps = get(opts, :eps, 1e-5); checki = get(opts, :checki, 100)
+    href = Ref{Ptr{Cvoid}}(C_NULL)
+    rc = ccall((:fos_create, libfos), Int32, (Ref{Ptr{Cvoid}}, Int32), href, Int32(device))
+    rc == 0 || error(unsafe_string(ccall((:fos_last_error, libfos), Cstring, (Ptr{Cvoid},), C_NULL)))
+    h = href[]
+    t1 = Int32[CONE_CODE[c[1]] for c in constr_cones]; l1 = Int64[length(c[2]) for c in constr_cones]
+    t2 = Int32[CONE_CODE[c[1]] for c in var_cones];    l2 = Int64[length(c[2]) for c in var_cones]
+    try
+        fos_check(h, ccall((:fos_load_conic_dense_batch, libfos), Int32,
+            (Ptr{Cvoid}, Int64, Int64, Int64, Ptr{Float64}, Int64, Int64, Int32, Ptr{Float64}, Ptr{Float64},
+             Int64, Ptr{Int32}, Ptr{Int64}, Int64, Ptr{Int32}, Ptr{Int64}),
+            h, B, m, n, As, n, m * n, Int32(0), bs, cs, length(t1), t1, l1, length(t2), t2, l2))
+        code, a, a1, a2, b, ip = algparams(alg)
+        fos_check(h, ccall((:fos_set_algorithm, libfos), Int32,
+            (Ptr{Cvoid}, Int32, Float64, Float64, Float64, Float64, Int64), h, code, a, a1, a2, b, ip))
+        N = 2 * (m + n + 1)
+        cap = div(max_iters, checki) + 2
+        guess = zeros(Float64, N, B); rec = zeros(Float64, FOS_REC_LEN, cap, B)
+        done = zeros(Int64, B); st = zeros(Int32, B); nrec = zeros(Int64, B)
+        fos_check(h, ccall((:fos_solve_batch, libfos), Int32,
+            (Ptr{Cvoid}, Int64, Int64, Float64, Ptr{Float64}, Ptr{Int64}, Ptr{Int32}, Ptr{Float64}, Int64, Ptr{Int64}),
+            h, max_iters, checki, eps, guess, done, st, rec, cap, nrec))
+        syms = (:Continue, :Optimal, :Unbounded, :Infeasible, :Indeterminate)
+        return guess, [syms[s + 1] for s in st], done, rec
+    finally
+        ccall((:fos_destroy, libfos), Int32, (Ptr{Cvoid},), h)
+    end
+end
+
+# ---------------------------------------------------------------------------------------------
+# Multi-GPU (one Julia process per GPU, e.g. MPI.jl): row-sharded dense A.
+#   fos_comm_unique_id on rank 0 -> MPI.Bcast -> fos_comm_init -> fos_load_conic_dense(row block)
+#   -> fos_comm_p2p_export -> MPI.Allgather of the 64-byte handles -> fos_comm_p2p_import.
+# After the import every pass over A exchanges its partial sums through CUDA-IPC peer memory inside
+# the fused kernels (k1_exchange_p2p / k_cg_tail_hsde); without it the library falls back to
+# fold + ncclAllReduce.
+# ---------------------------------------------------------------------------------------------
+function enable_p2p_exchange_b200(h::Ptr{Cvoid}, nranks::Integer, allgather::Function)
+    mine = zeros(UInt8, 64)
+    fos_check(h, ccall((:fos_comm_p2p_export, libfos), Int32, (Ptr{Cvoid}, Ptr{UInt8}), h, mine))
+    table = allgather(mine)::Vector{UInt8}          # nranks * 64 bytes, rank order
+    length(table) == 64 * nranks || error("handle table has the wrong size")
+    fos_check(h, ccall((:fos_comm_p2p_import, libfos), Int32, (Ptr{Cvoid}, Ptr{UInt8}), h, table))
+end
