@@ -29,10 +29,9 @@ class FOSAlgorithm:
         raise NotImplementedError
 
     def _check_supported(self):
-        if self.direct:
-            raise NotImplementedError(
-                "direct=true (factorisation inside ProximalOperators.IndAffine, HSDE.jl:10-15) is outside the "
-                "B200 hot path (SURVEY.md 8f rank 1); construct the algorithm with direct=False")
+        """direct=true (HSDE.jl:10-15) is served by ``fos_set_direct``: exact projection through the dense
+        inverse of I + QQ' built on the device at load time (conic form, m+n+1 <= 16384)."""
+        return None
 
 
 @dataclass

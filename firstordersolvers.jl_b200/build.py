@@ -14,7 +14,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libfos_b200.so"
-SOURCES = ["capi.cu", "solver.cu", "matop.cu", "psd.cu", "psd_large.cu", "batch.cu"]
+SOURCES = ["capi.cu", "solver.cu", "matop.cu", "psd.cu", "psd_large.cu", "batch.cu", "direct.cu"]
 HEADERS = ["common.cuh", "kernels.cuh", "matvec.cuh", "solver.cuh", "batch.cuh", "../../include/fos_b200.h"]
 
 NVCC_FLAGS = [

@@ -261,6 +261,13 @@ int32_t fos_set_algorithm(fos_handle_t hh, int32_t alg, double alpha, double alp
     FOS_API_END(hh)
 }
 
+int32_t fos_set_direct(fos_handle_t hh, int32_t on)
+{
+    FOS_API_BEGIN(hh)
+    hh->h.set_direct(on != 0);
+    FOS_API_END(hh)
+}
+
 int64_t fos_iterate_length(fos_handle_t hh)
 {
     if (!hh) return -1;

@@ -246,6 +246,9 @@ void Handle::finish_load_common(const std::vector<ConeSeg> &segs)
     cgiter = 0;
     firstrun = true;
     warn_maxit = false;
+    direct = false;
+    Wop.reset();
+    Winv.release();
     status = FOS_STATUS_CONTINUE;
     checked = false;
     stats = Stats();
@@ -468,6 +471,10 @@ void Handle::cg_solve(double tol, int max_iters, const double *x0, const double 
 // prox!(y, S::AffinePlusLinear, x) (affinepluslinear.jl:83-126).  Result: sol (= xinit).
 void Handle::s1_prox(const double *xin)
 {
+    if (direct) {  // HSDE.jl:10-15
+        s1_prox_direct(xin);
+        return;
+    }
     const double an_ = (double)(L.form == 0 ? (L.n + L.m + 1) : L.n);
     if (fuse_rhs) {
         // one pass fewer per projection: see k_fuse_prep.  Same mathematics, different association of

@@ -266,6 +266,12 @@ struct Handle {
     double cur_eps = 1e-5;
     // batch mode
     std::unique_ptr<BatchSolver> batch;
+    // direct = true (direct.cu): W = (I + Q Q')^-1 on the device, streamed by its own MatOp
+    bool direct = false;
+    DevBuf<double> Winv;
+    std::unique_ptr<MatOp> Wop;
+    void set_direct(bool on);
+    void s1_prox_direct(const double *xin);
 
     ~Handle();
     void create(int dev);

@@ -40,7 +40,6 @@ conearrays(K::ConeProduct, names) =
 
 # replaces init_algorithm! for every algorithm: the device handle takes the place of GAPData etc.
 function init_algorithm_b200!(alg::FOSAlgorithm, model::FOSMathProgModel, constr_cones, var_cones)
-    alg.direct && error("direct=true is outside the B200 hot path; construct the algorithm with direct=false")
     href = Ref{Ptr{Cvoid}}(C_NULL)
     rc = ccall((:fos_create, libfos), Int32, (Ref{Ptr{Cvoid}}, Int32), href, Int32(get(model.options, :device, 0)))
     rc == 0 || error(unsafe_string(ccall((:fos_last_error, libfos), Cstring, (Ptr{Cvoid},), C_NULL)))
@@ -54,6 +53,8 @@ function init_algorithm_b200!(alg::FOSAlgorithm, model::FOSMathProgModel, constr
          Int64, Ptr{Int32}, Ptr{Int64}, Int64, Ptr{Int32}, Ptr{Int64}, Int32),
         h, m, n, A.colptr, A.rowval, A.nzval, 1, model.b, model.c,
         length(t1), t1, l1, length(t2), t2, l2, Int32(0)))
+    # HSDE(model, direct=alg.direct) (FOSSolverInterface.jl:77, HSDE.jl:10-15): exact projection on the device
+    alg.direct && fos_check(h, ccall((:fos_set_direct, libfos), Int32, (Ptr{Cvoid}, Int32), h, Int32(1)))
     code, a, a1, a2, b, ip = algparams(alg)
     fos_check(h, ccall((:fos_set_algorithm, libfos), Int32,
         (Ptr{Cvoid}, Int32, Float64, Float64, Float64, Float64, Int64), h, code, a, a1, a2, b, ip))
@@ -61,7 +62,7 @@ function init_algorithm_b200!(alg::FOSAlgorithm, model::FOSMathProgModel, constr
     finalizer(d -> ccall((:fos_destroy, libfos), Int32, (Ptr{Cvoid},), d.handle), data)
     m2, n2 = size(model.A)
     status_generator = (mo, checki, eps, verbose, debug) ->
-        HSDEStatus(m2, n2, 0, mo, :Continue, checki, eps, verbose, false, false, time_ns(), model.init_duration, debug)
+        HSDEStatus(m2, n2, 0, mo, :Continue, checki, eps, verbose, false, alg.direct, time_ns(), model.init_duration, debug)
     return data, status_generator
 end
 

@@ -143,6 +143,9 @@ class _Handle:
         code, a, a1, a2, b, ip = alg._params()
         self.ck(self.L.fos_set_algorithm(self.h, code, a, a1, a2, b, ip))
 
+    def set_direct(self, on=True):
+        self.ck(self.L.fos_set_direct(self.h, 1 if on else 0))
+
     def set_iterate(self, z):
         z = _f64(z)
         self.ck(self.L.fos_set_iterate(self.h, _d(z), z.size))
@@ -452,6 +455,8 @@ def loadproblem(model: FOSMathProgModel, c, A, b, constr_cones, var_cones, *, de
         _, colptr, rowval, nzval = _csc_arrays(A)
         H.ck(H.L.fos_load_conic_csc(H.h, m, n, _i64p(colptr), _i64p(rowval), _d(nzval), 0, _d(b), _d(c), len(t1a),
                                     _i32p(t1a), _i64p(l1a), len(t2a), _i32p(t2a), _i64p(l2a), storage))
+    if model.alg.direct:  # HSDE(model, direct=alg.direct)  FOSSolverInterface.jl:77
+        H.set_direct(True)
     H.set_algorithm(model.alg)  # init_algorithm!(model.alg, model)  :58
     model.data = H
     model._form = "hsde"
@@ -542,7 +547,7 @@ def _solve_model(model, out=None):
     if verbose > 0:  # printstatusheader
         if hsde:
             # the HSDE closure captured the placeholder init_duration = 1 ns (SURVEY a-Q 11)
-            _print_header_hsde(1, False, out)
+            _print_header_hsde(1, bool(getattr(model.alg, "direct", False)), out)
         else:
             _print_header_feas(model.init_duration, True, out)  # Feasibility.jl:76: direct = true
     i, st, last_i = 1, 0, 0
@@ -585,10 +590,12 @@ def _hsde_record(model, r, t, verbose, debug, out):
             h.push("y", i, z[n:n + m].copy())
             h.push("s", i, z[l + n:l + n + m].copy())
     if verbose > 0:
-        h.push("cgiter", i, cgiter)  # HSDEStatus.jl:46
+        direct = bool(getattr(model.alg, "direct", False))
+        if not direct:
+            h.push("cgiter", i, cgiter)  # HSDEStatus.jl:43-47
         with np.errstate(all="ignore"):
             kt = np.float64(kap) / np.float64(tau)
-        _print_iter_hsde(i, p, d, g, ctx, bty, kt, cgiter, t, False, out)
+        _print_iter_hsde(i, p, d, g, ctx, bty, kt, cgiter, t, direct, out)
         if st == 1:
             print(f"Found solution i={i}", file=out)  # HSDEStatus.jl:56
 
@@ -626,7 +633,8 @@ def solve_batch(alg: FOSAlgorithm, cs, As, bs, constr_cones, var_cones, device=0
     CTA per problem.  Options (max_iters, eps, checki, debug) come from ``alg.options`` as for
     ``ConicModel``.  Returns a list of ``FOSMathProgModel`` with solve_stat / primal_sol / dual_sol /
     slack / obj_val / history filled in, in input order."""
-    alg._check_supported()
+    if alg.direct:
+        raise NotImplementedError("direct=true is not offered in batch mode; construct the algorithm with direct=False")
     opts = dict(alg.options)
     max_iters = int(opts.get("max_iters", 10000))
     eps = float(opts.get("eps", 1e-5))

@@ -56,7 +56,7 @@ typedef struct fos_handle_s *fos_handle_t;
 #define FOS_ALG_GAPA 1    /* GAPA(alpha,beta)          gapa.jl:9-15   */
 #define FOS_ALG_FISTA 2   /* FISTA(alpha)              fista.jl:6-11  */
 #define FOS_ALG_DYKSTRA 3 /* Dykstra()                 dykstra.jl:6-10 */
-#define FOS_ALG_GAPP 4    /* GAPP(alpha,alpha1,alpha2; iproj) gapproj.jl:6-14 (indirect S1 only) */
+#define FOS_ALG_GAPP 4    /* GAPP(alpha,alpha1,alpha2; iproj) gapproj.jl:6-14 */
 
 /* ---- status codes: HSDEStatus.jl:53-63, HSDE.jl:56-59 -------------------------------- */
 #define FOS_STATUS_CONTINUE 0
@@ -162,6 +162,11 @@ int32_t fos_load_affine_csc(fos_handle_t h, int64_t am, int64_t an, const int64_
  * p = q = 0) like init_algorithm!; does NOT reset S1's warm start / call counter. */
 int32_t fos_set_algorithm(fos_handle_t h, int32_t alg, double alpha, double alpha1, double alpha2, double beta,
                           int64_t iproj);
+/* direct = true (the `direct` field of every algorithm, HSDE.jl:10-15; the default of GAPP, gapproj.jl:14):
+ * S1 becomes IndAffine([Q -I], 0), the exact projection, instead of the truncated CG solve.  The one-time
+ * work (W = (I + Q Q')^-1, dense, on the device) happens in this call; every projection is then two passes
+ * over A and one over W.  Conic form only, l = m+n+1 up to 16384, no row sharding.  on = 0 returns to CG. */
+int32_t fos_set_direct(fos_handle_t h, int32_t on);
 int64_t fos_iterate_length(fos_handle_t h); /* 2(m+n+1) or an+am; <0 on error */
 /* initx / getinitialvalue (solverwrapper.jl:10, HSDE.jl:40-47, Feasibility.jl:57-58). */
 int32_t fos_set_iterate(fos_handle_t h, const double *z, int64_t len);

@@ -539,6 +539,10 @@ typedef struct {
     int64_t hist_cap, hist_len;
     /* GAPP line-search log: alpha_best of each projected iteration */
     double last_alphabest;
+    /* direct = true (HSDE.jl:10-15): S1 = IndAffine([Q -I], 0), exact projection through a dense
+       Cholesky factor of I + Q Q' (ProximalOperators factorises the same normal equations) */
+    int direct;
+    double *chol; /* l x l, lower triangle, row-major */
 } model_t;
 
 static void model_alloc_vectors(model_t *M)
@@ -630,6 +634,7 @@ FOSOR_API void fosor_destroy(void *h)
     apl_free(M->S1);
     free(M->x); free(M->tmp1); free(M->tmp2); free(M->fy); free(M->fxold);
     free(M->dp); free(M->dq); free(M->dy); free(M->work1); free(M->work2); free(M->work3); free(M->prev);
+    free(M->chol);
     free(M);
 }
 
@@ -692,7 +697,84 @@ static void prox_S2(model_t *M, double *y, const double *x)
     if (M->form == 0) dualconeprod_prox(y, &M->K1, &M->K2, x);
     else coneprod_prox(y, &M->K1, x, 0);
 }
-static void prox_S1(model_t *M, double *y, const double *x) { apl_prox(y, M->S1, x); }
+/* prox of IndAffine(B, 0) with B = [Q -I] (HSDE.jl:10-15; ProximalOperators' IndAffine:
+ * y = z - B'(B B')^{-1} B z, B B' = Q Q' + I):   w = Q u - v ;  (I + Q Q') t = w ;  y = [u - Q't ; v + t] */
+static void direct_prox(model_t *M, double *y, const double *x)
+{
+    const linop_t *Q = &M->S1->op;
+    int64_t l = Q->an;
+    double *w = (double *)malloc(sizeof(double) * (size_t)l), *t = (double *)malloc(sizeof(double) * (size_t)l);
+    linop_mul(w, Q, x);
+    for (int64_t i = 0; i < l; i++) w[i] -= x[l + i];
+    const double *L = M->chol;
+    for (int64_t i = 0; i < l; i++) { /* forward substitution L z = w */
+        double s = w[i];
+        for (int64_t k = 0; k < i; k++) s -= L[i * l + k] * t[k];
+        t[i] = s / L[i * l + i];
+    }
+    for (int64_t i = l - 1; i >= 0; i--) { /* back substitution L' t = z */
+        double s = t[i];
+        for (int64_t k = i + 1; k < l; k++) s -= L[k * l + i] * t[k];
+        t[i] = s / L[i * l + i];
+    }
+    linop_mul_t(w, Q, t);
+    for (int64_t i = 0; i < l; i++) {
+        y[i] = x[i] - w[i];
+        y[l + i] = x[l + i] + t[i];
+    }
+    free(w);
+    free(t);
+}
+static void prox_S1(model_t *M, double *y, const double *x)
+{
+    if (M->direct) direct_prox(M, y, x);
+    else apl_prox(y, M->S1, x);
+}
+
+/* Switches the conic model to direct = true / false.  Returns 0, or -1 when the factorisation fails. */
+FOSOR_API int32_t fosor_set_direct(void *h, int32_t on)
+{
+    model_t *M = (model_t *)h;
+    if (M->form != 0) return -1;
+    free(M->chol);
+    M->chol = NULL;
+    M->direct = 0;
+    if (!on) return 0;
+    const linop_t *Q = &M->S1->op;
+    int64_t l = Q->an;
+    double *Qd = (double *)calloc((size_t)(l * l), sizeof(double)); /* Qd[j*l + i] = Q_ij (column j contiguous) */
+    double *e = (double *)calloc((size_t)l, sizeof(double));
+    for (int64_t j = 0; j < l; j++) {
+        e[j] = 1.0;
+        linop_mul(Qd + j * l, Q, e);
+        e[j] = 0.0;
+    }
+    double *G = (double *)calloc((size_t)(l * l), sizeof(double));
+    for (int64_t j = 0; j < l; j++)
+        for (int64_t i = 0; i < l; i++) {
+            double qij = Qd[j * l + i];
+            if (qij == 0.0) continue;
+            for (int64_t k = 0; k <= i; k++) G[i * l + k] += qij * Qd[j * l + k];
+        }
+    for (int64_t i = 0; i < l; i++) G[i * l + i] += 1.0;
+    for (int64_t j = 0; j < l; j++) { /* Cholesky, lower, in place */
+        double d = G[j * l + j];
+        for (int64_t k = 0; k < j; k++) d -= G[j * l + k] * G[j * l + k];
+        if (!(d > 0.0)) { free(Qd); free(e); free(G); return -1; }
+        d = sqrt(d);
+        G[j * l + j] = d;
+        for (int64_t i = j + 1; i < l; i++) {
+            double s2 = G[i * l + j];
+            for (int64_t k = 0; k < j; k++) s2 -= G[i * l + k] * G[j * l + k];
+            G[i * l + j] = s2 / d;
+        }
+    }
+    free(Qd);
+    free(e);
+    M->chol = G;
+    M->direct = 1;
+    return 0;
+}
 
 static void push_rec(model_t *M, const double *rec)
 {
@@ -996,7 +1078,7 @@ FOSOR_API void fosor_q_mul(void *h, const double *B, double *Y, int32_t transpos
     else linop_mul(Y, &M->S1->op, B);
 }
 FOSOR_API void fosor_kkt_mul(void *h, const double *x, double *y) { kkt_mul(y, &((model_t *)h)->S1->op, x); }
-FOSOR_API void fosor_affine_prox(void *h, const double *x, double *y) { apl_prox(y, ((model_t *)h)->S1, x); }
+FOSOR_API void fosor_affine_prox(void *h, const double *x, double *y) { prox_S1((model_t *)h, y, x); }
 FOSOR_API void fosor_cone_prox(void *h, const double *x, double *y) { prox_S2((model_t *)h, y, x); }
 FOSOR_API void fosor_a_mul(void *h, const double *x, double *y, int32_t transpose)
 {

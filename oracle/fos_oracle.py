@@ -59,6 +59,8 @@ def lib():
     L.fosor_create_feasibility.argtypes = [C.c_int64, C.c_int64, _ip, _ip, _dp, C.c_int64, _dp, _dp,
                                            C.c_int64, C.c_int32, C.c_int64, _i32p, _ip]
     L.fosor_destroy.argtypes = [C.c_void_p]
+    L.fosor_set_direct.restype = C.c_int32
+    L.fosor_set_direct.argtypes = [C.c_void_p, C.c_int32]
     L.fosor_iterate_length.restype = C.c_int64
     L.fosor_iterate_length.argtypes = [C.c_void_p]
     L.fosor_set_algorithm.argtypes = [C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double,
@@ -243,7 +245,7 @@ class _OracleBase:
 class OracleConic(_OracleBase):
     """HSDE conic model: minimise c'x s.t. b - A x in K1, x in K2 (MathProgBase convention)."""
 
-    def __init__(self, c, A, b, constr_cones, var_cones):
+    def __init__(self, c, A, b, constr_cones, var_cones, direct=False):
         super().__init__()
         A, colptr, rowval, nzval = _csc(A)
         self.m, self.n = A.shape
@@ -257,6 +259,12 @@ class OracleConic(_OracleBase):
             raise ValueError("cones do not cover 1:m / 1:n (cones.jl:66-72)")
         self.N = lib().fosor_iterate_length(self._h)
         self.l = self.m + self.n + 1
+        if direct:  # HSDE(model, direct=true): S1 = IndAffine([Q -I], 0)  (HSDE.jl:10-15)
+            self.set_direct(True)
+
+    def set_direct(self, on=True):
+        if lib().fosor_set_direct(self._h, 1 if on else 0) != 0:
+            raise RuntimeError("factorisation of I + Q Q' failed")
 
     def initial_value(self):
         """HSDE_getinitialvalue (HSDE.jl:40-47)."""

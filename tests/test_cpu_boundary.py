@@ -70,8 +70,7 @@ def test_algorithm_constructors_match_reference_defaults(fos):
     s = fos.GAP(0.5, 2.0, 2.0, max_iters=2000, proji=50)                   # unknown keys are swallowed
     assert s.options == {"max_iters": 2000, "proji": 50}
     assert fos.supportedcones(s) == ["Free", "Zero", "NonNeg", "NonPos", "SOC", "SDP", "ExpPrimal", "ExpDual"]
-    with pytest.raises(NotImplementedError):
-        gp._check_supported()                                              # direct=true is "next" (8f)
+    assert gp._check_supported() is None                                   # direct=true -> fos_set_direct (HSDE.jl:10-15)
 
 
 def test_cone_ranges_follow_cones_jl(fos):

@@ -204,6 +204,85 @@ def test_fused_cg_tail_matches_kernel_per_step_path(fos, oracle, kind, alg):
     assert Hs[0].info("launches") < Hs[1].info("launches")
 
 
+# ---------------------------------------------------------------------------------------------
+# direct = true (HSDE.jl:10-15): S1 = IndAffine([Q -I], 0), exact projection
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["nnls", "lasso", "sdp"])
+def test_direct_affine_projection_is_exact(fos, oracle, kind):
+    """test/HSDEAffine.jl:72-80 (IndAffine vs dense solve): the device projection lands on {Qu = v}, is
+    idempotent, and equals the oracle's Cholesky-based projection to 1e-11."""
+    from fos_b200 import problems
+    P = _problem(problems, kind)
+    O = oracle.OracleConic(P.c, P.A, P.b, P.constr_cones, P.var_cones, direct=True)
+    for storage in ("dense", "sparse"):
+        H = load_conic(fos, P, storage=storage)
+        H.set_direct(True)
+        rng = np.random.default_rng(3)
+        l = P.m + P.n + 1
+        for _ in range(3):
+            z = rng.standard_normal(2 * l)
+            y = H.affine_prox(z)
+            assert rel_err(y, O.affine_prox(z)) < 1e-11
+            assert rel_err(H.q_mul(y[:l]), y[l:]) < 1e-11          # Q u = v
+            assert rel_err(H.affine_prox(y), y) < 1e-11            # idempotent
+            assert abs(np.dot(z - y, y)) < 1e-9 * np.dot(z, z)     # z - P z orthogonal to the subspace
+        assert H.info("cgiter") == 0
+
+
+@pytest.mark.parametrize("kind,alg", [("nnls", "DR"), ("nnls", "GAPP_direct"), ("nnls", "GAPA"), ("lasso", "FISTA"),
+                                      ("socls", "Dykstra"), ("sdp", "GAP")])
+def test_direct_lockstep_and_solve(fos, oracle, kind, alg):
+    """direct = true on the UNSCALED instances: with the exact projection there is no truncated CG to
+    amplify rounding, so lock-step holds at 1e-10 on the BASELINE shapes themselves, and the
+    free-running solve reproduces status, iteration count and records."""
+    from fos_b200 import problems
+    P = _problem(problems, kind) if kind != "socls" else problems.soc_constrained_ls(300, 40, seed=3)
+    O = oracle.OracleConic(P.c, P.A, P.b, P.constr_cones, P.var_cones, direct=True)
+    H = load_conic(fos, P)
+    H.set_direct(True)
+    if alg == "GAPP_direct":
+        O.set_algorithm("GAPP", 0.8, 1.8, 1.8, 0.0, 7)
+        H.set_algorithm(fos.GAPP(iproj=7))          # the reference default: direct=true (gapproj.jl:14)
+        assert fos.GAPP().direct is True
+        name = "GAPP"
+    else:
+        set_alg_both(fos, H, O, alg)
+        name = alg
+    O.set_iterate(O.initial_value())
+    H.ck(H.L.fos_begin_solve(H.h))
+    for i in range(1, 31):
+        sync_state_from_oracle(H, O, name)
+        ro = O.run(i, 1, checki=5, eps=1e-12)
+        done, st, rec, _ = H.run(i, 1, 5, 1e-12)
+        tol = STEP_TOL * (100 if name == "GAPP" else 1)   # alpha_best = 2^k scales the rounding (see above)
+        assert rel_err(H.get_iterate(), O.get_state("x")) < tol, i
+        if i % 5 == 0:
+            assert rec[0, 8] == 0
+            np.testing.assert_allclose(rec[0, 1:8], [ro["history"][k][0] for k in ("p", "d", "g", "ctx", "bty", "kappa", "tau")],
+                                       rtol=1e-8, atol=1e-11, equal_nan=True)
+    if name != "GAPP":
+        O.set_iterate(O.initial_value())
+        H.set_initial_iterate()
+        ro = O.solve(max_iters=1500, checki=100, eps=1e-5)
+        done, st, rec, guess = H.solve(1500, 100, 1e-5)
+        assert fos.model.STATUS_SYMBOLS[st] == ro["status"]
+        assert done == ro["iterations"]
+        np.testing.assert_allclose(rec[:, 1:4], np.array([ro["history"][k] for k in ("p", "d", "g")]).T, rtol=1e-5, atol=1e-9)
+        assert rel_err(guess, ro["guess"]) < 1e-7
+
+
+def test_direct_api_prints_without_cg_column(fos, capsys):
+    from fos_b200 import problems
+    P = problems.nnls_conic(20, 25, seed=1)
+    model = fos.ConicModel(fos.GAPP(0.8, 1.8, 1.8, max_iters=300, iproj=50))      # direct=true by default
+    fos.loadproblem(model, P.c, P.A, P.b, P.constr_cones, P.var_cones)
+    fos.optimize(model)
+    out = capsys.readouterr().out.splitlines()
+    assert out[2] == " Iter | pri res | dua res | rel gap | pri obj | dua obj | kap/tau | time"   # HSDEStatus.jl:76-80
+    assert len(out[1]) == 76
+    assert "cgiter" not in model.history
+
+
 def test_solve_tail_forced_check_and_getsol_side_effects(fos, oracle):
     """a-Q 1-3: forced final check iff the last iteration was not a check iteration; getsol runs one
     more CG solve that advances S1.i; a second solve! continues the tolerance schedule."""
