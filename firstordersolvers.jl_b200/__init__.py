@@ -7,7 +7,7 @@ Exports mirror the reference (src/FirstOrderSolvers.jl:12, src/solvers/solvers.j
 ``Feasibility, GAP, GAPA, GAPP, DR, AP, Dykstra, FISTA`` plus the MathProgBase-style methods
 of src/FOSSolverInterface.jl with the ``!`` dropped.
 """
-from .algorithms import AP, DR, FISTA, GAP, GAPA, GAPP, Dykstra, FOSAlgorithm
+from .algorithms import AP, DR, FISTA, GAP, GAPA, GAPP, Dykstra, FOSAlgorithm, LineSearchWrapper
 from .model import (AffinePlusLinear, ConeProduct, ConicModel, Feasibility, FeasibilityModel, FeasibilitySolution,
                     FOSMathProgModel, MVHistory, Solution, getobjval, getsolution, loadproblem, numconstr, numvar,
                     optimize, solve, solve_batch, status, supportedcones)
@@ -18,7 +18,7 @@ from . import problems
 
 build_library = _build.build
 
-__all__ = ["AP", "DR", "FISTA", "GAP", "GAPA", "GAPP", "Dykstra", "FOSAlgorithm", "AffinePlusLinear", "ConeProduct",
+__all__ = ["AP", "DR", "FISTA", "GAP", "GAPA", "GAPP", "Dykstra", "FOSAlgorithm", "LineSearchWrapper", "AffinePlusLinear", "ConeProduct",
            "ConicModel", "Feasibility", "FeasibilityModel", "FeasibilitySolution", "FOSMathProgModel", "MVHistory",
            "Solution", "getobjval", "getsolution", "loadproblem", "numconstr", "numvar", "optimize", "solve", "solve_batch", "status",
            "supportedcones", "Handle", "FosError", "lib_path", "load_library", "build_library", "problems"]

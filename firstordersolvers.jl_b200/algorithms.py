@@ -105,3 +105,24 @@ class _GAPP(FOSAlgorithm):
 def GAPP(α=0.8, α1=1.8, α2=1.8, *, direct=True, iproj=100, **kwargs):
     """Reference default is direct=true (gapproj.jl:14); only direct=False runs on the B200 path."""
     return _GAPP(direct=direct, options=dict(kwargs), α=float(α), α1=float(α1), α2=float(α2), iproj=int(iproj))
+
+
+@dataclass
+class _LineSearchWrapper(FOSAlgorithm):
+    """``LineSearchWrapper(alg; lsinterval=100, kwargs...)`` src/wrappers/linesearch.jl:3-24: fields
+    ``lsinterval``, ``alg``, ``options`` (= merge(alg.options, kwargs))."""
+    lsinterval: int = 100
+    alg: FOSAlgorithm = None
+
+    def _params(self):
+        return self.alg._params()
+
+
+def LineSearchWrapper(alg, *, lsinterval=100, **kwargs):
+    if not isinstance(alg, (_GAP, _GAPA)):
+        # support_linesearch(alg) == Val{:False}: the reference logs an @error and carries on (linesearch.jl:20-22)
+        import warnings
+        warnings.warn(f"Algorithm {type(alg).__name__} does not support line search")
+    opts = dict(alg.options)
+    opts.update(kwargs)
+    return _LineSearchWrapper(direct=alg.direct, options=opts, lsinterval=int(lsinterval), alg=alg)

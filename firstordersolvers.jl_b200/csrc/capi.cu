@@ -261,6 +261,15 @@ int32_t fos_set_algorithm(fos_handle_t hh, int32_t alg, double alpha, double alp
     FOS_API_END(hh)
 }
 
+int32_t fos_set_linesearch(fos_handle_t hh, int64_t lsinterval)
+{
+    FOS_API_BEGIN(hh)
+    hh->h.require_loaded();
+    FOS_REQUIRE(lsinterval >= 0, "lsinterval must be >= 0");
+    hh->h.lsinterval = lsinterval;
+    FOS_API_END(hh)
+}
+
 int32_t fos_set_direct(fos_handle_t hh, int32_t on)
 {
     FOS_API_BEGIN(hh)

@@ -506,7 +506,7 @@ __device__ __forceinline__ double cone_project(uint8_t op, double x, const doubl
     return add_(x, pj);
 }
 
-enum { EPI_NONE = 0, EPI_GAP = 1, EPI_GAPA = 2, EPI_FISTA = 3, EPI_DYKSTRA = 4, EPI_GAPP_PROJ = 5, EPI_LS = 6 };
+enum { EPI_NONE = 0, EPI_GAP = 1, EPI_GAPA = 2, EPI_FISTA = 3, EPI_DYKSTRA = 4, EPI_GAPP_PROJ = 5, EPI_LS = 6, EPI_LSW = 7 };
 
 struct EpiArgs {
     double a2, om_a2;  // alpha2, 1 - alpha2
@@ -517,7 +517,8 @@ struct EpiArgs {
     double *x;         // iterate (updated in place)
     double *aux1;      // FISTA: xold (out) ; Dykstra: q (in/out)
     double *aux2;      // FISTA: y (out)    ; Dykstra: y (in)
-    double ls_alpha;   // EPI_LS: the step length tested
+    double ls_alpha;   // EPI_LS / EPI_LSW: the step length tested
+    int use_a12;       // EPI_GAPP_PROJ / EPI_LSW: take alpha2 from ctrl->alpha12 (GAPA under LineSearchWrapper)
 };
 
 // proj = P_S2(in);  then the algorithm-specific epilogue:
@@ -527,6 +528,7 @@ struct EpiArgs {
 //   EPI_DYKSTRA (dykstra.jl:32-35)  x = proj ; q = in - x        (in = y + q)
 //   EPI_GAPP_PROJ (gapproj.jl:61-62) tmp2 = a2*proj + (1-a2)*in ; x = tmp2
 //   EPI_LS    (gapproj.jl:49-55)    ||proj - in|| ; last block keeps the strictly smallest
+//   EPI_LSW   (wrappers/linesearch.jl:63-69)  t3 = a2*proj + (1-a2)*in ; ||x - t3|| ; strictly smallest
 template <int EPI>
 __global__ void __launch_bounds__(VBLOCK)
 k4_cone_apply(int64_t NP, const double *__restrict__ in, double *__restrict__ proj, const uint8_t *__restrict__ ops,
@@ -534,7 +536,7 @@ k4_cone_apply(int64_t NP, const double *__restrict__ in, double *__restrict__ pr
               RedBuf rb)
 {
     double a2 = E.a2, om_a2 = E.om_a2;
-    if (EPI == EPI_GAPA) {
+    if (EPI == EPI_GAPA || ((EPI == EPI_GAPP_PROJ || EPI == EPI_LSW) && E.use_a12)) {
         a2 = ctrl->alpha12;
         om_a2 = 1.0 - a2;
     }
@@ -569,6 +571,10 @@ k4_cone_apply(int64_t NP, const double *__restrict__ in, double *__restrict__ pr
         } else if (EPI == EPI_LS) {
             const double d = sub_(pj, t1);
             q[0] = fma(d, d, q[0]);
+        } else if (EPI == EPI_LSW) {
+            const double t3 = add_(mul_(a2, pj), mul_(om_a2, t1));
+            const double d = sub_(E.x[e], t3);  // normdiff(x, tmp3), linesearch.jl:64,77-85
+            q[0] = fma(d, d, q[0]);
         }
     }
     if (EPI == EPI_GAPA) {
@@ -581,7 +587,7 @@ k4_cone_apply(int64_t NP, const double *__restrict__ in, double *__restrict__ pr
             const double aopt = 2.0 / (1.0 + s);
             ctrl->alpha12 = (1.0 - E.betaA) * aopt + E.betaA * 2.0;
         }
-    } else if (EPI == EPI_LS) {
+    } else if (EPI == EPI_LS || EPI == EPI_LSW) {
         double tot[3];
         if (grid_reduce<3, VBLOCK>(q, tot, rb) && threadIdx.x == 0) {
             const double nt = sqrt(tot[0]);
@@ -593,10 +599,11 @@ k4_cone_apply(int64_t NP, const double *__restrict__ in, double *__restrict__ pr
     }
 }
 
-static __global__ void k_ls_begin(Ctrl *ctrl)
+// normbest = Inf ; alpha_best = -1.0 (gapproj.jl:44-45) or 1.0 (wrappers/linesearch.jl:55-56)
+static __global__ void k_ls_begin(Ctrl *ctrl, double alpha_init)
 {
     ctrl->ls_normbest = INFINITY;
-    ctrl->ls_alphabest = -1.0;
+    ctrl->ls_alphabest = alpha_init;
 }
 
 // =======================================================================================

@@ -211,6 +211,7 @@ void Handle::cone_project(ConeSet &K, const double *in, double *projbuf, int epi
         CONE_CASE(EPI_DYKSTRA)
         CONE_CASE(EPI_GAPP_PROJ)
         CONE_CASE(EPI_LS)
+        CONE_CASE(EPI_LSW)
     default: throw Error(FOS_ERR_INVALID, "bad epilogue");
     }
 #undef CONE_CASE
@@ -249,6 +250,7 @@ void Handle::finish_load_common(const std::vector<ConeSeg> &segs)
     direct = false;
     Wop.reset();
     Winv.release();
+    lsinterval = 0;
     status = FOS_STATUS_CONTINUE;
     checked = false;
     stats = Stats();
@@ -589,6 +591,33 @@ void Handle::step(int64_t i)
     case FOS_ALG_GAP:
     case FOS_ALG_GAPA: {
         const bool ada = alg == FOS_ALG_GAPA;
+        if (lsinterval > 0 && i % lsinterval == 0) {
+            // step(::LineSearchWrapper, ...) on a line-search iteration (wrappers/linesearch.jl:42-72)
+            double *t1s = w3.p, *res = w2.p, *t3 = w1.p;
+            FOS_CUDA(cudaMemcpyAsync(t1s, x.p, (size_t)L.NP * 8, cudaMemcpyDeviceToDevice, stream));  // :43
+            s1_prox(x.p);                                                                           // S1! :47
+            FOS_LAUNCH(this, k_relax, g, VBLOCK, 0, L.NP, tmp1.p, alpha1, sol.p, 1.0 - alpha1, x.p, p2off, p2scale,
+                       d_ctrl.p, ada ? 1 : 0);
+            E.a2 = alpha2;
+            E.om_a2 = 1.0 - alpha2;
+            E.use_a12 = ada ? 1 : 0;
+            cone_project(cones, tmp1.p, proj.p, EPI_GAPP_PROJ, E);  // S2! :48: x = a2*P2(tmp2) + (1-a2)*tmp2
+            check(proj.p, i, false);                                // checkstatus inside S2! (gap.jl:56)
+            FOS_LAUNCH(this, k_sub, g, VBLOCK, 0, L.NP, res, x.p, t1s);  // :51
+            FOS_LAUNCH(this, k_ls_begin, 1, 1, 0, d_ctrl.p, 1.0);
+            double at = 0.1;
+            for (int k = 0; k <= 30; k++) {  // :58-70, NoStatus
+                at = at * 1.8;               // :59
+                FOS_LAUNCH(this, k_add_scaled, g, VBLOCK, 0, L.NP, x.p, t1s, at, res, d_ctrl.p, 0);  // :60
+                s1_prox(x.p);
+                FOS_LAUNCH(this, k_relax, g, VBLOCK, 0, L.NP, tmp1.p, alpha1, sol.p, 1.0 - alpha1, x.p, p2off, p2scale,
+                           d_ctrl.p, ada ? 1 : 0);
+                E.ls_alpha = at;
+                cone_project(cones, tmp1.p, t3, EPI_LSW, E);
+            }
+            FOS_LAUNCH(this, k_add_scaled, g, VBLOCK, 0, L.NP, x.p, t1s, 0.0, res, d_ctrl.p, 1);  // :72
+            break;
+        }
         s1_prox(x.p);  // gap.jl:45
         FOS_LAUNCH(this, k_relax, g, VBLOCK, 0, L.NP, tmp1.p, alpha1, sol.p, 1.0 - alpha1, x.p, p2off, p2scale,
                    d_ctrl.p, ada ? 1 : 0);  // :48
@@ -636,7 +665,7 @@ void Handle::step(int64_t i)
             s1_prox(proj.p);                                   // :40
             sol_scaled_to(w3.p);
             FOS_LAUNCH(this, k_sub, g, VBLOCK, 0, L.NP, w3.p, w3.p, tmp1.p);  // :41 res
-            FOS_LAUNCH(this, k_ls_begin, 1, 1, 0, d_ctrl.p);
+            FOS_LAUNCH(this, k_ls_begin, 1, 1, 0, d_ctrl.p, -1.0);
             for (int k = 0; k <= 20; k++) {  // :46-56
                 const double at = std::ldexp(1.0, k);
                 FOS_LAUNCH(this, k_add_scaled, g, VBLOCK, 0, L.NP, w1.p, tmp1.p, at, w3.p, d_ctrl.p, 0);

@@ -237,6 +237,7 @@ struct Handle {
     int alg = FOS_ALG_GAP;
     double alpha = 0.8, alpha1 = 1.8, alpha2 = 1.8, betaA = 0.0;
     int64_t iproj = 100;
+    int64_t lsinterval = 0;  // LineSearchWrapper (wrappers/linesearch.jl); 0 = no wrapper
     double fista_t = 1.0;
     DevBuf<double> x, tmp1, tmp2, proj, fy, fxold, dp, dq, dy, w1, w2, w3, prev;
     ConeSet cones;

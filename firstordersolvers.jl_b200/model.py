@@ -142,6 +142,13 @@ class _Handle:
     def set_algorithm(self, alg: FOSAlgorithm):
         code, a, a1, a2, b, ip = alg._params()
         self.ck(self.L.fos_set_algorithm(self.h, code, a, a1, a2, b, ip))
+        # LineSearchWrapper(alg; lsinterval) (wrappers/linesearch.jl): only GAP / GAPA take part
+        ls = int(getattr(alg, "lsinterval", 0)) if code in (0, 1) else 0
+        if self.batch_size() < 0:
+            self.ck(self.L.fos_set_linesearch(self.h, ls))
+
+    def set_linesearch(self, lsinterval):
+        self.ck(self.L.fos_set_linesearch(self.h, int(lsinterval)))
 
     def set_direct(self, on=True):
         self.ck(self.L.fos_set_direct(self.h, 1 if on else 0))

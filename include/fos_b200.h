@@ -162,6 +162,13 @@ int32_t fos_load_affine_csc(fos_handle_t h, int64_t am, int64_t an, const int64_
  * p = q = 0) like init_algorithm!; does NOT reset S1's warm start / call counter. */
 int32_t fos_set_algorithm(fos_handle_t h, int32_t alg, double alpha, double alpha1, double alpha2, double beta,
                           int64_t iproj);
+/* LineSearchWrapper(alg; lsinterval) (wrappers/linesearch.jl:19-75) around GAP / GAPA (the algorithms with
+ * support_linesearch, gap.jl:89, gapa.jl:117): on iterations i % lsinterval == 0 the step is replaced by one
+ * relaxed S1/S2 pass (with the status check inside S2!), 31 trial steps x = x0 + alpha*res, alpha = 0.1*1.8^(k+1),
+ * each scored by ||x - S2!(S1!(x))||, and x = x0 + alpha_best*res.  alpha_best: fos_get_info(h, 8).  The
+ * reference's 33 println lines per search are not reproduced.  lsinterval = 0 removes the wrapper; other
+ * algorithms ignore it (the reference logs an error at construction). */
+int32_t fos_set_linesearch(fos_handle_t h, int64_t lsinterval);
 /* direct = true (the `direct` field of every algorithm, HSDE.jl:10-15; the default of GAPP, gapproj.jl:14):
  * S1 becomes IndAffine([Q -I], 0), the exact projection, instead of the truncated CG solve.  The one-time
  * work (W = (I + Q Q')^-1, dense, on the device) happens in this call; every projection is then two passes

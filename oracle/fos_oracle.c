@@ -543,6 +543,9 @@ typedef struct {
        Cholesky factor of I + Q Q' (ProximalOperators factorises the same normal equations) */
     int direct;
     double *chol; /* l x l, lower triangle, row-major */
+    /* LineSearchWrapper (wrappers/linesearch.jl): 0 = no wrapper */
+    int64_t lsinterval;
+    double *ls1, *ls2, *ls3, *lsres; /* LineSearchWrapperData tmp1, tmp2, tmp3, res (:9-17) */
 } model_t;
 
 static void model_alloc_vectors(model_t *M)
@@ -635,6 +638,7 @@ FOSOR_API void fosor_destroy(void *h)
     free(M->x); free(M->tmp1); free(M->tmp2); free(M->fy); free(M->fxold);
     free(M->dp); free(M->dq); free(M->dy); free(M->work1); free(M->work2); free(M->work3); free(M->prev);
     free(M->chol);
+    free(M->ls1); free(M->ls2); free(M->ls3); free(M->lsres);
     free(M);
 }
 
@@ -654,6 +658,22 @@ FOSOR_API void fosor_set_algorithm(void *h, int32_t alg, double alpha, double al
     memset(M->fxold, 0, sizeof(double) * (size_t)M->N);
     memset(M->dp, 0, sizeof(double) * (size_t)M->N); /* dykstra.jl:22 */
     memset(M->dq, 0, sizeof(double) * (size_t)M->N);
+}
+
+/* LineSearchWrapper(alg; lsinterval) (wrappers/linesearch.jl:19-24): GAP and GAPA only (support_linesearch) */
+FOSOR_API int32_t fosor_set_linesearch(void *h, int64_t lsinterval)
+{
+    model_t *M = (model_t *)h;
+    if (lsinterval < 0) return -1;
+    M->lsinterval = lsinterval;
+    if (lsinterval > 0 && !M->ls1) {
+        size_t N = (size_t)M->N;
+        M->ls1 = (double *)calloc(N, sizeof(double));
+        M->ls2 = (double *)calloc(N, sizeof(double));
+        M->ls3 = (double *)calloc(N, sizeof(double));
+        M->lsres = (double *)calloc(N, sizeof(double));
+    }
+    return 0;
 }
 
 FOSOR_API void fosor_set_iterate(void *h, const double *z)
@@ -689,6 +709,7 @@ FOSOR_API double fosor_get_fista_t(void *h) { return ((model_t *)h)->fista_t; }
 FOSOR_API int64_t fosor_get_s1_calls(void *h) { return ((model_t *)h)->S1->i; }
 FOSOR_API int64_t fosor_get_cgiter(void *h) { return ((model_t *)h)->S1->cgiter; }
 FOSOR_API double fosor_get_alpha12(void *h) { return ((model_t *)h)->alpha12; }
+FOSOR_API double fosor_get_alphabest(void *h) { return ((model_t *)h)->last_alphabest; }
 FOSOR_API int32_t fosor_get_cg_warned(void *h) { return ((model_t *)h)->S1->cg_maxit_warned; }
 
 /* prox on S2 */
@@ -977,8 +998,56 @@ static void step_gapp(model_t *M)
     }
 }
 
+/* relaxed S1! / S2! of GAP and GAPA (gap.jl:42-60, gapa.jl:61-79); with_status = the real status object
+ * (checkstatus inside S2!) or NoStatus (status.jl:3-9) */
+static void ls_S1(model_t *M, double *y, const double *x)
+{
+    double a1 = M->alg == ALG_GAPA ? M->alpha12 : M->alpha1;
+    prox_S1(M, y, x);
+    for (int64_t i = 0; i < M->N; i++) y[i] = a1 * y[i] + (1 - a1) * x[i];
+}
+static void ls_S2(model_t *M, double *y, const double *x, int with_status)
+{
+    double a2 = M->alg == ALG_GAPA ? M->alpha12 : M->alpha2;
+    prox_S2(M, y, x);
+    if (with_status) checkstatus(M, y, 0);
+    for (int64_t i = 0; i < M->N; i++) y[i] = a2 * y[i] + (1 - a2) * x[i];
+}
+
+/* step(::LineSearchWrapper, ...) on a line-search iteration (wrappers/linesearch.jl:42-71).  The 33
+ * println calls of the reference are not restated. */
+static void step_linesearch(model_t *M)
+{
+    int64_t N = M->N;
+    double *x = M->x, *t1 = M->ls1, *t2 = M->ls2, *t3 = M->ls3, *res = M->lsres;
+    memcpy(t1, x, sizeof(double) * (size_t)N);                       /* :43 */
+    ls_S1(M, t2, x);                                                 /* :47 */
+    ls_S2(M, x, t2, 1);                                              /* :48 */
+    for (int64_t i = 0; i < N; i++) res[i] = x[i] - t1[i];           /* :51 */
+    double best = INFINITY, abest = 1.0, a = 0.1;                    /* :55-57 */
+    for (int k = 0; k <= 30; k++) {                                  /* :58 */
+        a = a * 1.8;                                                 /* :59 */
+        for (int64_t i = 0; i < N; i++) x[i] = t1[i] + a * res[i];   /* :60 */
+        ls_S1(M, t2, x);                                             /* :62 */
+        ls_S2(M, t3, t2, 0);                                         /* :63 */
+        double sacc = 0.0;                                           /* normdiff :77-85 */
+        for (int64_t j = 0; j < N; j++) sacc += (x[j] - t3[j]) * (x[j] - t3[j]);
+        double testres = sqrt(sacc);
+        if (testres < best) {                                        /* :66-69 */
+            best = testres;
+            abest = a;
+        }
+    }
+    for (int64_t i = 0; i < N; i++) x[i] = t1[i] + abest * res[i];   /* :72 */
+    M->last_alphabest = abest;
+}
+
 static void do_step(model_t *M)
 {
+    if (M->lsinterval > 0 && (M->alg == ALG_GAP || M->alg == ALG_GAPA) && M->cur_i % M->lsinterval == 0) {
+        step_linesearch(M);                                          /* :41-42 */
+        return;
+    }
     switch (M->alg) {
     case ALG_GAP: step_gap(M); break;
     case ALG_GAPA: step_gapa(M); break;

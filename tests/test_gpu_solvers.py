@@ -283,6 +283,65 @@ def test_direct_api_prints_without_cg_column(fos, capsys):
     assert "cgiter" not in model.history
 
 
+# ---------------------------------------------------------------------------------------------
+# LineSearchWrapper (wrappers/linesearch.jl; test/linesearch.jl, test/testfeasibility.jl:36)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind,inner", [("nnls", "GAP"), ("nnls", "GAPA"), ("lasso", "DR")])
+def test_linesearch_wrapper_lockstep(fos, oracle, kind, inner):
+    """Every iteration -- plain ones and the line-search ones (i % lsinterval == 0: 32 S1 solves, each
+    advancing the CG tolerance schedule and warm start) -- from the oracle's state, at 1e-10."""
+    from fos_b200 import problems
+    P = _problem(problems, kind, WELL[kind])
+    O = oracle.OracleConic(P.c, P.A, P.b, P.constr_cones, P.var_cones)
+    H = load_conic(fos, P)
+    oargs, fac = ALG_SETUPS[inner]
+    O.set_algorithm(*oargs)
+    O.set_linesearch(4)
+    H.set_algorithm(fos.LineSearchWrapper(fac(fos), lsinterval=4))
+    O.set_iterate(O.initial_value())
+    H.ck(H.L.fos_begin_solve(H.h))
+    for i in range(1, 14):
+        sync_state_from_oracle(H, O, inner)
+        ro = O.run(i, 1, checki=2, eps=1e-12)
+        done, st, rec, _ = H.run(i, 1, 2, 1e-12)
+        assert H.info("s1_calls") == O.s1_calls, i          # 32 projections on a line-search iteration
+        # right after a search the CG warm start is the one left by the LAST trial (alpha = 0.1*1.8^31 ~ 8e6
+        # times the residual), far from the new right-hand side: the truncated CG on the indefinite KKT matrix
+        # then runs long and amplifies rounding (DESIGN.md, parity budget)
+        tol = 1e-7 if i > 1 and ((i - 1) % 4 == 0 or i % 4 == 0) else 10 * STEP_TOL   # x0 + alpha_best*res scales rounding too
+        e = rel_err(H.get_iterate(), O.get_state("x"))
+        assert e < tol, (i, e)
+        if i % 4 == 0:
+            assert H.info("alphabest") == pytest.approx(lib_alpha(O), rel=0, abs=0)
+        if i % 2 == 0:
+            _assert_record_matches(rec, ro["history"], i)
+
+
+def lib_alpha(O):
+    from oracle import fos_oracle as fo
+    fo.lib().fosor_get_alphabest.restype = __import__("ctypes").c_double
+    fo.lib().fosor_get_alphabest.argtypes = [__import__("ctypes").c_void_p]
+    return fo.lib().fosor_get_alphabest(O._h)
+
+
+def test_linesearch_wrapper_feasibility_solve(fos, oracle):
+    """test/testfeasibility.jl:33-42: LineSearchWrapper(GAP(eps=1e-8)) finds x >= 0 with A x = b."""
+    from fos_b200 import problems
+    A, b, cones = problems.feasibility_problem(50, 100, seed=2)
+    prob = fos.Feasibility(fos.AffinePlusLinear(A, b, np.zeros(100), 1), fos.ConeProduct(cones), 150)
+    sol, model = fos.solve(prob, fos.LineSearchWrapper(fos.GAP(eps=1e-8, verbose=0)))
+    assert sol.status == "Optimal"
+    assert sol.x[:100].min() > -1e-12
+    assert np.abs(A @ sol.x[:100] - b).max() < 1e-6
+    O = oracle.OracleFeasibility(A, b, np.zeros(100), 1, cones)
+    O.set_algorithm("GAP", 0.8, 1.8, 1.8, 0.0, 100)
+    O.set_linesearch(100)
+    O.set_iterate(O.initial_value())
+    ro = O.solve(max_iters=10000, checki=100, eps=1e-8)
+    assert ro["status"] == "Optimal"
+    assert abs(model.last_iteration - ro["iterations"]) <= 100
+
+
 def test_solve_tail_forced_check_and_getsol_side_effects(fos, oracle):
     """a-Q 1-3: forced final check iff the last iteration was not a check iteration; getsol runs one
     more CG solve that advances S1.i; a second solve! continues the tolerance schedule."""
