@@ -39,6 +39,7 @@ SIGNATURES = {
     "fos_load_affine_csc": (C.c_int32, [_h, C.c_int64, C.c_int64, _i64p, _i64p, _dp, C.c_int64, _dp, _dp,
                                         C.c_int32, C.c_int32, C.c_int64, _i32p, _i64p, C.c_int32]),
     "fos_set_algorithm": (C.c_int32, [_h, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int64]),
+    "fos_set_box": (C.c_int32, [_h, C.c_int64, C.c_int64, C.c_double, C.c_double]),
     "fos_set_linesearch": (C.c_int32, [_h, C.c_int64]),
     "fos_set_direct": (C.c_int32, [_h, C.c_int32]),
     "fos_iterate_length": (C.c_int64, [_h]),

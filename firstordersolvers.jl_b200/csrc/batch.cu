@@ -867,8 +867,8 @@ void BatchSolver::load(Handle *h_, int64_t B_, int64_t m, int64_t n, const doubl
             int64_t off = base;
             for (int64_t k = 0; k < nc; k++) {
                 FOS_REQUIRE(ln[k] >= 0, "negative cone length");
-                if (t[k] == FOS_CONE_SDP)
-                    throw Error(FOS_ERR_UNSUPPORTED, "SDP cones are not offered in batch mode");
+                if (t[k] == FOS_CONE_SDP || t[k] == FOS_CONE_SOCROT || t[k] == FOS_CONE_EXPPRIMAL || t[k] == FOS_CONE_EXPDUAL)
+                    throw Error(FOS_ERR_UNSUPPORTED, "batch mode offers Free, Zero, NonNeg, NonPos and SOC cones");
                 segs.push_back(ConeSeg{t[k], dual, off, ln[k]});
                 off += ln[k];
             }

@@ -261,6 +261,21 @@ int32_t fos_set_algorithm(fos_handle_t hh, int32_t alg, double alpha, double alp
     FOS_API_END(hh)
 }
 
+int32_t fos_set_box(fos_handle_t hh, int64_t start, int64_t len, double lo, double hi)
+{
+    FOS_API_BEGIN(hh)
+    Handle &h = hh->h;
+    h.require_loaded();
+    FOS_REQUIRE(h.L.form == 1, "IndBox applies to the S2 of the Feasibility form");
+    FOS_REQUIRE(start >= 0 && len >= 0 && start + len <= h.N, "box range out of bounds");
+    // logical [x(an); z(am)] -> padded offsets; a range may straddle the x / z boundary
+    const int64_t an = h.L.n;
+    const int64_t a0 = start, a1 = start + len;
+    if (a0 < an) h.cones.set_box(a0, std::min(a1, an) - a0, lo, hi);
+    if (a1 > an) h.cones.set_box(h.L.n_pad + std::max<int64_t>(a0 - an, 0), a1 - std::max(a0, an), lo, hi);
+    FOS_API_END(hh)
+}
+
 int32_t fos_set_linesearch(fos_handle_t hh, int64_t lsinterval)
 {
     FOS_API_BEGIN(hh)

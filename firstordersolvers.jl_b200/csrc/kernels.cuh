@@ -409,7 +409,18 @@ enum : uint8_t {
     OP_SOC_TAIL = 5,
     OP_SOCD_HEAD = 6,  // dual via Moreau, cones.jl:80-85
     OP_SOCD_TAIL = 7,
-    OP_PRE = 8         // projected value already in proj[] (PSD cones, K5)
+    OP_PRE = 8,        // projected value already in proj[] (PSD cones, K5)
+    OP_RSOC_H0 = 9,    // rotated SOC (IndRotatedSOC): first, second entry, tail
+    OP_RSOC_H1 = 10,
+    OP_RSOC_TAIL = 11,
+    OP_RSOCD_H0 = 12,  // ... its dual via Moreau
+    OP_RSOCD_H1 = 13,
+    OP_RSOCD_TAIL = 14,
+    OP_EXPP = 15,      // exponential cone (IndExpPrimal), 3 entries, cone_of[e] = position 0..2
+    OP_EXPP_D = 16,    // proxDual! of ExpPrimal: x + P_K(-x)
+    OP_EXPD = 17,      // IndExpDual: x + P_K(-x) as well (Moreau)
+    OP_EXPD_D = 18,    // proxDual! of ExpDual: x + P_K*(-x)
+    OP_BOX = 19        // IndBox(lo, hi): clamp, bounds in box[cone_of[e]]
 };
 
 struct SocCone {
@@ -418,7 +429,7 @@ struct SocCone {
     int32_t chunk0; // first norm chunk
     int32_t nchunk;
     int32_t dual;
-    int32_t pad_;
+    int32_t rot;    // 1: rotated SOC, entries (x1, x2, w): the cone is 2 x1 x2 >= ||w||^2, x1, x2 >= 0
 };
 struct SocScale {  // result of the norm pass for one cone
     int32_t mode;  // primal: 0 -> 0, 1 -> copy, 2 -> scale.  dual: 0 -> copy x, 1 -> 0, 2 -> scale
@@ -427,6 +438,97 @@ struct SocScale {  // result of the norm pass for one cone
     double nx;
 };
 constexpr int SOC_CHUNK = 2048;
+
+constexpr double RSOC_C = 0.7071067811865475;  // sin(pi/4) = cos(pi/4), the literal of ProximalOperators' IndRotatedSOC
+// rotated coordinates of the first two entries: x1' = c x1 + c x2, x2' = c x1 - c x2
+__device__ __forceinline__ void rsoc_rotate(double a, double b, double &r1, double &r2)
+{
+    r1 = add_(mul_(RSOC_C, a), mul_(RSOC_C, b));
+    r2 = sub_(mul_(RSOC_C, a), mul_(RSOC_C, b));
+}
+// From the squared tail norm: IndSOC on (t, w) / IndRotatedSOC on (x1, x2, w) (rotate the first two entries by
+// pi/4, project onto the SOC with t = x1', tail (x2', w), rotate back).  Dual cones project -x (Moreau).
+__device__ __forceinline__ SocScale soc_classify(const SocCone &K, double tail_sq, const double *__restrict__ in)
+{
+    double nx, t;
+    const double sg = K.dual ? -1.0 : 1.0;
+    if (K.rot) {
+        double r1, r2;
+        rsoc_rotate(sg * in[K.head], sg * in[K.head + 1], r1, r2);
+        const double nw = sqrt(tail_sq);  // norm(x[3:end])
+        nx = sqrt(add_(mul_(r2, r2), mul_(nw, nw)));
+        t = r1;
+    } else {
+        nx = sqrt(tail_sq);
+        t = sg * in[K.head];
+    }
+    SocScale R;
+    R.pad_ = 0;
+    R.nx = nx;
+    R.rho = 0.0;
+    if (t <= -nx) R.mode = 0;
+    else if (t >= nx) R.mode = 1;
+    else {
+        R.mode = 2;
+        R.rho = 0.5 * (1.0 + t / nx);
+    }
+    return R;
+}
+
+// ---- exponential cone: cl{(r, s, t) : s > 0, s exp(r/s) <= t}.  ProximalOperators' IndExpPrimal follows the
+// projection of SCS (cones.c, proj_exp_cone): membership tests, the analytic case r, s < 0, otherwise bisection on
+// the dual variable rho with a 1-D Newton solve inside (tolerance 1e-8, at most 100 iterations each). ----
+constexpr double EXP_TOL = 1e-8;
+__device__ __forceinline__ double exp_newton_one_d(double rho, double y_hat, double z_hat)
+{
+    double t = fmax(-z_hat, 1e-6);
+    for (int i = 0; i < 100; i++) {
+        const double f = t * (t + z_hat) / rho / rho - y_hat / rho + log(t / rho) + 1.0;
+        const double fp = (2.0 * t + z_hat) / rho / rho + 1.0 / t;
+        t = t - f / fp;
+        if (t <= -z_hat) return 0.0;
+        else if (t <= 0.0) return z_hat;
+        else if (fabs(f) < EXP_TOL) break;
+    }
+    return t + z_hat;
+}
+__device__ __forceinline__ double exp_calc_grad(const double (&v)[3], double (&x)[3], double rho)
+{
+    x[2] = exp_newton_one_d(rho, v[1], v[2]);
+    x[1] = (x[2] - v[2]) * x[2] / rho;
+    x[0] = v[0] - rho;
+    if (x[1] <= 1e-12) return x[0];
+    return x[0] + x[1] * log(x[1] / x[2]);
+}
+__device__ __forceinline__ void proj_exp_cone(const double (&v)[3], double (&y)[3])
+{
+    const double r = v[0], s = v[1], t = v[2];
+    if ((s * exp(r / s) - t <= EXP_TOL && s > 0.0) || (r <= 0.0 && s == 0.0 && t >= 0.0)) {  // v in cl(K)
+        y[0] = r; y[1] = s; y[2] = t;
+        return;
+    }
+    if ((-r < 0.0 && r * exp(s / r) + exp(1.0) * t <= EXP_TOL) || (-r == 0.0 && -s >= 0.0 && -t >= 0.0)) {  // -v in K*
+        y[0] = y[1] = y[2] = 0.0;
+        return;
+    }
+    if (r < 0.0 && s < 0.0) {  // analytic
+        y[0] = r; y[1] = 0.0; y[2] = fmax(t, 0.0);
+        return;
+    }
+    double x[3], lb = 0.0, ub = 0.125;
+    while (exp_calc_grad(v, x, ub) > 0.0) {
+        lb = ub;
+        ub *= 2.0;
+    }
+    for (int i = 0; i < 100; i++) {
+        const double rho = (ub + lb) / 2.0;
+        const double g = exp_calc_grad(v, x, rho);
+        if (g > 0.0) lb = rho;
+        else ub = rho;
+        if (ub - lb < EXP_TOL) break;
+    }
+    y[0] = x[0]; y[1] = x[1]; y[2] = x[2];
+}
 
 // pass 1: one block per chunk of a SOC tail, squared-norm partial; the last block folds the
 // chunk partials per cone (in chunk order) and classifies each cone.
@@ -439,12 +541,13 @@ k4_soc_norms(const double *__restrict__ in, const SocCone *__restrict__ cones, i
     __shared__ bool s_last;
     const int ch = blockIdx.x;
     const SocCone C = cones[chunk_cone[ch]];
+    const int64_t skip = C.rot ? 2 : 1;  // entries before the tail
     const int64_t k0 = (int64_t)(ch - C.chunk0) * SOC_CHUNK;  // offset inside the tail
-    const int64_t tail = C.len - 1;
+    const int64_t tail = C.len - skip;
     const int64_t k1 = k0 + SOC_CHUNK < tail ? k0 + SOC_CHUNK : tail;
     double acc = 0.0;
     for (int64_t k = k0 + threadIdx.x; k < k1; k += VBLOCK) {
-        const double w = in[C.head + 1 + k];
+        const double w = in[C.head + skip + k];
         acc = fma(w, w, acc);
     }
     acc = warp_sum(acc);
@@ -465,26 +568,15 @@ k4_soc_norms(const double *__restrict__ in, const SocCone *__restrict__ cones, i
         double s = 0.0;
         const volatile double *cs = chunk_sum;
         for (int k = 0; k < K.nchunk; k++) s += cs[K.chunk0 + k];
-        const double nx = sqrt(s);
-        double t = in[K.head];
-        if (K.dual) t = -t;
-        SocScale R;
-        R.pad_ = 0;
-        R.nx = nx;
-        R.rho = 0.0;
-        if (t <= -nx) R.mode = 0;
-        else if (t >= nx) R.mode = 1;
-        else {
-            R.mode = 2;
-            R.rho = 0.5 * (1.0 + t / nx);
-        }
-        scale[cidx] = R;
+        scale[cidx] = soc_classify(K, s, in);
     }
     if (threadIdx.x == 0) *counter = 0u;
 }
 
 __device__ __forceinline__ double cone_project(uint8_t op, double x, const double *__restrict__ proj, int64_t e,
-                                               const int32_t *__restrict__ cone_of, const SocScale *__restrict__ scale)
+                                               const int32_t *__restrict__ cone_of, const SocScale *__restrict__ scale,
+                                               const double *in = nullptr, const double2 *__restrict__ box = nullptr,
+                                               const SocCone *__restrict__ soc = nullptr)
 {
     switch (op) {
     case OP_ZERO: return 0.0;
@@ -492,7 +584,29 @@ __device__ __forceinline__ double cone_project(uint8_t op, double x, const doubl
     case OP_MAX0: return x > 0.0 ? x : 0.0;   // max(x,0); NaN -> 0 like Julia's max? (NaN stays NaN in Julia)
     case OP_MIN0: return x < 0.0 ? x : 0.0;
     case OP_PRE: return proj[e];
+    case OP_BOX: {  // IndBox: min(max(x, lo), hi)
+        const double2 b = box[cone_of[e]];
+        return x < b.x ? b.x : (x > b.y ? b.y : x);
+    }
     default: break;
+    }
+    if (op >= OP_EXPP && op <= OP_EXPD_D) {
+        const int pos = cone_of[e];
+        const double *p0 = in + (e - pos);
+        const double v[3] = {p0[0], p0[1], p0[2]};
+        double y[3];
+        if (op == OP_EXPP) {  // P_K(x)
+            proj_exp_cone(v, y);
+            return y[pos];
+        }
+        if (op == OP_EXPP_D || op == OP_EXPD) {  // x + P_K(-x)   (cones.jl:80-85 / IndExpDual by Moreau)
+            const double nv[3] = {-v[0], -v[1], -v[2]};
+            proj_exp_cone(nv, y);
+            return add_(x, y[pos]);
+        }
+        // proxDual! of ExpDual: x + P_K*(-x),  P_K*(-x) = -x + P_K(x)
+        proj_exp_cone(v, y);
+        return add_(x, add_(-x, y[pos]));
     }
     const SocScale S = scale[cone_of[e]];
     if (op == OP_SOC_HEAD) return S.mode == 0 ? 0.0 : (S.mode == 1 ? x : mul_(S.rho, S.nx));
@@ -502,8 +616,26 @@ __device__ __forceinline__ double cone_project(uint8_t op, double x, const doubl
         const double pj = S.mode == 0 ? 0.0 : (S.mode == 1 ? -x : mul_(S.rho, S.nx));
         return add_(x, pj);
     }
-    const double pj = S.mode == 0 ? 0.0 : (S.mode == 1 ? -x : mul_(S.rho, -x));
-    return add_(x, pj);
+    if (op == OP_SOCD_TAIL) {
+        const double pj = S.mode == 0 ? 0.0 : (S.mode == 1 ? -x : mul_(S.rho, -x));
+        return add_(x, pj);
+    }
+    // rotated SOC
+    const bool dual = op >= OP_RSOCD_H0;
+    const double sg = dual ? -1.0 : 1.0;
+    double pj;
+    if (op == OP_RSOC_TAIL || op == OP_RSOCD_TAIL) {
+        pj = S.mode == 0 ? 0.0 : (S.mode == 1 ? sg * x : mul_(S.rho, sg * x));
+    } else {
+        const int64_t head = soc[cone_of[e]].head;
+        double r1, r2;
+        rsoc_rotate(sg * in[head], sg * in[head + 1], r1, r2);
+        const double y1 = S.mode == 0 ? 0.0 : (S.mode == 1 ? r1 : mul_(S.rho, S.nx));
+        const double y2 = S.mode == 0 ? 0.0 : (S.mode == 1 ? r2 : mul_(S.rho, r2));
+        const bool first = (op == OP_RSOC_H0 || op == OP_RSOCD_H0);
+        pj = first ? add_(mul_(RSOC_C, y1), mul_(RSOC_C, y2)) : sub_(mul_(RSOC_C, y1), mul_(RSOC_C, y2));
+    }
+    return dual ? add_(x, pj) : pj;
 }
 
 enum { EPI_NONE = 0, EPI_GAP = 1, EPI_GAPA = 2, EPI_FISTA = 3, EPI_DYKSTRA = 4, EPI_GAPP_PROJ = 5, EPI_LS = 6, EPI_LSW = 7 };
@@ -532,8 +664,8 @@ struct EpiArgs {
 template <int EPI>
 __global__ void __launch_bounds__(VBLOCK)
 k4_cone_apply(int64_t NP, const double *__restrict__ in, double *__restrict__ proj, const uint8_t *__restrict__ ops,
-              const int32_t *__restrict__ cone_of, const SocScale *__restrict__ scale, EpiArgs E, Ctrl *ctrl,
-              RedBuf rb)
+              const int32_t *__restrict__ cone_of, const SocScale *__restrict__ scale, const SocCone *__restrict__ soc,
+              const double2 *__restrict__ box, EpiArgs E, Ctrl *ctrl, RedBuf rb)
 {
     double a2 = E.a2, om_a2 = E.om_a2;
     if (EPI == EPI_GAPA || ((EPI == EPI_GAPP_PROJ || EPI == EPI_LSW) && E.use_a12)) {
@@ -543,7 +675,7 @@ k4_cone_apply(int64_t NP, const double *__restrict__ in, double *__restrict__ pr
     double q[3] = {0, 0, 0};
     for (int64_t e = (int64_t)blockIdx.x * VBLOCK + threadIdx.x; e < NP; e += (int64_t)gridDim.x * VBLOCK) {
         const double t1 = in[e];
-        const double pj = cone_project(ops[e], t1, proj, e, cone_of, scale);
+        const double pj = cone_project(ops[e], t1, proj, e, cone_of, scale, in, box, soc);
         proj[e] = pj;
         if (EPI == EPI_GAP || EPI == EPI_GAPA) {
             const double t2 = add_(mul_(a2, pj), mul_(om_a2, t1));

@@ -131,24 +131,41 @@ void ConeSet::build(int64_t NP_, const std::vector<ConeSeg> &segs)
         case FOS_CONE_ZERO: op = s.dual ? OP_COPY : OP_ZERO; break;  // cones.jl:98
         case FOS_CONE_NONNEG: op = OP_MAX0; break;                   // cones.jl:101
         case FOS_CONE_NONPOS: op = OP_MIN0; break;                   // cones.jl:102
-        case FOS_CONE_SOC: {
+        case FOS_CONE_SOC:
+        case FOS_CONE_SOCROT: {
             if (s.len == 0) continue;
+            const bool rot = s.type == FOS_CONE_SOCROT;
+            FOS_REQUIRE(!rot || s.len >= 2, "a rotated SOC needs at least 2 entries");
             SocCone c;
             c.head = s.off;
             c.len = s.len;
             c.dual = s.dual;
-            c.pad_ = 0;
+            c.rot = rot ? 1 : 0;
             c.chunk0 = (int32_t)h_chunk_cone.size();
-            int64_t tail = s.len - 1;
+            int64_t tail = s.len - (rot ? 2 : 1);
             c.nchunk = (int32_t)std::max<int64_t>(1, (tail + SOC_CHUNK - 1) / SOC_CHUNK);
             for (int k = 0; k < c.nchunk; k++) h_chunk_cone.push_back((int32_t)h_soc.size());
-            h_ops[(size_t)s.off] = s.dual ? OP_SOCD_HEAD : OP_SOC_HEAD;
-            h_cone_of[(size_t)s.off] = (int32_t)h_soc.size();
-            for (int64_t k = 1; k < s.len; k++) {
-                h_ops[(size_t)(s.off + k)] = s.dual ? OP_SOCD_TAIL : OP_SOC_TAIL;
+            const int64_t nhead = rot ? 2 : 1;
+            for (int64_t k = 0; k < s.len; k++) {
+                uint8_t o;
+                if (rot) o = k == 0 ? (s.dual ? OP_RSOCD_H0 : OP_RSOC_H0) : k == 1 ? (s.dual ? OP_RSOCD_H1 : OP_RSOC_H1)
+                                                                                  : (s.dual ? OP_RSOCD_TAIL : OP_RSOC_TAIL);
+                else o = k < nhead ? (s.dual ? OP_SOCD_HEAD : OP_SOC_HEAD) : (s.dual ? OP_SOCD_TAIL : OP_SOC_TAIL);
+                h_ops[(size_t)(s.off + k)] = o;
                 h_cone_of[(size_t)(s.off + k)] = (int32_t)h_soc.size();
             }
             h_soc.push_back(c);
+            continue;
+        }
+        case FOS_CONE_EXPPRIMAL:
+        case FOS_CONE_EXPDUAL: {
+            // cones.jl:12-13; a cone entry may hold several 3-blocks (MathProgBase passes one triple per cone)
+            FOS_REQUIRE(s.len % 3 == 0, "exponential cones have 3 entries");
+            const uint8_t o = s.type == FOS_CONE_EXPPRIMAL ? (s.dual ? OP_EXPP_D : OP_EXPP) : (s.dual ? OP_EXPD_D : OP_EXPD);
+            for (int64_t k = 0; k < s.len; k++) {
+                h_ops[(size_t)(s.off + k)] = o;
+                h_cone_of[(size_t)(s.off + k)] = (int32_t)(k % 3);
+            }
             continue;
         }
         case FOS_CONE_SDP: {
@@ -170,13 +187,16 @@ void ConeSet::build(int64_t NP_, const std::vector<ConeSeg> &segs)
             continue;
         }
         default:
-            throw Error(FOS_ERR_UNSUPPORTED, "cone type " + std::to_string(s.type) +
-                                                 " is outside the hot-path scope (SOCRotated/Exp cones: SURVEY 8f)");
+            throw Error(FOS_ERR_UNSUPPORTED, "unknown cone type " + std::to_string(s.type));
         }
         for (int64_t k = 0; k < s.len; k++) h_ops[(size_t)(s.off + k)] = op;
     }
     ops.upload(h_ops);
     cone_of.upload(h_cone_of);
+    h_ops_keep = h_ops;
+    h_cone_of_keep = h_cone_of;
+    h_box.clear();
+    box.release();
     nsoc = (int)h_soc.size();
     nchunks = (int)h_chunk_cone.size();
     if (nsoc > 0) {
@@ -190,6 +210,23 @@ void ConeSet::build(int64_t NP_, const std::vector<ConeSeg> &segs)
     if (!psd_large.empty()) d_psd_large.upload(psd_large);
 }
 
+// IndBox(lo, hi) over padded entries [off, off+len): overrides whatever elementwise cone was there
+void ConeSet::set_box(int64_t off, int64_t len, double lo, double hi)
+{
+    FOS_REQUIRE(off >= 0 && len >= 0 && off + len <= NP, "box range out of bounds");
+    FOS_REQUIRE(!(lo > hi), "IndBox needs lo <= hi");
+    for (int64_t k = 0; k < len; k++) {
+        const uint8_t o = h_ops_keep[(size_t)(off + k)];
+        FOS_REQUIRE(o <= OP_MIN0 || o == OP_BOX, "a box cannot overlap a SOC / SDP / exponential cone");
+        h_ops_keep[(size_t)(off + k)] = OP_BOX;
+        h_cone_of_keep[(size_t)(off + k)] = (int32_t)h_box.size();
+    }
+    h_box.push_back(make_double2(lo, hi));
+    ops.upload(h_ops_keep);
+    cone_of.upload(h_cone_of_keep);
+    box.upload(h_box);
+}
+
 void Handle::cone_project(ConeSet &K, const double *in, double *projbuf, int epi, const EpiArgs &E)
 {
     if (K.nsoc > 0)
@@ -201,7 +238,7 @@ void Handle::cone_project(ConeSet &K, const double *in, double *projbuf, int epi
 #define CONE_CASE(EPI)                                                                                            \
     case EPI:                                                                                                     \
         FOS_LAUNCH(this, k4_cone_apply<EPI>, g, VBLOCK, 0, K.NP, in, projbuf, K.ops.p, K.cone_of.p, K.soc_scale.p, \
-                   E, d_ctrl.p, rb);                                                                              \
+                   K.soc.p, K.box.p, E, d_ctrl.p, rb);                                                            \
         break;
     switch (epi) {
         CONE_CASE(EPI_NONE)
@@ -348,8 +385,8 @@ void Handle::load_affine(int64_t am, int64_t an, const double *b, const double *
         if (a1 <= an) segs.push_back(ConeSeg{t[k], 0, a0, l[k]});
         else if (a0 >= an) segs.push_back(ConeSeg{t[k], 0, L.n_pad + (a0 - an), l[k]});
         else {
-            FOS_REQUIRE(t[k] != FOS_CONE_SOC && t[k] != FOS_CONE_SDP,
-                        "a SOC/SDP cone may not straddle the x/z boundary of the affine form");
+            FOS_REQUIRE(t[k] >= FOS_CONE_FREE && t[k] <= FOS_CONE_NONPOS,
+                        "only elementwise cones may straddle the x/z boundary of the affine form");
             segs.push_back(ConeSeg{t[k], 0, a0, an - a0});
             segs.push_back(ConeSeg{t[k], 0, L.n_pad, a1 - an});
         }

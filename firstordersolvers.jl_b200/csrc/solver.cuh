@@ -161,6 +161,11 @@ struct ConeSet {
     DevBuf<uint8_t> ops;
     DevBuf<int32_t> cone_of;
     DevBuf<SocCone> soc;
+    DevBuf<double2> box;  // IndBox bounds, indexed by cone_of[e] where ops[e] == OP_BOX
+    std::vector<double2> h_box;
+    std::vector<uint8_t> h_ops_keep;
+    std::vector<int32_t> h_cone_of_keep;
+    void set_box(int64_t off, int64_t len, double lo, double hi);
     DevBuf<SocScale> soc_scale;
     DevBuf<int32_t> chunk_cone;
     DevBuf<double> chunk_sum;

@@ -741,7 +741,19 @@ class FeasibilityModel:  # Feasibility.jl:15-49
         am, an = Am.shape
         if am + an != problem.n:
             raise AssertionError("Feasibility.n must equal an + am")
-        t, ln = _cone_arrays(problem.S2.cones, am + an, "S2")
+        # ("Box", range-or-length, lo, hi) entries are IndBox(lo, hi) (ProximalOperators): loaded as Free, then
+        # turned into clamps with fos_set_box
+        plain, boxes, pos = [], [], 0
+        for entry in problem.S2.cones:
+            name = entry[0].lstrip(":") if isinstance(entry[0], str) else entry[0]
+            cnt = int(entry[1]) if isinstance(entry[1], (int, np.integer)) else len(entry[1])
+            if name == "Box":
+                boxes.append((pos, cnt, float(entry[2]), float(entry[3])))
+                plain.append(("Free", entry[1]))
+            else:
+                plain.append((entry[0], entry[1]))
+            pos += cnt
+        t, ln = _cone_arrays(plain, am + an, "S2")
         b = _f64(S1.b)
         q = _f64(S1.q)
         H = _Handle(int(allkw.get("device", 0)))
@@ -749,6 +761,8 @@ class FeasibilityModel:  # Feasibility.jl:15-49
         H.ck(H.L.fos_load_affine_csc(H.h, am, an, _i64p(colptr), _i64p(rowval), _d(nzval), 0, _d(b), _d(q),
                                      int(S1.β), 1 if S1.decreasing_accuracy else 0, len(t), _i32p(t), _i64p(ln),
                                      storage))
+        for (start, cnt, lo, hi) in boxes:
+            H.ck(H.L.fos_set_box(H.h, start, cnt, lo, hi))
         H.set_algorithm(alg)
         self.data = H
         self._form = "feas"

@@ -46,10 +46,10 @@ typedef struct fos_handle_s *fos_handle_t;
 #define FOS_CONE_NONNEG 2
 #define FOS_CONE_NONPOS 3
 #define FOS_CONE_SOC 4
-#define FOS_CONE_SOCROT 5    /* in conemap; FOS_ERR_UNSUPPORTED ("next") */
+#define FOS_CONE_SOCROT 5    /* IndRotatedSOC on (x1, x2, w): 2 x1 x2 >= ||w||^2, x1, x2 >= 0 */
 #define FOS_CONE_SDP 6
-#define FOS_CONE_EXPPRIMAL 7 /* FOS_ERR_UNSUPPORTED ("next") */
-#define FOS_CONE_EXPDUAL 8   /* FOS_ERR_UNSUPPORTED ("next") */
+#define FOS_CONE_EXPPRIMAL 7 /* IndExpPrimal: cl{(r,s,t): s > 0, s exp(r/s) <= t}, triples */
+#define FOS_CONE_EXPDUAL 8   /* IndExpDual (its dual cone) */
 
 /* ---- algorithm codes: solvers/{gap,gapa,fista,dykstra,gapproj}.jl --------------------- */
 #define FOS_ALG_GAP 0     /* GAP(alpha,alpha1,alpha2) gap.jl:6-13; DR/AP are GAP(a,2,2)/GAP(a,1,1) solvers.jl:10-11 */
@@ -162,6 +162,10 @@ int32_t fos_load_affine_csc(fos_handle_t h, int64_t am, int64_t an, const int64_
  * p = q = 0) like init_algorithm!; does NOT reset S1's warm start / call counter. */
 int32_t fos_set_algorithm(fos_handle_t h, int32_t alg, double alpha, double alpha1, double alpha2, double beta,
                           int64_t iproj);
+/* IndBox(lo, hi) (ProximalOperators; S2 of test/testfeasibility.jl:10) on entries [start, start+len) (0-based) of
+ * the Feasibility iterate [x; z]: the projection clamps to [lo, hi] (use +-INFINITY for one-sided boxes).  Call
+ * after fos_load_affine_csc; it overrides the elementwise cone given there for that range. */
+int32_t fos_set_box(fos_handle_t h, int64_t start, int64_t len, double lo, double hi);
 /* LineSearchWrapper(alg; lsinterval) (wrappers/linesearch.jl:19-75) around GAP / GAPA (the algorithms with
  * support_linesearch, gap.jl:89, gapa.jl:117): on iterations i % lsinterval == 0 the step is replaced by one
  * relaxed S1/S2 pass (with the status check inside S2!), 31 trial steps x = x0 + alpha*res, alpha = 0.1*1.8^(k+1),

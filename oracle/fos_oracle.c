@@ -40,10 +40,10 @@ enum {
     CONE_NONNEG = 2,
     CONE_NONPOS = 3,
     CONE_SOC = 4,
-    CONE_SOCROT = 5, /* in conemap, outside every config: not restated */
+    CONE_SOCROT = 5, /* IndRotatedSOC -- parity unpinned: no reference test touches it */
     CONE_SDP = 6,
-    CONE_EXPPRIMAL = 7, /* not restated */
-    CONE_EXPDUAL = 8    /* not restated */
+    CONE_EXPPRIMAL = 7, /* IndExpPrimal -- parity unpinned, see prox_exp */
+    CONE_EXPDUAL = 8    /* IndExpDual */
 };
 
 /* algorithm codes (solvers/*.jl) */
@@ -419,9 +419,101 @@ static void prox_soc(double *y, const double *x, int64_t len)
     }
 }
 
+/* IndRotatedSOC of ProximalOperators.jl (published algorithm, restated): rotate (x1, x2) by pi/4 with the
+ * literal 0.7071067811865475, project (x1', (x2', w)) onto the SOC, rotate back.  PARITY UNPINNED. */
+static void prox_socrot(double *y, const double *x, int64_t len)
+{
+    const double c = 0.7071067811865475;
+    double x1 = c * x[0] + c * x[1];
+    double x2 = c * x[0] - c * x[1];
+    double nw = vnorm(x + 2, len - 2);
+    double nx = sqrt(x2 * x2 + nw * nw);
+    double t = x1, y1, y2;
+    if (t <= -nx) {
+        for (int64_t i = 0; i < len; i++) y[i] = 0.0;
+        y1 = 0.0; y2 = 0.0;
+    } else if (t >= nx) {
+        y1 = x1; y2 = x2;
+        for (int64_t i = 2; i < len; i++) y[i] = x[i];
+    } else {
+        double r = 0.5 * (1.0 + t / nx);
+        y1 = r * nx; y2 = r * x2;
+        for (int64_t i = 2; i < len; i++) y[i] = r * x[i];
+    }
+    y[0] = c * y1 + c * y2;
+    y[1] = c * y1 - c * y2;
+}
+
+/* Exponential cone cl{(r,s,t): s > 0, s exp(r/s) <= t}.  ProximalOperators' IndExpPrimal follows the projection
+ * of SCS (cones.c: proj_exp_cone, exp_newton_one_d, exp_calc_grad, exp_get_rho_ub), restated here with its
+ * tolerance 1e-8 and iteration caps of 100.  PARITY UNPINNED (un-vendored dependency, no reference test). */
+#define EXP_TOL 1e-8
+static double exp_newton_one_d(double rho, double y_hat, double z_hat)
+{
+    double t = fmax(-z_hat, 1e-6);
+    for (int i = 0; i < 100; i++) {
+        double f = t * (t + z_hat) / rho / rho - y_hat / rho + log(t / rho) + 1.0;
+        double fp = (2.0 * t + z_hat) / rho / rho + 1.0 / t;
+        t = t - f / fp;
+        if (t <= -z_hat) return 0.0;
+        else if (t <= 0.0) return z_hat;
+        else if (fabs(f) < EXP_TOL) break;
+    }
+    return t + z_hat;
+}
+static double exp_calc_grad(const double *v, double *x, double rho)
+{
+    x[2] = exp_newton_one_d(rho, v[1], v[2]);
+    x[1] = (x[2] - v[2]) * x[2] / rho;
+    x[0] = v[0] - rho;
+    if (x[1] <= 1e-12) return x[0];
+    return x[0] + x[1] * log(x[1] / x[2]);
+}
+static void prox_exp3(double *y, const double *v)
+{
+    double r = v[0], s = v[1], t = v[2];
+    if ((s * exp(r / s) - t <= EXP_TOL && s > 0.0) || (r <= 0.0 && s == 0.0 && t >= 0.0)) {
+        y[0] = r; y[1] = s; y[2] = t;
+        return;
+    }
+    if ((-r < 0.0 && r * exp(s / r) + exp(1.0) * t <= EXP_TOL) || (-r == 0.0 && -s >= 0.0 && -t >= 0.0)) {
+        y[0] = y[1] = y[2] = 0.0;
+        return;
+    }
+    if (r < 0.0 && s < 0.0) {
+        y[0] = r; y[1] = 0.0; y[2] = fmax(t, 0.0);
+        return;
+    }
+    double x[3], lb = 0.0, ub = 0.125;
+    while (exp_calc_grad(v, x, ub) > 0.0) { lb = ub; ub *= 2.0; }
+    for (int i = 0; i < 100; i++) {
+        double rho = (ub + lb) / 2.0;
+        double g = exp_calc_grad(v, x, rho);
+        if (g > 0.0) lb = rho; else ub = rho;
+        if (ub - lb < EXP_TOL) break;
+    }
+    y[0] = x[0]; y[1] = x[1]; y[2] = x[2];
+}
+static int prox_exp(double *y, const double *x, int64_t len, int dualcone)
+{
+    if (len % 3 != 0) return -1;
+    for (int64_t k = 0; k < len; k += 3) {
+        if (!dualcone) prox_exp3(y + k, x + k);
+        else { /* IndExpDual by Moreau: x + P_K(-x) */
+            double nv[3] = {-x[k], -x[k + 1], -x[k + 2]}, p[3];
+            prox_exp3(p, nv);
+            for (int j = 0; j < 3; j++) y[k + j] = x[k + j] + p[j];
+        }
+    }
+    return 0;
+}
+
 static int prox_cone(double *y, int type, const double *x, int64_t len)
 {
     switch (type) {
+    case CONE_SOCROT: if (len < 2) return -1; prox_socrot(y, x, len); return 0;
+    case CONE_EXPPRIMAL: return prox_exp(y, x, len, 0);
+    case CONE_EXPDUAL: return prox_exp(y, x, len, 1);
     case CONE_FREE: for (int64_t i = 0; i < len; i++) y[i] = x[i]; return 0;
     case CONE_ZERO: for (int64_t i = 0; i < len; i++) y[i] = 0.0; return 0;
     case CONE_NONNEG: for (int64_t i = 0; i < len; i++) y[i] = x[i] > 0.0 ? x[i] : 0.0; return 0;
@@ -543,6 +635,9 @@ typedef struct {
        Cholesky factor of I + Q Q' (ProximalOperators factorises the same normal equations) */
     int direct;
     double *chol; /* l x l, lower triangle, row-major */
+    /* IndBox(lo, hi) entries of S2 in the Feasibility form (test/testfeasibility.jl:10) */
+    double *box_lo, *box_hi;
+    unsigned char *box_on;
     /* LineSearchWrapper (wrappers/linesearch.jl): 0 = no wrapper */
     int64_t lsinterval;
     double *ls1, *ls2, *ls3, *lsres; /* LineSearchWrapperData tmp1, tmp2, tmp3, res (:9-17) */
@@ -639,6 +734,7 @@ FOSOR_API void fosor_destroy(void *h)
     free(M->dp); free(M->dq); free(M->dy); free(M->work1); free(M->work2); free(M->work3); free(M->prev);
     free(M->chol);
     free(M->ls1); free(M->ls2); free(M->ls3); free(M->lsres);
+    free(M->box_on); free(M->box_lo); free(M->box_hi);
     free(M);
 }
 
@@ -716,7 +812,26 @@ FOSOR_API int32_t fosor_get_cg_warned(void *h) { return ((model_t *)h)->S1->cg_m
 static void prox_S2(model_t *M, double *y, const double *x)
 {
     if (M->form == 0) dualconeprod_prox(y, &M->K1, &M->K2, x);
-    else coneprod_prox(y, &M->K1, x, 0);
+    else {
+        coneprod_prox(y, &M->K1, x, 0);
+        if (M->box_on)
+            for (int64_t i = 0; i < M->N; i++)
+                if (M->box_on[i]) y[i] = x[i] < M->box_lo[i] ? M->box_lo[i] : (x[i] > M->box_hi[i] ? M->box_hi[i] : x[i]);
+    }
+}
+
+/* IndBox(lo, hi) on entries [start, start+len) of the Feasibility iterate */
+FOSOR_API int32_t fosor_set_box(void *h, int64_t start, int64_t len, double lo, double hi)
+{
+    model_t *M = (model_t *)h;
+    if (M->form != 1 || start < 0 || len < 0 || start + len > M->N || lo > hi) return -1;
+    if (!M->box_on) {
+        M->box_on = (unsigned char *)calloc((size_t)M->N, 1);
+        M->box_lo = (double *)calloc((size_t)M->N, sizeof(double));
+        M->box_hi = (double *)calloc((size_t)M->N, sizeof(double));
+    }
+    for (int64_t i = start; i < start + len; i++) { M->box_on[i] = 1; M->box_lo[i] = lo; M->box_hi[i] = hi; }
+    return 0;
 }
 /* prox of IndAffine(B, 0) with B = [Q -I] (HSDE.jl:10-15; ProximalOperators' IndAffine:
  * y = z - B'(B B')^{-1} B z, B B' = Q Q' + I):   w = Q u - v ;  (I + Q Q') t = w ;  y = [u - Q't ; v + t] */

@@ -59,6 +59,8 @@ def lib():
     L.fosor_create_feasibility.argtypes = [C.c_int64, C.c_int64, _ip, _ip, _dp, C.c_int64, _dp, _dp,
                                            C.c_int64, C.c_int32, C.c_int64, _i32p, _ip]
     L.fosor_destroy.argtypes = [C.c_void_p]
+    L.fosor_set_box.restype = C.c_int32
+    L.fosor_set_box.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_double, C.c_double]
     L.fosor_set_linesearch.restype = C.c_int32
     L.fosor_set_linesearch.argtypes = [C.c_void_p, C.c_int64]
     L.fosor_set_direct.restype = C.c_int32
@@ -153,6 +155,11 @@ class _OracleBase:
     # -- algorithm (a20) -------------------------------------------------------------
     def set_algorithm(self, name, alpha=0.8, alpha1=1.8, alpha2=1.8, beta=0.0, iproj=100):
         lib().fosor_set_algorithm(self._h, ALG_CODES[name], alpha, alpha1, alpha2, beta, iproj)
+
+    def set_box(self, start, length, lo, hi):
+        """IndBox(lo, hi) on entries [start, start+length) of the Feasibility iterate (0-based)."""
+        if lib().fosor_set_box(self._h, int(start), int(length), float(lo), float(hi)) != 0:
+            raise ValueError("bad box")
 
     def set_linesearch(self, lsinterval):
         """LineSearchWrapper(alg; lsinterval) (wrappers/linesearch.jl:19-24); 0 removes the wrapper."""

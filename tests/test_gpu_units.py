@@ -205,6 +205,112 @@ def test_prox_cone_elementwise_and_soc(fos, oracle, name, ln, dual):
             np.testing.assert_array_equal(H.prox_cone(name, x, dual), oracle.prox_cone(name, x, dual))
 
 
+@pytest.mark.parametrize("ln", [2, 3, 4, 9, 2051, 6000])
+@pytest.mark.parametrize("dual", [False, True])
+def test_prox_rotated_soc(fos, oracle, ln, dual):
+    """IndRotatedSOC (cones.jl:10): against the oracle, against R' P_SOC(R x) with the pi/4 rotation of the
+    first two entries, and as a projection (membership 2 y1 y2 >= ||w||^2, idempotence)."""
+    H = fos.Handle(0)
+    rng = np.random.default_rng(ln)
+    for scale in (1.0, 10.0, 0.1, -3.0):
+        x = rng.standard_normal(ln)
+        x[:2] *= scale
+        y = H.prox_cone("SOCRotated", x, dual)
+        assert rel_err(y, oracle.prox_cone("SOCRotated", x, dual)) < 1e-13
+        if not dual:
+            c = np.sqrt(0.5)
+            Rx = x.copy()
+            Rx[0], Rx[1] = c * x[0] + c * x[1], c * x[0] - c * x[1]
+            ps = oracle.prox_cone("SOC", Rx)
+            ref = ps.copy()
+            ref[0], ref[1] = c * ps[0] + c * ps[1], c * ps[0] - c * ps[1]
+            assert rel_err(y, ref) < 1e-12
+            assert y[0] >= -1e-12 and y[1] >= -1e-12
+            assert 2 * y[0] * y[1] - np.sum(y[2:] ** 2) >= -1e-9 * max(1.0, np.abs(x).max()) ** 2
+            assert rel_err(H.prox_cone("SOCRotated", y), y) < 1e-12 or np.abs(y).max() < 1e-12
+
+
+@pytest.mark.parametrize("name", ["ExpPrimal", "ExpDual"])
+@pytest.mark.parametrize("dual", [False, True])
+def test_prox_exponential_cones(fos, oracle, name, dual):
+    """IndExpPrimal / IndExpDual (cones.jl:12-13), SCS's bisection + Newton projection: device == oracle (same
+    algorithm; a bisection decision can flip on rounding, hence 1e-6), the result lies in the cone, the
+    projection is idempotent to the algorithm's own accuracy and obeys Moreau's decomposition."""
+    H = fos.Handle(0)
+    rng = np.random.default_rng(7)
+    X = rng.standard_normal((400, 3)) * rng.choice([0.3, 1.0, 5.0], size=(400, 1))
+    X[:5] = [[1.0, 1.0, 3.0], [0.0, 0.0, 1.0], [-1.0, -1.0, 2.0], [-1.0, -2.0, -3.0], [2.0, 0.5, -1.0]]
+    x = X.reshape(-1)                         # one cone entry holding 400 triples
+    y = H.prox_cone(name, x, dual).reshape(-1, 3)
+    yo = oracle.prox_cone(name, x, dual).reshape(-1, 3)
+    assert np.abs(y - yo).max() <= 1e-6 * 5
+    assert np.median(np.abs(y - yo)) < 1e-13
+    if name == "ExpPrimal" and not dual:
+        r, s, t = y[:, 0], y[:, 1], y[:, 2]
+        with np.errstate(all="ignore"):
+            inside = ((s > 0) & (s * np.exp(r / np.where(s > 0, s, 1.0)) <= t + 1e-4 * 5)) | \
+                     ((r <= 1e-6) & (np.abs(s) <= 1e-6) & (t >= -1e-6))
+        assert inside.all()
+        y2 = H.prox_cone(name, y.reshape(-1)).reshape(-1, 3)
+        assert np.abs(y2 - y).max() < 1e-5 * 5
+        # Moreau: x = P_K(x) - P_K*(-x), with <P_K(x), P_K*(-x)> = 0
+        pd = H.prox_cone("ExpDual", -x).reshape(-1, 3)
+        assert np.abs(y - pd - X).max() < 1e-12 * 5
+        assert np.abs(np.sum(y * pd, axis=1)).max() < 1e-5 * 25
+
+
+def test_dual_cone_product_with_every_cone_type(fos, oracle):
+    """cones.jl:122-142 with all nine cone types of conemap in K1 (supportedcones, FOSSolverInterface.jl:69)."""
+    from fos_b200 import problems
+    rng = np.random.default_rng(11)
+    c1 = [("Zero", 4), ("SOCRotated", 7), ("ExpPrimal", 3), ("NonNeg", 5), ("ExpDual", 3), ("SOC", 6), ("SDP", 6),
+          ("SOCRotated", 2), ("ExpPrimal", 3), ("NonPos", 2), ("Free", 3)]
+    m = sum(l for _, l in c1)
+    c2 = [("Free", 9), ("NonNeg", 4)]
+    n = sum(l for _, l in c2)
+    A = sp.random(m, n, density=0.4, random_state=rng, data_rvs=rng.standard_normal).tocsc()
+    P = problems.ConicProblem(rng.standard_normal(n), A, rng.standard_normal(m), c1, c2)
+    O = oracle.OracleConic(P.c, P.A, P.b, P.constr_cones, P.var_cones)
+    H = load_conic(fos, P)
+    for _ in range(4):
+        z = rng.standard_normal(2 * (m + n + 1)) * 2
+        assert np.abs(H.cone_prox(z) - O.cone_prox(z)).max() < 1e-6      # exp cones: 1e-6, everything else 1e-12
+    # a few GAP iterations run end to end in lock-step
+    O.set_algorithm("GAP", 0.8, 1.8, 1.8, 0.0, 100)
+    H.set_algorithm(fos.GAP())
+    O.set_iterate(O.initial_value())
+    H.ck(H.L.fos_begin_solve(H.h))
+    for i in range(1, 6):
+        H.set_state("x", O.get_state("x"))
+        if O.s1_calls > 1:
+            H.set_state("xinit", O.get_state("xinit"))
+        H.set_info("s1_calls", O.s1_calls)
+        O.run(i, 1, checki=100, eps=1e-9)
+        H.run(i, 1, 100, 1e-9)
+        assert rel_err(H.get_iterate(), O.get_state("x")) < 1e-5
+
+
+def test_feasibility_with_indbox(fos, oracle):
+    """test/testfeasibility.jl:9-19 shape: S2 = IndBox(0, Inf) on x (here also a two-sided box), S1 affine."""
+    from fos_b200 import problems
+    A, b, _ = problems.feasibility_problem(30, 60, seed=4)
+    for lo, hi in ((0.0, np.inf), (0.0, 2.5)):
+        cones = [("Box", 60, lo, hi), ("Zero", 30)]
+        prob = fos.Feasibility(fos.AffinePlusLinear(A, b, np.zeros(60), 1), fos.ConeProduct(cones), 90)
+        sol, model = fos.solve(prob, fos.DR(eps=1e-8, verbose=0), checki=10, max_iters=4000)
+        O = oracle.OracleFeasibility(A, b, np.zeros(60), 1, [("Free", 60), ("Zero", 30)])
+        O.set_box(0, 60, lo, hi)
+        O.set_algorithm("GAP", 0.5, 2.0, 2.0, 0.0, 100)
+        O.set_iterate(O.initial_value())
+        ro = O.solve(max_iters=4000, checki=10, eps=1e-8)
+        assert sol.status == ro["status"]
+        assert abs(model.last_iteration - ro["iterations"]) <= 10
+        if sol.status == "Optimal":
+            x = sol.x[:60]
+            assert x.min() > lo - 1e-9 and x.max() < hi + 1e-9
+            assert np.abs(A @ x - b).max() < 1e-6
+
+
 YS = np.array([[-0.0064709, -0.22443], [-0.22443, -1.02411]])          # test/testPSD.jl:3-4
 P_PSD_YS = np.array([[0.03909044662082823, -0.00823811392936668],
                      [-0.00823811392936668, 0.00173614084718757]])
@@ -293,7 +399,7 @@ def test_errors_are_loud(fos):
     with pytest.raises(fos.FosError):
         H.get_iterate()                      # nothing loaded
     with pytest.raises(fos.FosError):
-        H.prox_cone("ExpPrimal", np.ones(3))  # outside the hot-path scope -> FOS_ERR_UNSUPPORTED
+        H.prox_cone("ExpPrimal", np.ones(4))  # exponential cones come in triples
     P = problems.nnls_conic(4, 5, 1)
     P.constr_cones = [("SOC", 5)]            # does not cover 1:m
     with pytest.raises((fos.FosError, AssertionError)):
