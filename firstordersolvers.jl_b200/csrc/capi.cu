@@ -94,6 +94,8 @@ int32_t fos_set_option(fos_handle_t hh, const char *key, double value)
         h.cg_batch = (int)value;
     } else if (k == "fuse_rhs") {
         h.fuse_rhs = value != 0;
+    } else if (k == "psd_warm") {
+        h.cones.psd_warm_enabled = value != 0;
     } else if (k == "fuse_tail") {
         h.fuse_tail = value != 0;
     } else if (k == "profile_matvec") {

@@ -27,6 +27,7 @@
 namespace fos {
 
 constexpr int PL_MAX_SWEEPS = 48;
+constexpr int PL_MAX_BLOCKS = 128;  // d_pad / BS for d <= 1024
 constexpr int PL_TILE = 64;
 constexpr int PL_JC = 32;  // columns of W per shared-memory chunk of the final product
 
@@ -37,6 +38,8 @@ struct PsdLargeCtl {  // one per cone, zeroed before every launch
     unsigned int flag;  // last completed barrier target, on its own cache line (the waiters poll this one)
     unsigned int pad1_[31];
     unsigned long long maxcos[PL_MAX_SWEEPS];  // bit pattern of the largest |cos| seen in sweep k
+    unsigned int ready[PL_MAX_BLOCKS];  // version of every column block in global memory: 1 after the initial
+                                        // fill, +1 per Jacobi step (each block is rotated once per step)
 };
 
 struct PsdLargeArgs {
@@ -46,6 +49,9 @@ struct PsdLargeArgs {
     double *work;
     int64_t work_stride;  // doubles per cone: G [d_pad][dS] | M [d_pad][dS] | lam [d_pad]
     PsdLargeCtl *ctl;
+    double *vstore;       // per cone: the orthonormal eigenvector basis V of the previous projection [d_pad][dS]
+    int64_t vstore_stride;
+    int warm;             // 1: start from G = (M + sigma I) V_prev instead of G = M + sigma I
     int CT;     // CTAs per cone; the tournament has 2*CT blocks
     int d_pad;  // padded number of columns = 2*CT*bs
 };
@@ -199,6 +205,26 @@ __device__ __forceinline__ void rotate_pair_reg(double2 (&P)[DK], double &al, do
     al = fma(-t, ga, al);
 }
 
+// acc[j] = sum_k M[i][k] * vc[j][k] for the BS columns vc (shared memory) and row i; M symmetric, column k
+// contiguous in global memory (so the loads of a warp are coalesced over i)
+template <int BS, int DS>
+__device__ __forceinline__ void sym_times_cols(const double *__restrict__ M0, int d, const double *vc, int i,
+                                               double (&acc)[BS])
+{
+#pragma unroll
+    for (int j = 0; j < BS; j++) acc[j] = 0.0;
+    for (int k = 0; k < d; k += 2) {
+        const double a0 = M0[(size_t)k * DS + i];
+        const double a1 = (k + 1 < d) ? M0[(size_t)(k + 1) * DS + i] : 0.0;
+#pragma unroll
+        for (int j = 0; j < BS; j++) {
+            const double2 v = *reinterpret_cast<const double2 *>(vc + (size_t)j * DS + k);
+            acc[j] = fma(a0, v.x, acc[j]);
+            acc[j] = fma(a1, v.y, acc[j]);
+        }
+    }
+}
+
 template <int DK>
 __global__ void __launch_bounds__(PLCfg<DK>::THREADS, 1) k5_psd_hestenes(const PsdLargeArgs a)
 {
@@ -274,18 +300,59 @@ __global__ void __launch_bounds__(PLCfg<DK>::THREADS, 1) k5_psd_hestenes(const P
         }
     }
     group_barrier(ctl, epoch, a.CT);
+    constexpr uint32_t BLK_BYTES0 = (uint32_t)(BS * DS * sizeof(double));
+    double *Vst = a.vstore + (size_t)cone * a.vstore_stride;
+    if (a.warm) {
+        // Warm start: consecutive solver iterates have nearly the same eigenvectors, so start the sweeps from
+        // G = (M + sigma I) V_prev (columns almost orthogonal already; V_prev is orthonormal, so the singular
+        // vectors of G are still the eigenvectors of M).  Each CTA builds the columns of its two blocks.
+        double *v0 = Vst + (size_t)(2 * cta) * BS * DS;
+        double *g0w = G + (size_t)(2 * cta) * BS * DS;
+        if (threadIdx.x == 0) {
+            asm volatile("fence.proxy.async;" ::: "memory");
+            mbar_expect_tx(&s_mbar, 2 * BLK_BYTES0);
+            bulk_load_1d(cols, v0, 2 * BLK_BYTES0, &s_mbar);
+        }
+        mbar_wait(&s_mbar, mphase);
+        mphase ^= 1;
+        for (int half = 0; half < 2; half++) {
+            const double *vc = cols + (size_t)half * BS * DS;
+            for (int i = threadIdx.x; i < DS; i += T) {
+                double acc[BS];
+                if (i < d) sym_times_cols<BS, DS>(M0, d, vc, i, acc);
+#pragma unroll
+                for (int j = 0; j < BS; j++)
+                    g0w[(size_t)(half * BS + j) * DS + i] = i < d ? fma(sigma, vc[(size_t)j * DS + i], acc[j]) : 0.0;
+            }
+        }
+        group_barrier(ctl, epoch, a.CT);
+    }
 
     // ---- phase 2: block Jacobi sweeps ----
+    // Between steps a CTA only depends on the two CTAs that rotated its next blocks: every block carries a
+    // version counter in global memory (ready[]), bumped by its owner after the store and awaited by the next
+    // owner before the load.  Only the current owner reads or writes a block, so there is no WAR hazard and no
+    // group-wide barrier inside a sweep (one per sweep remains, for the convergence test).
     constexpr uint32_t BLK_BYTES = (uint32_t)(BS * DS * sizeof(double));
     double prev_max = 1.0;
     int sweeps_done = 0;
+    unsigned int gstep = 0;  // global step counter: blocks must have version gstep + 1
     for (int sweep = 0; sweep < PL_MAX_SWEEPS; sweep++) {
         double lmax = 0.0;
-        for (int step = 0; step < NBk - 1; step++) {
+        for (int step = 0; step < NBk - 1; step++, gstep++) {
             int ba, bb;
             rr_pair_l(step, cta, NBk, ba, bb);
             double *ga_ = G + (size_t)ba * BS * DS, *gb_ = G + (size_t)bb * BS * DS;
             if (threadIdx.x == 0) {
+                if (gstep > 0) {
+                    const unsigned int want = gstep + 1u;
+                    unsigned int va, vb;
+                    do {
+                        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(va) : "l"(&ctl->ready[ba]) : "memory");
+                        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(vb) : "l"(&ctl->ready[bb]) : "memory");
+                    } while (va < want || vb < want);
+                    __threadfence();
+                }
                 asm volatile("fence.proxy.async;" ::: "memory");
                 mbar_expect_tx(&s_mbar, 2 * BLK_BYTES);
                 bulk_load_1d(cols, ga_, BLK_BYTES, &s_mbar);
@@ -340,6 +407,9 @@ __global__ void __launch_bounds__(PLCfg<DK>::THREADS, 1) k5_psd_hestenes(const P
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
                 asm volatile("fence.proxy.async;" ::: "memory");
+                __threadfence();
+                asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&ctl->ready[ba]), "r"(gstep + 2u) : "memory");
+                asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&ctl->ready[bb]), "r"(gstep + 2u) : "memory");
             }
             if (step == NBk - 2) {
                 // publish this CTA's largest |cos| of the sweep (non-negative doubles order like integers)
@@ -351,8 +421,10 @@ __global__ void __launch_bounds__(PLCfg<DK>::THREADS, 1) k5_psd_hestenes(const P
                     mx = sqrt(mx);  // lmax tracks cos^2
                     atomicMax(&ctl->maxcos[sweep], (unsigned long long)__double_as_longlong(mx));
                 }
+                group_barrier(ctl, epoch, a.CT);  // once per sweep: everybody's maxcos is in
+            } else {
+                __syncthreads();  // thread 0 has finished the store before the buffer is reused
             }
-            group_barrier(ctl, epoch, a.CT);
         }
         sweeps_done = sweep + 1;
         const double mx = __longlong_as_double((long long)*((volatile unsigned long long *)&ctl->maxcos[sweep]));
@@ -380,6 +452,14 @@ __global__ void __launch_bounds__(PLCfg<DK>::THREADS, 1) k5_psd_hestenes(const P
             const double inv = nn > 0.0 ? 1.0 / sqrt(nn) : 0.0;
             for (int i = lane; i < DS; i += 32) cp[i] *= inv;
         }
+        // keep the orthonormal basis for the next projection of this cone (warm start)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            bulk_store_1d(Vst + (size_t)(2 * cta) * BS * DS, cols, 2 * BLK_BYTES);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the source may be modified again
+        }
         __syncthreads();
         // Y = M V_J by halves of BS columns (register budget), lambda_j = sum_i v_ij y_ij
         for (int half = 0; half < 2; half++) {
@@ -390,18 +470,7 @@ __global__ void __launch_bounds__(PLCfg<DK>::THREADS, 1) k5_psd_hestenes(const P
             for (int i = threadIdx.x; i < DS; i += T) {
                 if (i >= d) continue;
                 double acc[BS];
-#pragma unroll
-                for (int j = 0; j < BS; j++) acc[j] = 0.0;
-                for (int k = 0; k < d; k += 2) {
-                    const double a0 = M0[(size_t)k * DS + i];
-                    const double a1 = (k + 1 < d) ? M0[(size_t)(k + 1) * DS + i] : 0.0;
-#pragma unroll
-                    for (int j = 0; j < BS; j++) {
-                        const double2 v = *reinterpret_cast<const double2 *>(vc + (size_t)j * DS + k);
-                        acc[j] = fma(a0, v.x, acc[j]);
-                        acc[j] = fma(a1, v.y, acc[j]);
-                    }
-                }
+                sym_times_cols<BS, DS>(M0, d, vc, i, acc);
 #pragma unroll
                 for (int j = 0; j < BS; j++) lp[j] = fma(acc[j], vc[(size_t)j * DS + i], lp[j]);
             }
@@ -511,6 +580,15 @@ __global__ void __launch_bounds__(PLCfg<DK>::THREADS, 1) k5_psd_hestenes(const P
     }
 }
 
+// V = I for every cone: an orthonormal basis to start from
+__global__ void k_psd_identity(double *V, int nc, int d_pad, int dS)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nc * d_pad) return;
+    const int cone = idx / d_pad, j = idx - cone * d_pad;
+    if (j < dS) V[((size_t)cone * d_pad + j) * dS + j] = 1.0;
+}
+
 template <int DK>
 static void launch_large(Handle *h, const PsdLargeArgs &a, int ncones)
 {
@@ -549,6 +627,14 @@ void psd_project_large(Handle *h, ConeSet &K, const double *in, double *projbuf)
     const int chunk = std::min(per_launch, nc);
     if (K.psd_work.n < (size_t)a.work_stride * chunk) K.psd_work.alloc((size_t)a.work_stride * chunk);
     if (K.psd_ctl.n < (size_t)chunk * sizeof(PsdLargeCtl)) K.psd_ctl.alloc((size_t)chunk * sizeof(PsdLargeCtl));
+    // eigenvector bases of the previous call, one per cone (warm start); cold when the geometry changed
+    const size_t vneed = (size_t)a.d_pad * dS * nc;
+    if (K.psd_vstore.n != vneed) {
+        K.psd_vstore.alloc(vneed);  // zeroed
+        k_psd_identity<<<(unsigned)(nc * a.d_pad + 255) / 256, 256, 0, h->stream>>>(K.psd_vstore.p, nc, a.d_pad, dS);
+        K.psd_warm = true;  // V = I is a valid basis: the first projection is the cold start
+    }
+    a.vstore_stride = (int64_t)a.d_pad * dS;
     a.in = in;
     a.proj = projbuf;
     a.work = K.psd_work.p;
@@ -556,6 +642,8 @@ void psd_project_large(Handle *h, ConeSet &K, const double *in, double *projbuf)
     for (int c0 = 0; c0 < nc; c0 += chunk) {
         const int n = std::min(chunk, nc - c0);
         a.cones = K.d_psd_large.p + c0;
+        a.vstore = K.psd_vstore.p + (size_t)c0 * a.vstore_stride;
+        a.warm = (K.psd_warm && K.psd_warm_enabled) ? 1 : 0;
         FOS_CUDA(cudaMemsetAsync(K.psd_ctl.p, 0, (size_t)n * sizeof(PsdLargeCtl), h->stream));
         switch (DK) {
         case 2: launch_large<2>(h, a, n); break;

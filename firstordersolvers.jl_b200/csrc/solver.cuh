@@ -176,6 +176,8 @@ struct ConeSet {
     DevBuf<PsdCone> d_psd, d_psd_large;
     DevBuf<double> psd_work;
     DevBuf<uint8_t> psd_ctl;
+    DevBuf<double> psd_vstore;   // eigenvector bases of the previous projection (warm start of K5L)
+    bool psd_warm = false, psd_warm_enabled = true;
     int psd_max_d = 0;
     void build(int64_t NP_, const std::vector<ConeSeg> &segs);
 };

@@ -102,6 +102,9 @@ const char *fos_last_error(fos_handle_t h);
  *   "fuse_tail"    1 (default) = conic form: everything of a CG iteration after the pass over A (peer
  *                  exchange, KKT epilogue, both dot products, x/r/p updates, stop test) runs in ONE
  *                  cooperative kernel; 0 = one kernel per step (K2, K3 update, K3 direction)
+ *   "psd_warm"     1 (default) = large PSD cones start their Jacobi sweeps from the eigenvector basis of the
+ *                  previous projection of the same cone (consecutive iterates are close: 2-4 sweeps instead
+ *                  of ~10); 0 = always start from the identity.  Set after loading.
  *   "exchange_impl" multi-GPU: 1 = fused peer-memory exchange (after fos_comm_p2p_import), 0 = NCCL
  *   "profile_matvec" 1 = CUDA events around every mat-vec launch (read back with fos_get_info)
  *   "batch_ctas"   persistent CTAs of the batch kernel (default = #SMs)

@@ -342,6 +342,29 @@ def test_linesearch_wrapper_feasibility_solve(fos, oracle):
     assert abs(model.last_iteration - ro["iterations"]) <= 100
 
 
+@pytest.mark.parametrize("warm", [1, 0])
+def test_large_sdp_cone_in_the_solver_loop(fos, oracle, warm):
+    """Config 4 at test scale with a cone above the single-CTA limit (d = 120 > 112): the cooperative
+    block-Jacobi projection inside GAP iterations, warm-started from the previous iteration's eigenvectors
+    ("psd_warm" = 1) or from the identity (0), in lock-step with the oracle (LAPACK-free Jacobi on the CPU)."""
+    from fos_b200 import problems
+    P = problems.sdp_nearest_correlation(120, seed=4)
+    O = oracle.OracleConic(P.c, P.A, P.b, P.constr_cones, P.var_cones)
+    H = load_conic(fos, P, storage="sparse")
+    H.set_option("psd_warm", warm)
+    set_alg_both(fos, H, O, "GAP")
+    O.set_iterate(O.initial_value())
+    H.ck(H.L.fos_begin_solve(H.h))
+    for i in range(1, 9):
+        sync_state_from_oracle(H, O, "GAP")
+        ro = O.run(i, 1, checki=4, eps=1e-12)
+        done, st, rec, _ = H.run(i, 1, 4, 1e-12)
+        assert H.info("cgiter") == O.cgiter
+        assert rel_err(H.get_iterate(), O.get_state("x")) < STEP_TOL, i
+        if i % 4 == 0:
+            _assert_record_matches(rec, ro["history"], i)
+
+
 def test_solve_tail_forced_check_and_getsol_side_effects(fos, oracle):
     """a-Q 1-3: forced final check iff the last iteration was not a check iteration; getsol runs one
     more CG solve that advances S1.i; a second solve! continues the tolerance schedule."""
