@@ -746,6 +746,42 @@ __global__ void k_batch_reset(BatchCtl *ctl, int B, int what)
 // =======================================================================================
 // host side
 // =======================================================================================
+// Kernel geometry of one problem shape: tile layout of A, ring depth, consumer warps, column pairs per
+// consumer thread, CTAs per SM.  Pure host arithmetic (unit-tested on CPU through fos_batch_plan).
+BatchGeom batch_geometry(int64_t m, int64_t n)
+{
+    FOS_REQUIRE(m >= 1 && n >= 1, "empty problem");
+    BatchGeom g;
+    const int64_t n_pad = ru(n, PAD), m_pad = ru(m, PAD);
+    g.lda = n_pad;
+    if (g.lda > BT_MAX_LDA)
+        throw Error(FOS_ERR_UNSUPPORTED, "batch mode supports n <= " + std::to_string(BT_MAX_LDA) +
+                                             " (one CTA per problem); use one handle per problem for larger ones");
+    g.ntiles = (int)((m + BT_TR - 1) / BT_TR);
+    g.a_stride = (int64_t)g.ntiles * BT_TR * g.lda;
+    const int npairs = (int)(g.lda / 2);
+    g.KP = 1;
+    while (g.KP < BT_MAX_KP && (npairs + g.KP * 32 * BT_MAX_CW - 1) / (g.KP * 32 * BT_MAX_CW) > 1) g.KP++;
+    if ((int64_t)g.KP * 32 * BT_MAX_CW < npairs) throw Error(FOS_ERR_UNSUPPORTED, "batch mode: n too large");
+    g.CW = std::max(4, (npairs + g.KP * 32 - 1) / (g.KP * 32));
+    const size_t tile_bytes = (size_t)BT_TR * g.lda * 8;
+    const size_t fixed = (size_t)(4 * m_pad + 4 * n_pad + 8 * 16) * 8 + BT_MAX_SOC * sizeof(SocScale) +
+                         2 * BT_MAX_STAGES * 8 + 64;
+    // two CTAs (= two problems) per SM when they fit: one CTA's vector phases overlap the other's pass
+    g.ctas_per_sm = 1;
+    g.S = BT_MAX_STAGES;
+    if (g.KP == 1 && (g.CW + 1) * 32 <= 320 && 2 * tile_bytes + fixed <= (size_t)112 * 1024) {
+        g.ctas_per_sm = 2;
+        while (g.S > 2 && (size_t)g.S * tile_bytes + fixed > (size_t)112 * 1024) g.S--;
+    } else {
+        while (g.S > 2 && (size_t)g.S * tile_bytes + fixed > (size_t)220 * 1024) g.S--;
+    }
+    g.smem_bytes = (size_t)g.S * tile_bytes + fixed;
+    if (g.smem_bytes > (size_t)227 * 1024)
+        throw Error(FOS_ERR_UNSUPPORTED, "batch mode: problem does not fit one SM's shared memory");
+    return g;
+}
+
 void BatchSolver::load(Handle *h_, int64_t B_, int64_t m, int64_t n, const double *A, int64_t lda_src,
                        int64_t pstride_src, int location, const double *b, const double *c, int64_t nc1,
                        const int32_t *t1, const int64_t *l1, int64_t nc2, const int32_t *t2, const int64_t *l2)
@@ -777,34 +813,15 @@ void BatchSolver::load(Handle *h_, int64_t B_, int64_t m, int64_t n, const doubl
         seg.src[k] = srcs[k];
         seg.dst[k] = dsts[k];
     }
-    lda = L.n_pad;
-    if (lda > BT_MAX_LDA)
-        throw Error(FOS_ERR_UNSUPPORTED, "batch mode supports n <= " + std::to_string(BT_MAX_LDA) +
-                                             " (one CTA per problem); use one handle per problem for larger ones");
-    ntiles = (int)((m + BT_TR - 1) / BT_TR);
-    a_stride = (int64_t)ntiles * BT_TR * lda;
-    // kernel geometry
-    const int npairs = (int)(lda / 2);
-    KP = 1;
-    while (KP < BT_MAX_KP && (npairs + KP * 32 * BT_MAX_CW - 1) / (KP * 32 * BT_MAX_CW) > 1) KP++;
-    if ((int64_t)KP * 32 * BT_MAX_CW < npairs) throw Error(FOS_ERR_UNSUPPORTED, "batch mode: n too large");
-    CW = std::max(4, (npairs + KP * 32 - 1) / (KP * 32));
-    const size_t tile_bytes = (size_t)BT_TR * lda * 8;
-    const size_t fixed = (size_t)(4 * L.m_pad + 4 * L.n_pad + 8 * 16) * 8 + BT_MAX_SOC * sizeof(SocScale) +
-                         2 * BT_MAX_STAGES * 8 + 64;
-    // two CTAs (= two problems) per SM when they fit: one CTA's vector phases overlap the other's pass
-    ctas_per_sm = 1;
-    if (KP == 1 && (CW + 1) * 32 <= 320 && 2 * tile_bytes + fixed <= (size_t)112 * 1024) {
-        ctas_per_sm = 2;
-        S = BT_MAX_STAGES;
-        while (S > 2 && (size_t)S * tile_bytes + fixed > (size_t)112 * 1024) S--;
-    } else {
-        S = BT_MAX_STAGES;
-        while (S > 2 && (size_t)S * tile_bytes + fixed > (size_t)220 * 1024) S--;
-    }
-    smem_bytes = (size_t)S * tile_bytes + fixed;
-    if (smem_bytes > (size_t)227 * 1024)
-        throw Error(FOS_ERR_UNSUPPORTED, "batch mode: problem does not fit one SM's shared memory");
+    const BatchGeom g = batch_geometry(m, n);
+    lda = g.lda;
+    ntiles = g.ntiles;
+    a_stride = g.a_stride;
+    KP = g.KP;
+    CW = g.CW;
+    S = g.S;
+    ctas_per_sm = g.ctas_per_sm;
+    smem_bytes = g.smem_bytes;
 
     // matrices
     dA.alloc((size_t)B * a_stride, false);

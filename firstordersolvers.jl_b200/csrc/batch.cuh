@@ -67,4 +67,11 @@ struct BatchArgs {
     int32_t do_run, do_finish;
 };
 
+struct BatchGeom {
+    int64_t lda, a_stride;
+    int32_t ntiles, S, CW, KP, ctas_per_sm;
+    size_t smem_bytes;
+};
+BatchGeom batch_geometry(int64_t m, int64_t n);  // host only; throws FOS_ERR_UNSUPPORTED for shapes outside batch mode
+
 }  // namespace fos

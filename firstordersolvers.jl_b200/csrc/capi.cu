@@ -867,6 +867,27 @@ int32_t fos_k1_plan(int64_t m_local, int64_t n, int32_t ctas, int32_t *dims_out,
     }
 }
 
+int32_t fos_batch_plan(int64_t m, int64_t n, int64_t *out)
+{
+    if (!out) return fail(nullptr, FOS_ERR_INVALID, "null output");
+    try {
+        const BatchGeom g = batch_geometry(m, n);
+        out[0] = g.lda;
+        out[1] = g.ntiles;
+        out[2] = g.S;
+        out[3] = g.CW;
+        out[4] = g.KP;
+        out[5] = g.ctas_per_sm;
+        out[6] = (int64_t)g.smem_bytes;
+        out[7] = g.a_stride;
+        return FOS_OK;
+    } catch (const Error &e) {
+        return fail(nullptr, e.code, e.what());
+    } catch (const std::exception &e) {
+        return fail(nullptr, FOS_ERR_INVALID, e.what());
+    }
+}
+
 int32_t fos_time_matvec(fos_handle_t hh, int32_t nvec, int32_t reps, double *ms_per_launch, double *bytes_per_launch)
 {
     FOS_API_BEGIN(hh)

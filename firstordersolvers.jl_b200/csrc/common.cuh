@@ -72,6 +72,8 @@ struct Ctrl {
     double ls_alphabest;
     // scratch for scalar hand-off between kernels
     double scal[8];
+    uint32_t p2p_error;  // host copy only: peer-exchange timeout flag fetched by sync_ctrl
+    uint32_t pad_;
 };
 
 // deterministic two-level reduction workspace

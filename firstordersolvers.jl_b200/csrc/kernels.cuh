@@ -911,6 +911,7 @@ struct P2PView {
     int64_t bflags_off;      // per-block flags [nranks][P2P_MAX_BLOCKS] of the fused CG tail
     unsigned int *epoch;     // local: exchanges completed so far
     unsigned int *tickets;   // local: [0] phase-1 ticket, [1] exit ticket
+    unsigned int *error;     // local: set when a peer did not show up within P2P_TIMEOUT_CYCLES
 };
 
 __device__ __forceinline__ double ld_sys_f64(const double *p)
@@ -928,6 +929,20 @@ __device__ __forceinline__ unsigned int ld_acquire_sys_u32(const unsigned int *p
 __device__ __forceinline__ void st_release_sys_u32(unsigned int *p, unsigned int v)
 {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// A peer that died (or never launched the matching kernel) must not hang this GPU: the waits give up after
+// ~30 s of SM clock, raise the error flag (the host turns it into FOS_ERR_COMM at the next synchronisation) and
+// let the kernel finish with whatever it has.
+constexpr long long P2P_TIMEOUT_CYCLES = 60000000000LL;
+__device__ __forceinline__ void p2p_wait_flag(const unsigned int *f, unsigned int epoch, unsigned int *error)
+{
+    const long long t0 = clock64();
+    while ((int)(ld_acquire_sys_u32(f) - epoch) < 0) {
+        if (clock64() - t0 > P2P_TIMEOUT_CYCLES) {
+            atomicExch(error, 1u);
+            break;
+        }
+    }
 }
 
 // Sum over ranks (rank order) of NV entries `off + v*vstride` of every rank's slot.  All remote loads of a
@@ -1001,8 +1016,7 @@ k1_exchange_p2p(MVView V, P2PView X, int64_t n, int64_t n_pad, int64_t m_pad, do
     if (threadIdx.x < X.nranks) {
         const unsigned int *f = reinterpret_cast<const unsigned int *>(X.peer[X.rank] + X.flags_off) +
                                 (size_t)threadIdx.x * P2P_FLAG_STRIDE;
-        while ((int)(ld_acquire_sys_u32(f) - epoch) < 0) {
-        }
+        p2p_wait_flag(f, epoch, X.error);
     }
     __syncthreads();
     for (int64_t e = (int64_t)blockIdx.x * VBLOCK + threadIdx.x; e < total; e += (int64_t)gridDim.x * VBLOCK) {
@@ -1186,8 +1200,7 @@ k_cg_tail_hsde(Lay L, MVView V, P2PView X, const double *__restrict__ c, const d
                                epoch);
             const unsigned int *f = reinterpret_cast<const unsigned int *>(X.peer[X.rank] + X.bflags_off) +
                                     (size_t)threadIdx.x * P2P_MAX_BLOCKS + blockIdx.x;
-            while ((int)(ld_acquire_sys_u32(f) - epoch) < 0) {
-            }
+            p2p_wait_flag(f, epoch, X.error);
         }
         __syncthreads();
     }

@@ -193,6 +193,7 @@ void MatOp::p2p_import(const uint8_t *handles)
     p2p.slot_doubles = 2 * (n_pad + m_pad);
     p2p.epoch = p2p_local.p;
     p2p.tickets = p2p_local.p + 1;
+    p2p.error = p2p_local.p + 3;
     for (int r = 0; r < nranks; r++) {
         void *base = nullptr;
         if (r == rank) {

@@ -99,7 +99,11 @@ void Handle::unpack_to_host(const double *src, double *z)
 void Handle::sync_ctrl()
 {
     FOS_CUDA(cudaMemcpyAsync(h_ctrl, d_ctrl.p, sizeof(Ctrl), cudaMemcpyDeviceToHost, stream));
+    if (A.p2p_on) FOS_CUDA(cudaMemcpyAsync(&h_ctrl->p2p_error, A.p2p.error, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
     FOS_CUDA(cudaStreamSynchronize(stream));
+    if (A.p2p_on && h_ctrl->p2p_error != 0)
+        throw Error(FOS_ERR_COMM, "peer-memory exchange timed out: a rank did not reach the matching pass over A "
+                                  "(every rank must make the same calls in the same order)");
     A.prof_collect();
 }
 

@@ -297,6 +297,11 @@ int32_t fos_prox_cone(fos_handle_t h, int32_t cone_type, int32_t dual, const dou
 int32_t fos_k1_plan(int64_t m_local, int64_t n, int32_t ctas, int32_t *dims_out, int32_t *unit_begin,
                     int64_t unit_begin_cap, int32_t *slot_base, int32_t *first_cta, int64_t band_cap);
 
+/* Host-only: the kernel geometry batch mode picks for problems of shape m x n (needs no GPU; unit-tested on
+ * CPU).  out = {lda, tiles of 8 rows, ring stages, consumer warps, column pairs per consumer thread, CTAs per
+ * SM, dynamic shared memory bytes, doubles of A per problem}.  FOS_ERR_UNSUPPORTED for shapes outside batch mode. */
+int32_t fos_batch_plan(int64_t m, int64_t n, int64_t *out /* 8 */);
+
 /* ====================================================================================== */
 /* measurement helpers (bench.py)                                                         */
 /* ====================================================================================== */

@@ -146,3 +146,29 @@ def test_row_and_batch_shards(fos):
             assert all(b % 16 == 0 for b, c in spans if c > 0)
     assert [batch_shard(8192, r, 8) for r in range(8)] == [(1024 * r, 1024) for r in range(8)]
     assert sum(c for _, c in (batch_shard(10, r, 4) for r in range(4))) == 10
+
+
+def test_batch_mode_geometry(fos):
+    """fos_batch_plan (host only): the persistent-CTA geometry for a problem shape -- every column pair has an
+    owner, the ring fits shared memory, two CTAs per SM only when both fit, large shapes are refused."""
+    L = fos.load_library()
+    out = (C.c_int64 * 8)()
+    for (m, n) in [(769, 513), (91, 51), (17, 70), (5, 3), (2000, 1024), (300, 1280), (2400, 700)]:
+        assert L.fos_batch_plan(m, n, out) == 0, (m, n)
+        lda, ntiles, S, CW, KP, cps, smem, a_stride = list(out)
+        assert lda % 16 == 0 and lda >= n and lda - n < 16
+        assert ntiles * 8 >= m > (ntiles - 1) * 8
+        assert a_stride == ntiles * 8 * lda
+        assert 2 <= S <= 4 and 4 <= CW <= 15 and 1 <= KP <= 4
+        assert KP * 32 * CW >= lda // 2                      # every column pair is owned by a consumer thread
+        assert (KP - 1) * 32 * 15 < lda // 2                 # ... with the smallest KP that can cover the row
+        assert smem <= 227 * 1024
+        assert cps in (1, 2)
+        if cps == 2:
+            assert 2 * (smem + 1024) <= 227 * 1024 and (CW + 1) * 32 <= 320 and KP == 1
+    assert list(out[:6]) != []                               # last call succeeded
+    L.fos_batch_plan(769, 513, out)
+    assert list(out)[:6] == [528, 97, 2, 9, 1, 2]            # config 5: nine consumer warps, two problems per SM
+    assert L.fos_batch_plan(100, 1281, out) == -3            # FOS_ERR_UNSUPPORTED: n > 1280
+    assert L.fos_batch_plan(4000, 700, out) == -3            # the A X / W staging of m = 4000 rows does not fit an SM
+    assert L.fos_batch_plan(0, 5, out) != 0
