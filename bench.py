@@ -257,7 +257,9 @@ def main():
     H.ck(H.L.fos_load_conic_dense(H.h, m, n, C.c_void_p(A_loc.data_ptr()), n, 1, r0, cnt, _d(b), _d(c), len(t1),
                                   _i32p(t1), _i64p(l1), len(t2), _i32p(t2), _i64p(l2)))
     if world > 1 and args.exchange == "p2p":
-        parallel.enable_p2p_exchange(H, rank, world, dist)
+        if not parallel.enable_p2p_exchange(H, rank, world, dist):
+            args.exchange = "nccl"   # CUDA IPC unavailable on this box: every rank fell back together
+            config["parallelism"] = f"A row-sharded over {world} GPUs, NCCL all-reduce (peer-memory mapping unavailable)"
     H.set_algorithm(fos.DR(0.5))
     H.set_initial_iterate()
     H.ck(H.L.fos_begin_solve(H.h))

@@ -68,22 +68,44 @@ def init_comm(handle, rank: int, nranks: int, comm_id: bytes):
     handle.ck(handle.L.fos_comm_init(handle.h, rank, nranks, arr))
 
 
-def enable_p2p_exchange(handle, rank: int, nranks: int, dist=None):
+def enable_p2p_exchange(handle, rank: int, nranks: int, dist=None) -> bool:
     """After ``fos_load_conic_dense`` on every rank: export this rank's CUDA-IPC exchange slot,
     all-gather the 64-byte handles through ``torch.distributed`` (plumbing only) and import the
     table -- from then on every pass over A uses the fused peer-memory exchange kernel instead of
-    fold + ncclAllReduce."""
+    fold + ncclAllReduce.
+
+    Returns True when EVERY rank mapped every peer.  If any rank could not (CUDA IPC disabled in the
+    container, no peer access), all ranks switch back to the NCCL exchange together and False is returned:
+    the ranks must agree, a mixed configuration would dead-lock."""
     import torch
     if dist is None:
         import torch.distributed as dist
-    arr = (C.c_uint8 * _lib.FOS_IPC_HANDLE_BYTES)()
-    handle.ck(handle.L.fos_comm_p2p_export(handle.h, arr))
-    mine = torch.from_numpy(np.frombuffer(bytes(arr), dtype=np.uint8).copy())
-    if dist.get_backend() == "nccl":
+    on_gpu = dist.get_backend() == "nccl"
+    ok = 1
+    mine = torch.zeros(_lib.FOS_IPC_HANDLE_BYTES, dtype=torch.uint8)
+    try:
+        arr = (C.c_uint8 * _lib.FOS_IPC_HANDLE_BYTES)()
+        handle.ck(handle.L.fos_comm_p2p_export(handle.h, arr))
+        mine = torch.from_numpy(np.frombuffer(bytes(arr), dtype=np.uint8).copy())
+    except _lib.FosError:
+        ok = 0
+    if on_gpu:
         mine = mine.cuda()
     table = [torch.empty_like(mine) for _ in range(nranks)]
     dist.all_gather(table, mine)
-    flat = np.concatenate([t.cpu().numpy() for t in table]).astype(np.uint8)
-    buf = (C.c_uint8 * (nranks * _lib.FOS_IPC_HANDLE_BYTES)).from_buffer_copy(flat.tobytes())
-    handle.ck(handle.L.fos_comm_p2p_import(handle.h, buf))
+    flag = torch.tensor([ok], dtype=torch.int32, device=mine.device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if int(flag.item()) == 1:
+        try:
+            flat = np.concatenate([t.cpu().numpy() for t in table]).astype(np.uint8)
+            buf = (C.c_uint8 * (nranks * _lib.FOS_IPC_HANDLE_BYTES)).from_buffer_copy(flat.tobytes())
+            handle.ck(handle.L.fos_comm_p2p_import(handle.h, buf))
+        except _lib.FosError:
+            ok = 0
+    flag = torch.tensor([ok], dtype=torch.int32, device=mine.device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    all_ok = int(flag.item()) == 1
+    if not all_ok and ok == 1:
+        handle.set_option("exchange_impl", 0)  # this rank mapped its peers but another one did not
     dist.barrier()
+    return all_ok

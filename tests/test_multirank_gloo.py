@@ -49,7 +49,42 @@ def _worker(rank, world, port, q):
         err = float(np.abs(t.numpy() - full).max())
         # 3. batch split: disjoint cover
         bb, bc = parallel.batch_shard(11, rank, world)
-        q.put((rank, ok_id, err, (b0, cnt), (bb, bc)))
+        # 4. peer-memory exchange set-up: the ranks must agree.  Stub handles stand in for the library (no GPU
+        #    here): when one rank cannot map its peers, every rank falls back to the NCCL exchange together.
+        from fos_b200 import _lib as flib
+
+        class StubLib:
+            def __init__(self, fail_import):
+                self.fail_import = fail_import
+                self.imported = None
+
+            def fos_comm_p2p_export(self, h, arr):
+                for k in range(64):
+                    arr[k] = (rank * 64 + k) % 251
+                return 0
+
+            def fos_comm_p2p_import(self, h, buf):
+                self.imported = bytes(buf)
+                return -5 if self.fail_import else 0
+
+        class StubHandle:
+            def __init__(self, fail_import):
+                self.L, self.h, self.options = StubLib(fail_import), None, {}
+
+            def ck(self, rc):
+                if rc != 0:
+                    raise flib.FosError(rc, "stub failure")
+
+            def set_option(self, k, v):
+                self.options[k] = v
+
+        h_ok = StubHandle(False)
+        all_ok = parallel.enable_p2p_exchange(h_ok, rank, world, dist)
+        table_ok = h_ok.L.imported == bytes([(r * 64 + k) % 251 for r in range(world) for k in range(64)])
+        h_bad = StubHandle(fail_import=(rank == 1))
+        mixed = parallel.enable_p2p_exchange(h_bad, rank, world, dist)
+        fell_back = (h_bad.options.get("exchange_impl") == 0) if rank == 0 else (h_bad.options == {})
+        q.put((rank, ok_id, err, (b0, cnt), (bb, bc), all_ok and table_ok, (not mixed) and fell_back))
     finally:
         dist.destroy_process_group()
 
@@ -71,3 +106,5 @@ def test_two_rank_rendezvous_and_sharded_matvec():
     assert all(r[2] < 1e-12 for r in res)
     assert res[0][3] == (0, 64) and res[1][3] == (64, 36)
     assert res[0][4] == (0, 6) and res[1][4] == (6, 5)
+    assert all(r[5] for r in res), "peer-memory handle table was not gathered in rank order"
+    assert all(r[6] for r in res), "ranks did not fall back to NCCL together"
