@@ -36,6 +36,9 @@ struct BK {
     uint32_t phase;
     // current problem
     const double *b, *c;
+    const int32_t *drow, *srow_ptr, *srow_id, *scol, *ccol_ptr, *ccol_id, *crow;
+    const double *sval, *cval;
+    int ns, ncs;
     double *v[BV_COUNT];
     double nb, ncn;
     double *recs;
@@ -83,6 +86,7 @@ __device__ __forceinline__ void bt_pass(BK &k, const double *X0, const double *X
     const int S = a.S;
     const int64_t tile_elems = (int64_t)BT_TR * lda;
     const int64_t n_pad = a.L.n_pad, m_pad = a.L.m_pad;
+    const int mr = a.mr;
     const int CW = k.NT >> 5;
     for (int64_t e = k.ct; e < n_pad; e += k.NT) {
         k.s_x[e] = X0[e];
@@ -90,7 +94,7 @@ __device__ __forceinline__ void bt_pass(BK &k, const double *X0, const double *X
     }
     for (int64_t e = k.ct; e < m_pad; e += k.NT) {  // W rides in shared memory too: 16 broadcast reads per tile
         k.s_wv[e] = W0[e];
-        k.s_wv[m_pad + e] = W1[e];
+        k.s_wv[mr + e] = W1[e];
     }
     double2 ca[KP][2];
 #pragma unroll
@@ -102,7 +106,8 @@ __device__ __forceinline__ void bt_pass(BK &k, const double *X0, const double *X
         const int row0 = tile * BT_TR;
 #pragma unroll
         for (int r = 0; r < BT_TR; r++) {
-            const double w0 = k.s_wv[row0 + r], w1 = k.s_wv[m_pad + row0 + r];
+            const int rr = __ldg(k.drow + row0 + r);  // original row of this tile row
+            const double w0 = k.s_wv[rr], w1 = k.s_wv[mr + rr];
 #pragma unroll
             for (int kk = 0; kk < KP; kk++) {
                 const int cp = k.ct + kk * k.NT;
@@ -130,8 +135,9 @@ __device__ __forceinline__ void bt_pass(BK &k, const double *X0, const double *X
             }
             const double r0 = warp_sum(a0x + a0y), r1 = warp_sum(a1x + a1y);
             if (k.lane == 0) {
-                k.s_ax[row0 + r] = r0;
-                k.s_ax[m_pad + row0 + r] = r1;
+                const int rr = __ldg(k.drow + row0 + r);
+                k.s_ax[rr] = r0;
+                k.s_ax[mr + rr] = r1;
             }
         }
         __syncwarp();
@@ -149,6 +155,33 @@ __device__ __forceinline__ void bt_pass(BK &k, const double *X0, const double *X
             *reinterpret_cast<double2 *>(k.s_atw + 2 * cp) = ca[kk][0];
             *reinterpret_cast<double2 *>(k.s_atw + n_pad + 2 * cp) = ca[kk][1];
         }
+    }
+    // sparse rows (CSR): A x
+    for (int sr = k.ct; sr < k.ns; sr += k.NT) {
+        double a0 = 0.0, a1 = 0.0;
+        for (int p = __ldg(k.srow_ptr + sr); p < __ldg(k.srow_ptr + sr + 1); p++) {
+            const int j = __ldg(k.scol + p);
+            const double v = __ldg(k.sval + p);
+            a0 = fma(v, k.s_x[j], a0);
+            a1 = fma(v, k.s_x[n_pad + j], a1);
+        }
+        const int row = __ldg(k.srow_id + sr);
+        k.s_ax[row] = a0;
+        k.s_ax[mr + row] = a1;
+    }
+    cbar(k.NT);
+    // columns with sparse entries (CSC): add A' w of the sparse rows to the dense column sums
+    for (int sc = k.ct; sc < k.ncs; sc += k.NT) {
+        double a0 = 0.0, a1 = 0.0;
+        for (int p = __ldg(k.ccol_ptr + sc); p < __ldg(k.ccol_ptr + sc + 1); p++) {
+            const int i = __ldg(k.crow + p);
+            const double v = __ldg(k.cval + p);
+            a0 = fma(v, k.s_wv[i], a0);
+            a1 = fma(v, k.s_wv[mr + i], a1);
+        }
+        const int col = __ldg(k.ccol_id + sc);
+        k.s_atw[col] += a0;
+        k.s_atw[n_pad + col] += a1;
     }
     k.total_passes++;
     cbar(k.NT);
@@ -172,7 +205,7 @@ __device__ __forceinline__ double bt_kkt_epilogue(BK &k, const double *in, doubl
     const Lay &L = k.a->L;
     const int64_t LP = L.LP, oy = L.n_pad, ot = L.n_pad + L.m_pad;
     const double tau1 = in[ot], tau2 = in[LP + ot];
-    const double *ax0 = k.s_ax, *ax1 = k.s_ax + L.m_pad, *atw0 = k.s_atw, *atw1 = k.s_atw + L.n_pad;
+    const double *ax0 = k.s_ax, *ax1 = k.s_ax + k.a->mr, *atw0 = k.s_atw, *atw1 = k.s_atw + L.n_pad;
     double q[5] = {0, 0, 0, 0, 0};
     for (int64_t e = k.ct; e < ot; e += k.NT) {
         double o1 = 0.0, o2 = 0.0;
@@ -510,10 +543,10 @@ __global__ void __launch_bounds__(MAXT, MINB) k_batch_solve(const BatchArgs a)
     const int64_t tile_elems = (int64_t)BT_TR * a.lda;
     double *tiles = reinterpret_cast<double *>(bt_smem);
     double *s_ax = tiles + (size_t)a.S * tile_elems;
-    double *s_atw = s_ax + 2 * a.L.m_pad;
+    double *s_atw = s_ax + 2 * a.mr;
     double *s_x = s_atw + 2 * a.L.n_pad;
     double *s_wv = s_x + 2 * a.L.n_pad;
-    double *s_red = s_wv + 2 * a.L.m_pad;
+    double *s_red = s_wv + 2 * a.mr;
     SocScale *s_soc = reinterpret_cast<SocScale *>(s_red + 8 * 16);
     uint64_t *full = reinterpret_cast<uint64_t *>(s_soc + BT_MAX_SOC);
     uint64_t *empty = full + BT_MAX_STAGES;
@@ -532,7 +565,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_batch_solve(const BatchArgs a)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    for (int64_t e = threadIdx.x; e < 2 * (a.L.m_pad + a.L.n_pad); e += blockDim.x) s_ax[e] = 0.0;
+    for (int64_t e = threadIdx.x; e < 4 * ((int64_t)a.mr + a.L.n_pad); e += blockDim.x) s_ax[e] = 0.0;  // ax, atw, x, wv
     __syncthreads();
 
     if (warp == CW) {
@@ -617,6 +650,17 @@ __global__ void __launch_bounds__(MAXT, MINB) k_batch_solve(const BatchArgs a)
         const Lay &L = a.L;
         k.b = a.b + (size_t)pb * L.m_pad;
         k.c = a.c + (size_t)pb * L.n_pad;
+        k.drow = a.drow + (size_t)pb * a.ntiles * BT_TR;
+        k.ns = a.sp_count[2 * pb];
+        k.ncs = a.sp_count[2 * pb + 1];
+        k.srow_ptr = a.srow_ptr + (size_t)pb * (a.NS + 1);
+        k.srow_id = a.srow_id + (size_t)pb * a.NS;
+        k.scol = a.scol + (size_t)pb * a.NZ;
+        k.sval = a.sval + (size_t)pb * a.NZ;
+        k.ccol_ptr = a.ccol_ptr + (size_t)pb * (a.NCS + 1);
+        k.ccol_id = a.ccol_id + (size_t)pb * a.NCS;
+        k.crow = a.crow + (size_t)pb * a.NZ;
+        k.cval = a.cval + (size_t)pb * a.NZ;
         k.nb = a.nb[pb];
         k.ncn = a.ncn[pb];
         for (int j = 0; j < BV_COUNT; j++) k.v[j] = a.vec + ((size_t)pb * BV_COUNT + j) * L.NP;
@@ -700,18 +744,54 @@ k_unpack_batch(SegMap M, const double *padded, int64_t pstride, double *logical,
         }
     }
 }
-// A (B x m x n, row-major, leading dimension lda_src, problem stride pstride_src) -> padded tiles
+// non-zeros per row of every problem: one warp per row
 __global__ void __launch_bounds__(256)
-k_pad_matrix_batch(const double *src, int64_t lda_src, int64_t pstride_src, int64_t m, int64_t n,
-                   double *dst, int64_t lda, int64_t rows_pad, int64_t a_stride)
+k_row_nnz(const double *__restrict__ src, int64_t lda_src, int64_t pstride_src, int64_t m, int64_t n, int32_t *__restrict__ nnz)
 {
     const int64_t pb = blockIdx.y;
-    const double *s = src + (size_t)pb * pstride_src;
-    double *d = dst + (size_t)pb * a_stride;
-    const int64_t total = rows_pad * lda;
-    for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (int64_t)gridDim.x * 256) {
-        const int64_t i = e / lda, j = e - i * lda;
-        d[e] = (i < m && j < n) ? s[i * lda_src + j] : 0.0;
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= m) return;
+    const int lane = threadIdx.x & 31;
+    const double *r = src + (size_t)pb * pstride_src + (size_t)row * lda_src;
+    int c = 0;
+    for (int64_t j = lane; j < n; j += 32) c += r[j] != 0.0 ? 1 : 0;
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) nnz[(size_t)pb * m + row] = c;
+}
+// tile row t of problem pb <- row drow[pb][t] of its matrix (zero row for padding slots)
+__global__ void __launch_bounds__(128)
+k_gather_dense_rows(const double *__restrict__ src, int64_t lda_src, int64_t pstride_src, int64_t m, int64_t n,
+                    const int32_t *__restrict__ drow, int rows_pad, double *__restrict__ dst, int64_t lda, int64_t a_stride)
+{
+    const int64_t pb = blockIdx.y, t = blockIdx.x;
+    const int32_t row = drow[(size_t)pb * rows_pad + t];
+    double *d = dst + (size_t)pb * a_stride + (size_t)t * lda;
+    const double *s = src + (size_t)pb * pstride_src + (size_t)row * lda_src;
+    for (int64_t j = threadIdx.x; j < lda; j += 128) d[j] = (row < m && j < n) ? s[j] : 0.0;
+}
+// CSR of the sparse rows: one warp per row, non-zeros compacted in column order (ballot prefix)
+__global__ void __launch_bounds__(32)
+k_extract_sparse_rows(const double *__restrict__ src, int64_t lda_src, int64_t pstride_src, int64_t n,
+                      const int32_t *__restrict__ srow_id, const int32_t *__restrict__ srow_ptr, int NS,
+                      int32_t *__restrict__ scol, double *__restrict__ sval, int NZ)
+{
+    const int64_t pb = blockIdx.y;
+    const int sr = blockIdx.x;
+    const int32_t p0 = srow_ptr[(size_t)pb * (NS + 1) + sr], p1 = srow_ptr[(size_t)pb * (NS + 1) + sr + 1];
+    if (p1 == p0) return;  // padding slot
+    const int lane = threadIdx.x;
+    const double *r = src + (size_t)pb * pstride_src + (size_t)srow_id[(size_t)pb * NS + sr] * lda_src;
+    int32_t pos = p0;
+    for (int64_t j0 = 0; j0 < n; j0 += 32) {
+        const int64_t j = j0 + lane;
+        const double v = j < n ? r[j] : 0.0;
+        const unsigned int msk = __ballot_sync(0xffffffffu, v != 0.0);
+        if (v != 0.0) {
+            const int32_t q = pos + __popc(msk & ((1u << lane) - 1u));
+            scol[(size_t)pb * NZ + q] = (int32_t)j;
+            sval[(size_t)pb * NZ + q] = v;
+        }
+        pos += __popc(msk);
     }
 }
 __global__ void k_batch_reset(BatchCtl *ctl, int B, int what)
@@ -765,7 +845,7 @@ BatchGeom batch_geometry(int64_t m, int64_t n)
     if ((int64_t)g.KP * 32 * BT_MAX_CW < npairs) throw Error(FOS_ERR_UNSUPPORTED, "batch mode: n too large");
     g.CW = std::max(4, (npairs + g.KP * 32 - 1) / (g.KP * 32));
     const size_t tile_bytes = (size_t)BT_TR * g.lda * 8;
-    const size_t fixed = (size_t)(4 * m_pad + 4 * n_pad + 8 * 16) * 8 + BT_MAX_SOC * sizeof(SocScale) +
+    const size_t fixed = (size_t)(4 * (m_pad + 16) + 4 * n_pad + 8 * 16) * 8 + BT_MAX_SOC * sizeof(SocScale) +
                          2 * BT_MAX_STAGES * 8 + 64;
     // two CTAs (= two problems) per SM when they fit: one CTA's vector phases overlap the other's pass
     g.ctas_per_sm = 1;
@@ -823,36 +903,132 @@ void BatchSolver::load(Handle *h_, int64_t B_, int64_t m, int64_t n, const doubl
     ctas_per_sm = g.ctas_per_sm;
     smem_bytes = g.smem_bytes;
 
-    // matrices
-    dA.alloc((size_t)B * a_stride, false);
+    // matrices: classify the rows of every problem (dense / sparse / empty), gather the dense rows into tiles,
+    // extract the sparse rows as CSR on the device and build their CSC on the host (small)
     {
-        DevBuf<double> stage;
+        DevBuf<double> whole;
         const double *src = A;
         if (location == FOS_MEM_HOST) {
-            // host input: stage problem by problem groups to bound the temporary
-            const int64_t per = std::max<int64_t>(1, std::min<int64_t>(B, ((int64_t)256 << 20) / std::max<int64_t>(1, pstride_src * 8)));
-            stage.alloc((size_t)per * pstride_src, false);
-            for (int64_t p0 = 0; p0 < B; p0 += per) {
-                const int64_t cnt = std::min(per, B - p0);
-                FOS_CUDA(cudaMemcpyAsync(stage.p, A + (size_t)p0 * pstride_src, (size_t)cnt * pstride_src * 8,
-                                         cudaMemcpyHostToDevice, h->stream));
-                dim3 g((unsigned)std::min<int64_t>((a_stride + 255) / 256, 1024), (unsigned)cnt);
-                k_pad_matrix_batch<<<g, 256, 0, h->stream>>>(stage.p, lda_src, pstride_src, m, n,
-                                                             dA.p + (size_t)p0 * a_stride, lda, (int64_t)ntiles * BT_TR,
-                                                             a_stride);
-                FOS_CUDA(cudaStreamSynchronize(h->stream));
-            }
-        } else {
-            for (int64_t p0 = 0; p0 < B; p0 += 32768) {
-                const int64_t cnt = std::min<int64_t>(32768, B - p0);
-                dim3 g((unsigned)std::min<int64_t>((a_stride + 255) / 256, 1024), (unsigned)cnt);
-                k_pad_matrix_batch<<<g, 256, 0, h->stream>>>(src + (size_t)p0 * pstride_src, lda_src, pstride_src, m, n,
-                                                             dA.p + (size_t)p0 * a_stride, lda, (int64_t)ntiles * BT_TR,
-                                                             a_stride);
-            }
-            FOS_CUDA(cudaStreamSynchronize(h->stream));
+            const size_t elems = (size_t)(B - 1) * pstride_src + (size_t)(m - 1) * lda_src + n;
+            if (elems * 8 > ((size_t)96 << 30))
+                throw Error(FOS_ERR_NOMEM, "host batch larger than 96 GB: hand the matrices over in device memory");
+            whole.alloc(elems, false);
+            FOS_CUDA(cudaMemcpy(whole.p, A, elems * 8, cudaMemcpyHostToDevice));
+            FOS_SYNC_LEGACY();
+            src = whole.p;
         }
-        h->stats.launches += 1;
+        DevBuf<int32_t> d_nnz;
+        d_nnz.alloc((size_t)B * m);
+        k_row_nnz<<<dim3((unsigned)((m + 7) / 8), (unsigned)B), 256, 0, h->stream>>>(src, lda_src, pstride_src, m, n, d_nnz.p);
+        std::vector<int32_t> nnz((size_t)B * m);
+        FOS_CUDA(cudaMemcpy(nnz.data(), d_nnz.p, nnz.size() * 4, cudaMemcpyDeviceToHost));
+        const int64_t thr = hybrid ? std::max<int64_t>(1, n / 8) : 0;  // rows with <= thr non-zeros go to CSR
+        std::vector<std::vector<int32_t>> drows((size_t)B), srows((size_t)B);
+        int64_t ND = 0, NSmax = 0, NZmax = 0;
+        dense_rows_total = 0;
+        sparse_nnz_total = 0;
+        for (int64_t p = 0; p < B; p++) {
+            int64_t nz = 0;
+            for (int64_t i = 0; i < m; i++) {
+                const int32_t c = nnz[(size_t)p * m + i];
+                if (c == 0 && hybrid) continue;  // an empty row contributes nothing to A x or A' w
+                if (hybrid && c <= thr) {
+                    srows[(size_t)p].push_back((int32_t)i);
+                    nz += c;
+                } else {
+                    drows[(size_t)p].push_back((int32_t)i);
+                }
+            }
+            ND = std::max<int64_t>(ND, (int64_t)drows[(size_t)p].size());
+            NSmax = std::max<int64_t>(NSmax, (int64_t)srows[(size_t)p].size());
+            NZmax = std::max<int64_t>(NZmax, nz);
+            dense_rows_total += (int64_t)drows[(size_t)p].size();
+            sparse_nnz_total += nz;
+        }
+        ntiles = (int)std::max<int64_t>(1, (ND + BT_TR - 1) / BT_TR);
+        a_stride = (int64_t)ntiles * BT_TR * lda;
+        NS = (int32_t)std::max<int64_t>(NSmax, 1);
+        NZ = (int32_t)std::max<int64_t>(NZmax, 1);
+        const int32_t dummy = (int32_t)L.m_pad;  // a row slot whose W entry is always zero
+        std::vector<int32_t> h_drow((size_t)B * ntiles * BT_TR, dummy), h_sid((size_t)B * NS, 0),
+            h_sptr((size_t)B * (NS + 1), 0), h_cnt((size_t)B * 2, 0);
+        for (int64_t p = 0; p < B; p++) {
+            for (size_t k = 0; k < drows[(size_t)p].size(); k++) h_drow[(size_t)p * ntiles * BT_TR + k] = drows[(size_t)p][k];
+            int32_t acc = 0;
+            for (size_t k = 0; k < srows[(size_t)p].size(); k++) {
+                h_sid[(size_t)p * NS + k] = srows[(size_t)p][k];
+                h_sptr[(size_t)p * (NS + 1) + k] = acc;
+                acc += nnz[(size_t)p * m + srows[(size_t)p][k]];
+            }
+            for (size_t k = srows[(size_t)p].size(); k <= (size_t)NS; k++) h_sptr[(size_t)p * (NS + 1) + k] = acc;
+            h_cnt[(size_t)p * 2] = (int32_t)srows[(size_t)p].size();
+        }
+        d_drow.upload(h_drow);
+        d_sid.upload(h_sid);
+        d_sptr.upload(h_sptr);
+        dA.alloc((size_t)B * a_stride, false);
+        d_scol.alloc((size_t)B * NZ);
+        d_sval.alloc((size_t)B * NZ);
+        for (int64_t p0 = 0; p0 < B; p0 += 32768) {
+            const int64_t cnt = std::min<int64_t>(32768, B - p0);
+            k_gather_dense_rows<<<dim3((unsigned)(ntiles * BT_TR), (unsigned)cnt), 128, 0, h->stream>>>(
+                src + (size_t)p0 * pstride_src, lda_src, pstride_src, m, n, d_drow.p + (size_t)p0 * ntiles * BT_TR,
+                ntiles * BT_TR, dA.p + (size_t)p0 * a_stride, lda, a_stride);
+            k_extract_sparse_rows<<<dim3((unsigned)NS, (unsigned)cnt), 32, 0, h->stream>>>(
+                src + (size_t)p0 * pstride_src, lda_src, pstride_src, n, d_sid.p + (size_t)p0 * NS,
+                d_sptr.p + (size_t)p0 * (NS + 1), NS, d_scol.p + (size_t)p0 * NZ, d_sval.p + (size_t)p0 * NZ, NZ);
+        }
+        FOS_CUDA(cudaStreamSynchronize(h->stream));
+        // CSC of the sparse rows, on the host (sparse_nnz_total entries)
+        std::vector<int32_t> h_scol((size_t)B * NZ);
+        std::vector<double> h_sval((size_t)B * NZ);
+        FOS_CUDA(cudaMemcpy(h_scol.data(), d_scol.p, h_scol.size() * 4, cudaMemcpyDeviceToHost));
+        FOS_CUDA(cudaMemcpy(h_sval.data(), d_sval.p, h_sval.size() * 8, cudaMemcpyDeviceToHost));
+        std::vector<std::vector<int32_t>> ccols((size_t)B);
+        int64_t NCSmax = 0;
+        std::vector<int32_t> colcnt((size_t)n);
+        for (int64_t p = 0; p < B; p++) {
+            std::fill(colcnt.begin(), colcnt.end(), 0);
+            const int32_t nzp = h_sptr[(size_t)p * (NS + 1) + NS];
+            for (int32_t q = 0; q < nzp; q++) colcnt[(size_t)h_scol[(size_t)p * NZ + q]]++;
+            for (int64_t j = 0; j < n; j++)
+                if (colcnt[(size_t)j]) ccols[(size_t)p].push_back((int32_t)j);
+            NCSmax = std::max<int64_t>(NCSmax, (int64_t)ccols[(size_t)p].size());
+        }
+        NCS = (int32_t)std::max<int64_t>(NCSmax, 1);
+        std::vector<int32_t> h_cid((size_t)B * NCS, 0), h_cptr((size_t)B * (NCS + 1), 0), h_crow((size_t)B * NZ, 0);
+        std::vector<double> h_cval((size_t)B * NZ, 0.0);
+        std::vector<int32_t> slot((size_t)n), fill;
+        for (int64_t p = 0; p < B; p++) {
+            const std::vector<int32_t> &cc = ccols[(size_t)p];
+            std::fill(colcnt.begin(), colcnt.end(), 0);
+            const int32_t nzp = h_sptr[(size_t)p * (NS + 1) + NS];
+            for (int32_t q = 0; q < nzp; q++) colcnt[(size_t)h_scol[(size_t)p * NZ + q]]++;
+            int32_t acc = 0;
+            fill.assign(cc.size(), 0);
+            for (size_t k = 0; k < cc.size(); k++) {
+                slot[(size_t)cc[k]] = (int32_t)k;
+                h_cid[(size_t)p * NCS + k] = cc[k];
+                h_cptr[(size_t)p * (NCS + 1) + k] = acc;
+                fill[k] = acc;
+                acc += colcnt[(size_t)cc[k]];
+            }
+            for (size_t k = cc.size(); k <= (size_t)NCS; k++) h_cptr[(size_t)p * (NCS + 1) + k] = acc;
+            for (int32_t sr = 0; sr < h_cnt[(size_t)p * 2]; sr++)  // row order inside a column = sparse-row order
+                for (int32_t q = h_sptr[(size_t)p * (NS + 1) + sr]; q < h_sptr[(size_t)p * (NS + 1) + sr + 1]; q++) {
+                    const int32_t k = slot[(size_t)h_scol[(size_t)p * NZ + q]];
+                    const int32_t pos = fill[(size_t)k]++;
+                    h_crow[(size_t)p * NZ + pos] = h_sid[(size_t)p * NS + sr];
+                    h_cval[(size_t)p * NZ + pos] = h_sval[(size_t)p * NZ + q];
+                }
+            h_cnt[(size_t)p * 2 + 1] = (int32_t)cc.size();
+        }
+        d_cnt.upload(h_cnt);
+        d_cid.upload(h_cid);
+        d_cptr.upload(h_cptr);
+        d_crow.upload(h_crow);
+        d_cval.upload(h_cval);
+        h->stats.launches += 3;
     }
     // b, c and their norms (host vectors)
     {
@@ -1002,6 +1178,20 @@ void BatchSolver::launch(int64_t i_start, int64_t n_iters, int64_t checki, doubl
     a.KP = KP;
     a.A = dA.p;
     a.a_stride = a_stride;
+    a.drow = d_drow.p;
+    a.sp_count = d_cnt.p;
+    a.srow_ptr = d_sptr.p;
+    a.srow_id = d_sid.p;
+    a.scol = d_scol.p;
+    a.sval = d_sval.p;
+    a.ccol_ptr = d_cptr.p;
+    a.ccol_id = d_cid.p;
+    a.crow = d_crow.p;
+    a.cval = d_cval.p;
+    a.NS = NS;
+    a.NCS = NCS;
+    a.NZ = NZ;
+    a.mr = (int32_t)(L.m_pad + 16);
     a.b = db.p;
     a.c = dc.p;
     a.nb = dnb.p;
@@ -1080,6 +1270,11 @@ void BatchSolver::collect(int64_t *iters_done, int32_t *status, double *records,
     }
 }
 
-double BatchSolver::bytes_per_pass() const { return 8.0 * (double)L.m * (double)L.n; }
+// algorithmic bytes of one pass over one problem's A, batch average: dense rows as FP64 + sparse rows as
+// CSR and CSC entries (8-byte value + 4-byte index each)
+double BatchSolver::bytes_per_pass() const
+{
+    return (8.0 * (double)dense_rows_total * (double)L.n + 24.0 * (double)sparse_nnz_total) / (double)B;
+}
 
 }  // namespace fos

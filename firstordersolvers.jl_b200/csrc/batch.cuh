@@ -43,8 +43,19 @@ struct BatchArgs {
     int64_t lda;        // leading dimension of every A (doubles, multiple of 16)
     int32_t ntiles;     // tiles of BT_TR rows per problem
     int32_t S, CW, KP;  // ring stages, consumer warps, column pairs per consumer thread
-    const double *A;    // [B][ntiles*BT_TR][lda]
+    const double *A;    // [B][ntiles*BT_TR][lda]: the DENSE rows of every problem, gathered into tiles
     int64_t a_stride;
+    // Hybrid storage: rows with few non-zeros (<= n/8) are kept out of the dense tiles and stored as CSR (for
+    // A x) + CSC (for A' w); all-zero rows are stored nowhere.  Config 5's conic NNLS form has 256 dense rows
+    // and 513 rows with a single entry: 1.08 MB of tiles instead of 3.2 MB per problem and pass.
+    const int32_t *drow;      // [B][ntiles*BT_TR] original row of every tile row (mr - 16 = dummy slot for padding)
+    const int32_t *sp_count;  // [B][2] {sparse rows, columns with sparse entries}
+    const int32_t *srow_ptr, *srow_id, *scol;  // [B][NS+1], [B][NS], [B][NZ]
+    const double *sval;                        // [B][NZ]
+    const int32_t *ccol_ptr, *ccol_id, *crow;  // [B][NCS+1], [B][NCS], [B][NZ]
+    const double *cval;                        // [B][NZ]
+    int32_t NS, NCS, NZ;                       // capacities = strides of the arrays above
+    int32_t mr;                                // row slots of the shared-memory A X / W arrays (m_pad + 16)
     const double *b, *c;    // [B][m_pad], [B][n_pad]
     const double *nb, *ncn; // [B] ||b||, ||c||
     double *vec;            // [B][BV_COUNT][NP]

@@ -105,6 +105,9 @@ int32_t fos_set_option(fos_handle_t hh, const char *key, double value)
         FOS_REQUIRE(value == 0 || value == 1, "exchange_impl must be 0 (NCCL) or 1 (peer memory)");
         FOS_REQUIRE(value == 0 || h.A.p2p.nranks > 1, "exchange_impl = 1 needs fos_comm_p2p_import first");
         h.A.p2p_on = value != 0;
+    } else if (k == "batch_hybrid") {
+        FOS_REQUIRE(!(h.batch && h.batch->loaded), "batch_hybrid must be set before loading the batch");
+        h.batch_hybrid = value != 0;
     } else if (k == "batch_ctas") {
         h.batch_ctas = (int)value;
         if (h.batch) h.batch->grid_ctas = (int)value;
@@ -426,7 +429,7 @@ int32_t fos_get_info(fos_handle_t hh, int32_t which, double *out)
     case 11: *out = h.A.prof_ms[1]; break;
     case 12: *out = (double)h.A.prof_n[1]; break;
     case 13: *out = (double)h.A.prof_skipped; break;
-    case 14: *out = h.A.bytes_per_pass(); break;
+    case 14: *out = (h.batch && h.batch->loaded) ? h.batch->bytes_per_pass() : h.A.bytes_per_pass(); break;
     case 15: *out = (double)h.num_sms; break;
     case 16: *out = h.A.prof_ms[0]; break;
     case 17: *out = (double)h.A.prof_n[0]; break;
@@ -519,6 +522,7 @@ int32_t fos_load_conic_dense_batch(fos_handle_t hh, int64_t nprob, int64_t m, in
     h.loaded = false;
     h.batch.reset(new BatchSolver());
     h.batch->grid_ctas = h.batch_ctas;
+    h.batch->hybrid = h.batch_hybrid != 0;
     h.batch->load(&h, nprob, m, n, A, lda, pstride, a_location, b, c, ncones1, cone_type1, cone_len1, ncones2,
                   cone_type2, cone_len2);
     h.alg = FOS_ALG_GAP;
@@ -573,6 +577,7 @@ int32_t fos_set_state_batch(fos_handle_t hh, int32_t which, const double *buf)
         FOS_CUDA(cudaMemcpy(hc.data(), bs.dctl.p, hc.size() * sizeof(BatchCtl), cudaMemcpyDeviceToHost));
         for (BatchCtl &c : hc) c.firstrun = 0;
         FOS_CUDA(cudaMemcpy(bs.dctl.p, hc.data(), hc.size() * sizeof(BatchCtl), cudaMemcpyHostToDevice));
+        FOS_SYNC_LEGACY();
     }
     FOS_API_END(hh)
 }
@@ -619,6 +624,7 @@ int32_t fos_set_info_batch(fos_handle_t hh, int32_t which, const double *values)
         }
     }
     FOS_CUDA(cudaMemcpy(bs.dctl.p, hc.data(), hc.size() * sizeof(BatchCtl), cudaMemcpyHostToDevice));
+    FOS_SYNC_LEGACY();
     FOS_API_END(hh)
 }
 
@@ -932,6 +938,7 @@ int32_t fos_time_psd(fos_handle_t hh, int64_t d, int64_t ncones, const double *x
     dout.alloc((size_t)NP);
     FOS_CUDA(cudaMemcpy2D(din.p, (size_t)seglen * 8, x, (size_t)plen * 8, (size_t)plen * 8, (size_t)ncones,
                           cudaMemcpyHostToDevice));
+    FOS_SYNC_LEGACY();
     auto project = [&]() {
         if (!K.psd.empty()) psd_project(&h, K, din.p, dout.p);
         if (!K.psd_large.empty()) psd_project_large(&h, K, din.p, dout.p);

@@ -32,6 +32,11 @@ struct Error : std::runtime_error {
         }                                                                                                \
     } while (0)
 
+// A synchronous cudaMemcpy from pageable host memory returns once the data sit in the driver's staging buffer;
+// the DMA itself runs on the legacy default stream, which does not order against the handle's non-blocking
+// stream.  Every synchronous host-to-device copy (and cudaMemset) is therefore followed by this wait.
+#define FOS_SYNC_LEGACY() FOS_CUDA(cudaStreamSynchronize(cudaStreamLegacy))
+
 #define FOS_REQUIRE(cond, msg)                                                   \
     do {                                                                         \
         if (!(cond)) throw ::fos::Error(FOS_ERR_INVALID, std::string(msg));      \

@@ -70,9 +70,11 @@ void MatOp::init_dense(int64_t m_, int64_t n_, const double *Asrc, int64_t lda_s
         lda = ru(n, PAD);
         A_own.alloc((size_t)std::max<int64_t>(m_local, 1) * lda, false);
         FOS_CUDA(cudaMemset(A_own.p, 0, (size_t)std::max<int64_t>(m_local, 1) * lda * 8));
+        FOS_CUDA(cudaStreamSynchronize(cudaStreamLegacy));  // see DevBuf::alloc
         if (m_local > 0)
             FOS_CUDA(cudaMemcpy2D(A_own.p, (size_t)lda * 8, Asrc, (size_t)lda_src * 8, (size_t)n * 8, (size_t)m_local,
                                   location == FOS_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+        FOS_SYNC_LEGACY();
         A = A_own.p;
     }
     make_tmap(&tmap, A, std::max<int64_t>(m_local, 1), n, lda);
@@ -175,6 +177,7 @@ void MatOp::p2p_export(uint8_t *handle_out)
     hd.row_begin = row_begin;
     hd.m_local = m_local;
     FOS_CUDA(cudaMemcpy(p2p_region.p, &hd, sizeof(hd), cudaMemcpyHostToDevice));
+    FOS_SYNC_LEGACY();
     p2p_local.alloc(4);
     cudaIpcMemHandle_t hdl;
     FOS_CUDA(cudaIpcGetMemHandle(&hdl, p2p_region.p));

@@ -296,6 +296,7 @@ void Handle::finish_load_common(const std::vector<ConeSeg> &segs)
     checked = false;
     stats = Stats();
     FOS_CUDA(cudaMemset(d_ctrl.p, 0, sizeof(Ctrl)));
+    FOS_CUDA(cudaStreamSynchronize(cudaStreamLegacy));  // see DevBuf::alloc
     ensure_recs(256);
     ensure_stage((size_t)N);
     loaded = true;
@@ -401,6 +402,7 @@ void Handle::load_affine(int64_t am, int64_t an, const double *b, const double *
     std::vector<double> hb((size_t)L.m_pad, 0.0);
     for (int64_t i = 0; i < am; i++) hb[(size_t)i] = b ? b[i] : 0.0;
     FOS_CUDA(cudaMemcpy(rhs.p + L.n_pad, hb.data(), (size_t)L.m_pad * 8, cudaMemcpyHostToDevice));
+    FOS_SYNC_LEGACY();
     d_bhat.upload(hb);
 }
 
@@ -750,6 +752,7 @@ void Handle::begin_solve()
     if (L.form == 1) {
         std::vector<double> nanv((size_t)L.NP, std::nan(""));
         FOS_CUDA(cudaMemcpy(prev.p, nanv.data(), (size_t)L.NP * 8, cudaMemcpyHostToDevice));
+        FOS_SYNC_LEGACY();
     }
 }
 

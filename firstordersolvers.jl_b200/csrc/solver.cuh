@@ -41,12 +41,21 @@ struct DevBuf {
             throw Error(FOS_ERR_NOMEM, std::string("cudaMalloc of ") + std::to_string(count * sizeof(T)) +
                                            " bytes failed: " + cudaGetErrorString(e));
         }
-        if (zero) FOS_CUDA(cudaMemset(p, 0, count * sizeof(T)));
+        if (zero) {
+            // cudaMemset on device memory is asynchronous and runs on the legacy default stream, which does not
+            // order against the handle's non-blocking stream: wait for it, or a kernel enqueued right after the
+            // allocation can be overtaken by (and wiped out by) the zero fill
+            FOS_CUDA(cudaMemset(p, 0, count * sizeof(T)));
+            FOS_CUDA(cudaStreamSynchronize(cudaStreamLegacy));
+        }
     }
     void upload(const std::vector<T> &h)
     {
         alloc(h.size(), false);
-        if (!h.empty()) FOS_CUDA(cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+        if (!h.empty()) {
+            FOS_CUDA(cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+            FOS_SYNC_LEGACY();
+        }
     }
 };
 
@@ -195,7 +204,11 @@ struct BatchSolver {
     int ntiles = 0, S = 0, CW = 0, KP = 1, ctas_per_sm = 1;
     size_t smem_bytes = 0;
     int grid_ctas = 0;
-    DevBuf<double> dA, db, dc, dnb, dncn, vec, drecs, dtol;
+    DevBuf<double> dA, db, dc, dnb, dncn, vec, drecs, dtol, d_sval, d_cval;
+    DevBuf<int32_t> d_drow, d_cnt, d_sptr, d_sid, d_scol, d_cptr, d_cid, d_crow;
+    int32_t NS = 1, NCS = 1, NZ = 1;
+    int64_t dense_rows_total = 0, sparse_nnz_total = 0;
+    bool hybrid = true;  // rows with <= n/8 non-zeros as CSR/CSC instead of dense tiles
     DevBuf<BatchCtl> dctl;
     DevBuf<unsigned int> counter;
     ConeSet cones;
@@ -224,7 +237,7 @@ struct Handle {
     int num_sms = 148;
     std::string err;
     // options
-    int matvec_impl = 0, grid_ctas = 0, cg_batch = 0, fuse_rhs = 1, batch_ctas = 0, fuse_tail = 1;
+    int matvec_impl = 0, grid_ctas = 0, cg_batch = 0, fuse_rhs = 1, batch_ctas = 0, fuse_tail = 1, batch_hybrid = 1;
     // problem
     bool loaded = false;
     Lay L{};

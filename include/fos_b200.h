@@ -107,6 +107,8 @@ const char *fos_last_error(fos_handle_t h);
  *                  of ~10); 0 = always start from the identity.  Set after loading.
  *   "exchange_impl" multi-GPU: 1 = fused peer-memory exchange (after fos_comm_p2p_import), 0 = NCCL
  *   "profile_matvec" 1 = CUDA events around every mat-vec launch (read back with fos_get_info)
+ *   "batch_hybrid" 1 (default) = batch mode keeps rows with <= n/8 non-zeros out of the dense tiles (CSR + CSC) and
+ *                  skips empty rows; 0 = every row is streamed as dense FP64.  Set before loading the batch.
  *   "batch_ctas"   persistent CTAs of the batch kernel (default = #SMs)
  *   "use_graphs"   reserved                                                                */
 int32_t fos_set_option(fos_handle_t h, const char *key, double value);

@@ -215,6 +215,34 @@ def test_batch_config5_shape(fos):
             np.testing.assert_allclose(recs[j][:, 1:8], r1[:, 1:8], rtol=2e-2, atol=1e-6)
 
 
+def test_batch_hybrid_storage_equals_dense_storage(fos):
+    """Rows with few non-zeros travel as CSR/CSC instead of dense tiles ("batch_hybrid", default on): the
+    trajectories must equal the all-dense layout up to the association of the column sums, on matrices with
+    ragged patterns (different dense/sparse/empty rows per problem)."""
+    from fos_b200 import problems
+    rng = np.random.default_rng(8)
+    B, plist = 6, []
+    for j in range(B):
+        P = problems.nnls_conic(24, 30, seed=40 + j, scale=0.1)
+        A = np.asarray(P.A.todense())
+        A[1 + rng.integers(0, 24, size=j)] = 0.0              # a few empty rows, a different set per problem
+        A[1 + rng.integers(0, 24), rng.integers(0, 31, size=28)] = 0.0  # a dense row turned sparse
+        P.A = A
+        plist.append(P)
+    res = []
+    for hybrid in (1, 0):
+        H = _load_batch(fos, plist, batch_hybrid=hybrid)
+        H.set_algorithm(fos.DR(0.5))
+        H.ck(H.L.fos_begin_solve_batch(H.h))
+        done, st, recs = H.run_batch(1, 40, 10, 1e-12)
+        res.append((H.get_iterate_batch(), recs, H.info("bytes_per_pass"), H.info_batch("total_cg")))
+    assert rel_err(res[0][0], res[1][0]) < 1e-9
+    for ra, rb in zip(res[0][1], res[1][1]):
+        np.testing.assert_allclose(ra[:, 1:8], rb[:, 1:8], rtol=1e-8, atol=1e-13)
+    np.testing.assert_array_equal(res[0][3], res[1][3])
+    assert res[0][2] < 0.6 * res[1][2]                      # the hybrid layout streams far fewer bytes
+
+
 def test_batch_api_end_to_end_and_errors(fos):
     from fos_b200 import problems
     B = 4
