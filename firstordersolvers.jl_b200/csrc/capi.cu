@@ -94,6 +94,9 @@ int32_t fos_set_option(fos_handle_t hh, const char *key, double value)
         h.cg_batch = (int)value;
     } else if (k == "fuse_rhs") {
         h.fuse_rhs = value != 0;
+    } else if (k == "tail_blocks") {
+        FOS_REQUIRE(value >= 0 && value <= 2 * h.num_sms, "tail_blocks out of range");
+        h.tail_blocks = (int)value;
     } else if (k == "psd_warm") {
         h.cones.psd_warm_enabled = value != 0;
     } else if (k == "fuse_tail") {

@@ -138,6 +138,52 @@ __device__ __forceinline__ double mv_atw(const MVView &V, int v, int64_t j)
     return s;
 }
 
+// Both right-hand sides at once: the loads of v = 0 and v = 1 travel together (half the dependent round trips
+// of two mv_ax / mv_atw calls); each sum is still added in index order -> bitwise equal to the single versions.
+__device__ __forceinline__ void mv_ax2(const MVView &V, int64_t i, double &s0, double &s1)
+{
+    s0 = 0.0;
+    s1 = 0.0;
+    const double *p0 = V.rowpart + i, *p1 = V.rowpart + V.rp_sv + i;
+    for (int b0 = 0; b0 < V.nb; b0 += 8) {
+        double t0[8], t1[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const bool in = b0 + k < V.nb;
+            t0[k] = in ? p0[(int64_t)(b0 + k) * V.rp_sb] : 0.0;
+            t1[k] = in ? p1[(int64_t)(b0 + k) * V.rp_sb] : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            s0 += t0[k];
+            s1 += t1[k];
+        }
+    }
+}
+__device__ __forceinline__ void mv_atw2(const MVView &V, int64_t j, double &s0, double &s1)
+{
+    const int64_t band = j >> V.bw_shift;
+    const int64_t jj = j & V.bw_mask;
+    const int a = V.slot_base[band], b = V.slot_base[band + 1];
+    s0 = 0.0;
+    s1 = 0.0;
+    const double *p0 = V.colpart + jj, *p1 = V.colpart + V.cp_sv + jj;
+    for (int t0i = a; t0i < b; t0i += 8) {
+        double t0[8], t1[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const bool in = t0i + k < b;
+            t0[k] = in ? p0[(int64_t)(t0i + k) * V.cp_ss] : 0.0;
+            t1[k] = in ? p1[(int64_t)(t0i + k) * V.cp_ss] : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            s0 += t0[k];
+            s1 += t1[k];
+        }
+    }
+}
+
 // no-contraction arithmetic: the reference's broadcasts round every operation separately
 __device__ __forceinline__ double mul_(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double add_(double a, double b) { return __dadd_rn(a, b); }

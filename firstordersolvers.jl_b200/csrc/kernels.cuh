@@ -52,8 +52,10 @@ k2_kkt_hsde(Lay L, MVView V, const double *__restrict__ in, const double *__rest
             if (e < L.n) {
                 const double cj = c[e];
                 // (Q B).x = A'B.y + B.tau*c   (HSDEAffine.jl:51,54)
-                const double q1 = add_(mv_atw(V, 0, e), mul_(tau1, cj));
-                const double q2 = add_(mv_atw(V, 1, e), mul_(tau2, cj));
+                double w0, w1;
+                mv_atw2(V, e, w0, w1);
+                const double q1 = add_(w0, mul_(tau1, cj));
+                const double q2 = add_(w1, mul_(tau2, cj));
                 o1 = add_(-q2, i1);  // Q'in2 + in1  (transpose = negate, HSDEAffine.jl:61-65)
                 o2 = sub_(q1, i2);   // Q in1 - in2
                 q[0] = fma(cj, i1, q[0]);
@@ -64,8 +66,10 @@ k2_kkt_hsde(Lay L, MVView V, const double *__restrict__ in, const double *__rest
             if (i < L.m) {
                 const double bi = b[i];
                 // (Q B).y = -(A B.x - B.tau*b)   (HSDEAffine.jl:52,55,56)
-                const double q1 = -sub_(mv_ax(V, 0, i), mul_(tau1, bi));
-                const double q2 = -sub_(mv_ax(V, 1, i), mul_(tau2, bi));
+                double a0, a1;
+                mv_ax2(V, i, a0, a1);
+                const double q1 = -sub_(a0, mul_(tau1, bi));
+                const double q2 = -sub_(a1, mul_(tau2, bi));
                 o1 = add_(-q2, i1);
                 o2 = sub_(q1, i2);
                 q[1] = fma(bi, i1, q[1]);
@@ -1179,13 +1183,18 @@ k_cg_tail_hsde(Lay L, MVView V, P2PView X, const double *__restrict__ c, const d
         double *mine = reinterpret_cast<double *>(X.peer[X.rank] + X.buf_off) + (size_t)par * X.slot_doubles;
         const int64_t rb = X.row_begin[X.rank], ml = X.m_local[X.rank];
         for (int64_t e = e0; e < ot; e += stride) {
-#pragma unroll
-            for (int v = 0; v < 2; v++) {
-                if (e < oy) {
-                    mine[(size_t)v * L.n_pad + e] = e < L.n ? mv_atw(V, v, e) : 0.0;
-                } else {
-                    const int64_t row = e - oy, lr = row - rb;
-                    if (lr >= 0 && lr < ml) mine[(size_t)2 * L.n_pad + (size_t)v * L.m_pad + row] = mv_ax(V, v, lr);
+            if (e < oy) {
+                double w0 = 0.0, w1 = 0.0;
+                if (e < L.n) mv_atw2(V, e, w0, w1);
+                mine[e] = w0;
+                mine[(size_t)L.n_pad + e] = w1;
+            } else {
+                const int64_t row = e - oy, lr = row - rb;
+                if (lr >= 0 && lr < ml) {
+                    double a0, a1;
+                    mv_ax2(V, lr, a0, a1);
+                    mine[(size_t)2 * L.n_pad + row] = a0;
+                    mine[(size_t)2 * L.n_pad + (size_t)L.m_pad + row] = a1;
                 }
             }
         }
@@ -1219,8 +1228,7 @@ k_cg_tail_hsde(Lay L, MVView V, P2PView X, const double *__restrict__ c, const d
                     w0 = acc[0];
                     w1 = acc[1];
                 } else {
-                    w0 = mv_atw(V, 0, e);
-                    w1 = mv_atw(V, 1, e);
+                    mv_atw2(V, e, w0, w1);
                 }
                 const double cj = c[e];
                 const double q1 = add_(w0, mul_(tau1, cj));
@@ -1243,8 +1251,7 @@ k_cg_tail_hsde(Lay L, MVView V, P2PView X, const double *__restrict__ c, const d
                     a0 = ld_sys_f64(src + 2 * L.n_pad + i);
                     a1 = ld_sys_f64(src + 2 * L.n_pad + L.m_pad + i);
                 } else {
-                    a0 = mv_ax(V, 0, i);
-                    a1 = mv_ax(V, 1, i);
+                    mv_ax2(V, i, a0, a1);
                 }
                 const double bi = b[i];
                 const double q1 = -sub_(a0, mul_(tau1, bi));
@@ -1268,17 +1275,31 @@ k_cg_tail_hsde(Lay L, MVView V, P2PView X, const double *__restrict__ c, const d
     const double pAp = q[4] + o1t * tau1 + o2t * tau2;
     const double alpha = rn / pAp;  // cg :39
     // ---- x += alpha p ; r -= alpha Ap ; ||r||  (k3_cg_update) ----
+    // r_new and p of the first TAIL_EPT entries of every thread stay in registers for the direction update
+    // (one global round trip less on the critical path); longer vectors fall back to memory
+    constexpr int TAIL_EPT = 3;
+    double keep_r[TAIL_EPT][2], keep_p[TAIL_EPT][2];
     double q2r[1] = {0.0};
-    for (int64_t e = e0; e < LP; e += stride) {
+    {
+        int kx = 0;
+        for (int64_t e = e0; e < LP; e += stride, kx++) {
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const int64_t g = e + h * LP;
-            double ape = Ap[g];
-            if (e == ot) ape = h == 0 ? o1t : o2t;
-            sol[g] = add_(sol[g], mul_(alpha, p[g]));
-            const double re = sub_(r[g], mul_(alpha, ape));
-            r[g] = re;
-            q2r[0] = fma(re, re, q2r[0]);
+            for (int h = 0; h < 2; h++) {
+                const int64_t g = e + h * LP;
+                double ape = Ap[g];
+                if (e == ot) ape = h == 0 ? o1t : o2t;
+                const double pe = p[g];
+                sol[g] = add_(sol[g], mul_(alpha, pe));
+                const double re = sub_(r[g], mul_(alpha, ape));
+                r[g] = re;
+                q2r[0] = fma(re, re, q2r[0]);
+#pragma unroll
+                for (int t = 0; t < TAIL_EPT; t++)
+                    if (t == kx) {
+                        keep_r[t][h] = re;
+                        keep_p[t][h] = pe;
+                    }
+            }
         }
     }
     grid_allreduce<1>(q2r, gb.part + (size_t)gridDim.x * 8, gb, nbar, base);
@@ -1286,11 +1307,30 @@ k_cg_tail_hsde(Lay L, MVView V, P2PView X, const double *__restrict__ c, const d
     const double rnorm = sqrt(rr);
     const bool stop = rnorm <= tol || iter >= max_iters;  // cg :42
     const double beta = rr / rn;
-    if (!stop)
-        for (int64_t e = e0; e < LP; e += stride) {  // p = beta p + r  (:49-50)
-            p[e] = add_(mul_(beta, p[e]), r[e]);
-            p[LP + e] = add_(mul_(beta, p[LP + e]), r[LP + e]);
+    if (!stop) {
+        int kx = 0;
+        for (int64_t e = e0; e < LP; e += stride, kx++) {  // p = beta p + r  (:49-50)
+            double pe0, pe1, re0, re1;
+            if (kx < TAIL_EPT) {
+                pe0 = pe1 = re0 = re1 = 0.0;
+#pragma unroll
+                for (int t = 0; t < TAIL_EPT; t++)
+                    if (t == kx) {
+                        pe0 = keep_p[t][0];
+                        pe1 = keep_p[t][1];
+                        re0 = keep_r[t][0];
+                        re1 = keep_r[t][1];
+                    }
+            } else {
+                pe0 = p[e];
+                pe1 = p[LP + e];
+                re0 = r[e];
+                re1 = r[LP + e];
+            }
+            p[e] = add_(mul_(beta, pe0), re0);
+            p[LP + e] = add_(mul_(beta, pe1), re1);
         }
+    }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         Ap[ot] = o1t;
         Ap[LP + ot] = o2t;

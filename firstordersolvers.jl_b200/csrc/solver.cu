@@ -450,7 +450,8 @@ void Handle::cg_enqueue_iteration()
         const bool p2p = A.nranks > 1 && A.p2p_on;
         MVView V = kkt_pass(p.p, skip, /*defer_exchange=*/p2p);
         // identical on every rank (block i of all ranks owns the same entries); co-resident by construction
-        const int grid = (int)std::min<int64_t>((L.LP + VBLOCK - 1) / VBLOCK, std::min<int64_t>((int64_t)num_sms, P2P_MAX_BLOCKS));
+        const int grid = (int)std::min<int64_t>((L.LP + VBLOCK - 1) / VBLOCK,
+                                                std::min<int64_t>(tail_blocks > 0 ? tail_blocks : (int64_t)num_sms, P2P_MAX_BLOCKS));
         const double *cptr = d_c.p, *bptr = d_b.p;
         double *solp = sol.p, *rp = r.p, *pp = p.p, *App = Ap.p;
         Ctrl *cp = d_ctrl.p;
