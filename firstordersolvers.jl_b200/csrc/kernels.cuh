@@ -940,13 +940,19 @@ __device__ __forceinline__ void st_release_sys_u32(unsigned int *p, unsigned int
 constexpr long long P2P_TIMEOUT_CYCLES = 60000000000LL;
 __device__ __forceinline__ void p2p_wait_flag(const unsigned int *f, unsigned int epoch, unsigned int *error)
 {
+    // poll with relaxed system-scope loads (an acquire per poll would invalidate L1 every iteration) and
+    // acquire once, after the flag has been seen
     const long long t0 = clock64();
-    while ((int)(ld_acquire_sys_u32(f) - epoch) < 0) {
+    for (;;) {
+        unsigned int v;
+        asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+        if ((int)(v - epoch) >= 0) break;
         if (clock64() - t0 > P2P_TIMEOUT_CYCLES) {
             atomicExch(error, 1u);
             break;
         }
     }
+    asm volatile("fence.acq_rel.sys;" ::: "memory");
 }
 
 // Sum over ranks (rank order) of NV entries `off + v*vstride` of every rank's slot.  All remote loads of a
