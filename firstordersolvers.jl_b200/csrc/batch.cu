@@ -207,44 +207,67 @@ __device__ __forceinline__ double bt_kkt_epilogue(BK &k, const double *in, doubl
     const double tau1 = in[ot], tau2 = in[LP + ot];
     const double *ax0 = k.s_ax, *ax1 = k.s_ax + k.a->mr, *atw0 = k.s_atw, *atw1 = k.s_atw + L.n_pad;
     double q[5] = {0, 0, 0, 0, 0};
-    for (int64_t e = k.ct; e < ot; e += k.NT) {
-        double o1 = 0.0, o2 = 0.0;
-        const double i1 = in[e], i2 = in[LP + e];
-        if (e < oy) {
-            if (e < L.n) {
-                const double cj = k.c[e];
-                const double q1 = add_(atw0[e], mul_(tau1, cj));  // HSDEAffine.jl:51,54
-                const double q2 = add_(atw1[e], mul_(tau2, cj));
-                o1 = add_(-q2, i1);  // Q'in2 + in1 (HSDEAffine.jl:61-65)
-                o2 = sub_(q1, i2);   // Q in1 - in2
-                q[0] = fma(cj, i1, q[0]);
-                q[2] = fma(cj, i2, q[2]);
+    for (int64_t base = k.ct; base < ot; base += 4 * (int64_t)k.NT) {
+        // loads of four entries first (see the CG update loop), then the arithmetic and the stores
+        double i1s[4], i2s[4], cbs[4], r1s[4], r2s[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int64_t e = base + (int64_t)u * k.NT;
+            const bool inr = e < ot;
+            i1s[u] = inr ? in[e] : 0.0;
+            i2s[u] = inr ? in[LP + e] : 0.0;
+            cbs[u] = 0.0;
+            if (inr) {
+                if (e < oy) cbs[u] = e < L.n ? k.c[e] : 0.0;
+                else cbs[u] = (e - oy) < L.m ? k.b[e - oy] : 0.0;
             }
-        } else {
-            const int64_t i = e - oy;
-            if (i < L.m) {
-                const double bi = k.b[i];
-                const double q1 = -sub_(ax0[i], mul_(tau1, bi));  // HSDEAffine.jl:52,55,56
-                const double q2 = -sub_(ax1[i], mul_(tau2, bi));
-                o1 = add_(-q2, i1);
-                o2 = sub_(q1, i2);
-                q[1] = fma(bi, i1, q[1]);
-                q[3] = fma(bi, i2, q[3]);
+            if (MODE == K2_RESID) {
+                r1s[u] = inr ? rhs[e] : 0.0;
+                r2s[u] = inr ? rhs[LP + e] : 0.0;
             }
         }
-        if (MODE == K2_AP) {
-            out[e] = o1;
-            out[LP + e] = o2;
-            q[4] = fma(o1, i1, q[4]);
-            q[4] = fma(o2, i2, q[4]);
-        } else {
-            const double r1 = sub_(rhs[e], o1), r2 = sub_(rhs[LP + e], o2);
-            r[e] = r1;
-            r[LP + e] = r2;
-            p[e] = r1;
-            p[LP + e] = r2;
-            q[4] = fma(r1, r1, q[4]);
-            q[4] = fma(r2, r2, q[4]);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int64_t e = base + (int64_t)u * k.NT;
+            if (e >= ot) continue;
+            double o1 = 0.0, o2 = 0.0;
+            const double i1 = i1s[u], i2 = i2s[u];
+            if (e < oy) {
+                if (e < L.n) {
+                    const double cj = cbs[u];
+                    const double q1 = add_(atw0[e], mul_(tau1, cj));  // HSDEAffine.jl:51,54
+                    const double q2 = add_(atw1[e], mul_(tau2, cj));
+                    o1 = add_(-q2, i1);  // Q'in2 + in1 (HSDEAffine.jl:61-65)
+                    o2 = sub_(q1, i2);   // Q in1 - in2
+                    q[0] = fma(cj, i1, q[0]);
+                    q[2] = fma(cj, i2, q[2]);
+                }
+            } else {
+                const int64_t i = e - oy;
+                if (i < L.m) {
+                    const double bi = cbs[u];
+                    const double q1 = -sub_(ax0[i], mul_(tau1, bi));  // HSDEAffine.jl:52,55,56
+                    const double q2 = -sub_(ax1[i], mul_(tau2, bi));
+                    o1 = add_(-q2, i1);
+                    o2 = sub_(q1, i2);
+                    q[1] = fma(bi, i1, q[1]);
+                    q[3] = fma(bi, i2, q[3]);
+                }
+            }
+            if (MODE == K2_AP) {
+                out[e] = o1;
+                out[LP + e] = o2;
+                q[4] = fma(o1, i1, q[4]);
+                q[4] = fma(o2, i2, q[4]);
+            } else {
+                const double r1 = sub_(r1s[u], o1), r2 = sub_(r2s[u], o2);
+                r[e] = r1;
+                r[LP + e] = r2;
+                p[e] = r1;
+                p[LP + e] = r2;
+                q[4] = fma(r1, r1, q[4]);
+                q[4] = fma(r2, r2, q[4]);
+            }
         }
     }
     bt_reduce<5>(k, q);
@@ -301,12 +324,29 @@ __device__ __forceinline__ void bt_s1_prox(BK &k, const double *xin)
         const double pAp = bt_kkt_epilogue<K2_AP>(k, p, Ap, nullptr, nullptr, nullptr);
         const double alpha = rn / pAp;  // :39
         double q[1] = {0.0};
-        for (int64_t e = k.ct; e < NP; e += k.NT) {
-            const double pe = p[e];
-            sol[e] = add_(sol[e], mul_(alpha, pe));            // :40
-            const double re = sub_(r[e], mul_(alpha, Ap[e]));  // :41
-            r[e] = re;
-            q[0] = fma(re, re, q[0]);
+        // four entries per thread at a time, all loads first: the stores of one entry would otherwise fence the
+        // loads of the next (possible aliasing) and every entry would pay its own L2 round trip
+        for (int64_t base = k.ct; base < NP; base += 4 * (int64_t)k.NT) {
+            double ps[4], ss[4], rs[4], as[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int64_t e = base + (int64_t)u * k.NT;
+                const bool in = e < NP;
+                ps[u] = in ? p[e] : 0.0;
+                ss[u] = in ? sol[e] : 0.0;
+                rs[u] = in ? r[e] : 0.0;
+                as[u] = in ? Ap[e] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int64_t e = base + (int64_t)u * k.NT;
+                if (e < NP) {
+                    sol[e] = add_(ss[u], mul_(alpha, ps[u]));          // :40
+                    const double re = sub_(rs[u], mul_(alpha, as[u]));  // :41
+                    r[e] = re;
+                    q[0] = fma(re, re, q[0]);
+                }
+            }
         }
         bt_reduce<1>(k, q);
         const double rr = q[0];
@@ -318,7 +358,20 @@ __device__ __forceinline__ void bt_s1_prox(BK &k, const double *xin)
         const double beta = rr / rn;  // :45-47
         rn = rr;
         iter += 1;  // :51
-        for (int64_t e = k.ct; e < NP; e += k.NT) p[e] = add_(mul_(beta, p[e]), r[e]);  // :49-50
+        for (int64_t base = k.ct; base < NP; base += 4 * (int64_t)k.NT) {  // p = beta p + r  (:49-50)
+            double ps[4], rs[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int64_t e = base + (int64_t)u * k.NT;
+                ps[u] = e < NP ? p[e] : 0.0;
+                rs[u] = e < NP ? r[e] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int64_t e = base + (int64_t)u * k.NT;
+                if (e < NP) p[e] = add_(mul_(beta, ps[u]), rs[u]);
+            }
+        }
         cbar(k.NT);
     }
     k.cgiter = iter;
