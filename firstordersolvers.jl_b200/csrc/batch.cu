@@ -974,6 +974,8 @@ void BatchSolver::load(Handle *h_, int64_t B_, int64_t m, int64_t n, const doubl
         d_nnz.alloc((size_t)B * m);
         k_row_nnz<<<dim3((unsigned)((m + 7) / 8), (unsigned)B), 256, 0, h->stream>>>(src, lda_src, pstride_src, m, n, d_nnz.p);
         std::vector<int32_t> nnz((size_t)B * m);
+        // the handle's stream is non-blocking: a synchronous cudaMemcpy (legacy stream) does not wait for it
+        FOS_CUDA(cudaStreamSynchronize(h->stream));
         FOS_CUDA(cudaMemcpy(nnz.data(), d_nnz.p, nnz.size() * 4, cudaMemcpyDeviceToHost));
         const int64_t thr = hybrid ? std::max<int64_t>(1, n / 8) : 0;  // rows with <= thr non-zeros go to CSR
         std::vector<std::vector<int32_t>> drows((size_t)B), srows((size_t)B);

@@ -238,6 +238,9 @@ int32_t fos_load_conic_dense(fos_handle_t hh, int64_t m, int64_t n, const double
     h.loaded = false;
     FOS_REQUIRE(m > 0 && n > 0 && A && b && c, "bad dense problem arguments");
     FOS_REQUIRE(a_location == FOS_MEM_HOST || a_location == FOS_MEM_DEVICE, "bad a_location");
+    // a device-resident matrix was produced on the caller's stream(s); the library works on its own
+    // non-blocking stream, so wait for everything the caller has enqueued before reading it
+    if (a_location == FOS_MEM_DEVICE) FOS_CUDA(cudaDeviceSynchronize());
     h.A.impl = h.matvec_impl;
     h.A.init_dense(m, n, A, lda, a_location, row_begin, row_count, h.grid_ctas, h.stream);
     h.load_conic(m, n, b, c, ncones1, cone_type1, cone_len1, ncones2, cone_type2, cone_len2);
@@ -522,6 +525,7 @@ int32_t fos_load_conic_dense_batch(fos_handle_t hh, int64_t nprob, int64_t m, in
     FOS_REQUIRE(lda >= n && pstride >= (m - 1) * lda + n, "bad leading dimension / problem stride");
     FOS_REQUIRE(a_location == FOS_MEM_HOST || a_location == FOS_MEM_DEVICE, "bad a_location");
     FOS_REQUIRE(h.nranks == 1, "batch mode is split across GPUs by the caller (one handle per rank), not row-sharded");
+    if (a_location == FOS_MEM_DEVICE) FOS_CUDA(cudaDeviceSynchronize());  // see fos_load_conic_dense
     h.loaded = false;
     h.batch.reset(new BatchSolver());
     h.batch->grid_ctas = h.batch_ctas;
@@ -576,6 +580,7 @@ int32_t fos_set_state_batch(fos_handle_t hh, int32_t which, const double *buf)
     FOS_REQUIRE(buf != nullptr, "null input");
     bs.set_vector(batch_vec_of(which, true), buf, 0, bs.B);
     if (which == 3) {  // restoring the CG warm start clears S1's first-run flag (affinepluslinear.jl:101-104)
+        FOS_CUDA(cudaStreamSynchronize(hh->h.stream));
         std::vector<BatchCtl> hc((size_t)bs.B);
         FOS_CUDA(cudaMemcpy(hc.data(), bs.dctl.p, hc.size() * sizeof(BatchCtl), cudaMemcpyDeviceToHost));
         for (BatchCtl &c : hc) c.firstrun = 0;

@@ -65,6 +65,8 @@ def run_c5(args):
     for name, alg in (("FISTA", fos.FISTA()), ("Dykstra", fos.Dykstra())):
         H = fos.Handle(0)
         H.set_option("batch_hybrid", 0 if args.dense_batch else 1)
+        if args.batch_ctas:
+            H.set_option("batch_ctas", args.batch_ctas)
         H.load_conic_batch((B, m, n), b, c, cones1, cones2, device_ptr=(A.data_ptr(), n, m * n))
         H.set_algorithm(alg)
         stream = torch.cuda.ExternalStream(H.stream(), device=dev)
@@ -78,7 +80,7 @@ def run_c5(args):
         cgs = H.info_batch("total_cg").sum() - cg0
         bytes_pass = H.info("bytes_per_pass")   # dense rows as FP64 + sparse rows as CSR/CSC entries
         gbs = passes * bytes_pass / (ms / 1e3) / 1e9
-        line = {"config": "C5", "dense_equivalent_bytes_per_pass": 8.0 * m * n, "algorithm": name, "nprob": B, "m": m, "n": n, "iterations_timed": K,
+        line = {"config": "C5", "batch_ctas": args.batch_ctas, "dense_equivalent_bytes_per_pass": 8.0 * m * n, "algorithm": name, "nprob": B, "m": m, "n": n, "iterations_timed": K,
                 "ms_total": ms, "problem_iterations_per_s": B * K / (ms / 1e3),
                 "iterations_per_s_per_problem_stream": K / (ms / 1e3),
                 "cg_iterations_per_step": cgs / (B * K), "passes_over_A_per_step": passes / (B * K),
@@ -249,6 +251,7 @@ def main():
     ap.add_argument("--md", type=int, default=100000)
     ap.add_argument("--nx", type=int, default=20000)
     ap.add_argument("--cpu", action="store_true")
+    ap.add_argument("--batch-ctas", type=int, default=0, help="c5: persistent CTAs of the batch kernel (0 = default)")
     ap.add_argument("--dense-batch", action="store_true", help="c5: stream every row as dense FP64 (batch_hybrid = 0)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"])
     args = ap.parse_args()
