@@ -243,3 +243,142 @@ def test_hsde_status_and_solution_nnls():
     assert x[1:].min() > -1e-6
     # forced final check is absent when the last iteration was a check iteration (a-Q 3)
     assert r["history"]["i"][-1] == r["iterations"]
+
+
+# ---------------------------------------------------------------------------------------------
+# direct = true, LineSearchWrapper, the remaining cones (pins the oracle's restatements)
+# ---------------------------------------------------------------------------------------------
+def _dense_Q(P):
+    A = np.asarray(P.A.todense()) if sp.issparse(P.A) else np.asarray(P.A)
+    m, n = A.shape
+    l = m + n + 1
+    Q = np.zeros((l, l))
+    Q[:n, n:n + m] = A.T
+    Q[:n, -1] = P.c
+    Q[n:n + m, :n] = -A
+    Q[n:n + m, -1] = P.b
+    Q[-1, :n] = -P.c
+    Q[-1, n:n + m] = -P.b
+    return Q
+
+
+@pytest.mark.parametrize("kind", ["nnls", "sdp"])
+def test_direct_projection_is_indaffine(kind):
+    """HSDE.jl:10-15 / test/HSDEAffine.jl:72-80: with direct = true S1 is IndAffine([Q -I], 0); its prox is
+    z - B'(B B')^-1 B z, lands on {Qu = v} and is idempotent."""
+    P = problems.nnls_conic(12, 15, seed=1) if kind == "nnls" else problems.sdp_nearest_correlation(5, seed=4)
+    O = fo.OracleConic(P.c, P.A, P.b, P.constr_cones, P.var_cones, direct=True)
+    Q = _dense_Q(P)
+    l = Q.shape[0]
+    B = np.hstack([Q, -np.eye(l)])
+    rng = np.random.default_rng(0)
+    for _ in range(3):
+        z = rng.standard_normal(2 * l)
+        y = O.affine_prox(z)
+        ref = z - B.T @ np.linalg.solve(B @ B.T, B @ z)
+        assert np.abs(y - ref).max() < 1e-12 * max(1.0, np.abs(z).max())
+        assert np.abs(B @ y).max() < 1e-12 * np.abs(z).max() * l
+        assert np.abs(O.affine_prox(y) - y).max() < 1e-12
+
+
+def test_direct_and_indirect_solves_agree_and_gapp_default_works():
+    """test/testDRandGAPA.jl:37, test/testprint.jl:49: solvers constructed with direct=true (GAPP's default)
+    reach the same optimum as the CG-based S1 and as SciPy's NNLS."""
+    from scipy.optimize import nnls
+    P = problems.nnls_conic(20, 25, seed=3)
+    rng = np.random.default_rng(3)
+    D, d = rng.standard_normal((20, 25)), rng.standard_normal(20)
+    _, rn = nnls(D, d)
+    sols = []
+    for direct, alg in ((True, ("GAPP", 0.8, 1.8, 1.8, 0.0, 100)), (True, ("GAP", 0.5, 2.0, 2.0, 0.0, 100)),
+                        (False, ("GAP", 0.5, 2.0, 2.0, 0.0, 100))):
+        O = fo.OracleConic(P.c, P.A, P.b, P.constr_cones, P.var_cones, direct=direct)
+        O.set_algorithm(*alg)
+        O.set_iterate(O.initial_value())
+        r = O.solve(max_iters=20000, checki=100, eps=1e-7)
+        assert r["status"] == "Optimal", (direct, alg[0])
+        x, y, s = O.populate_solution(r["guess"])
+        assert abs(x[0] - rn) < 1e-4 * max(rn, 1.0)
+        sols.append(x)
+    assert np.abs(sols[1] - sols[2]).max() < 1e-4
+
+
+def test_linesearch_wrapper_feasibility():
+    """test/testfeasibility.jl:33-42 and test/linesearch.jl: LineSearchWrapper(GAP(eps=1e-8)) -> :Optimal,
+    x >= 0, A x = b; on non-search iterations the wrapper is the inner algorithm."""
+    A, b, cones = problems.feasibility_problem(50, 100, seed=2)
+    O = fo.OracleFeasibility(A, b, np.zeros(100), 1, cones)
+    O.set_algorithm("GAP", 0.8, 1.8, 1.8, 0.0, 100)
+    O.set_linesearch(100)
+    O.set_iterate(O.initial_value())
+    r = O.solve(max_iters=10000, checki=100, eps=1e-8)
+    assert r["status"] == "Optimal"
+    x = r["guess"][:100]
+    assert x.min() > -1e-12 and np.abs(A @ x - b).max() < 1e-6
+    # lsinterval larger than the run: identical to the plain algorithm
+    O1 = fo.OracleFeasibility(A, b, np.zeros(100), 1, cones)
+    O2 = fo.OracleFeasibility(A, b, np.zeros(100), 1, cones)
+    for O_, ls in ((O1, 0), (O2, 10 ** 6)):
+        O_.set_algorithm("GAP", 0.8, 1.8, 1.8, 0.0, 100)
+        O_.set_linesearch(ls)
+        O_.set_iterate(O_.initial_value())
+        O_.run(1, 50, checki=100, eps=1e-8)
+    np.testing.assert_array_equal(O1.get_state("x"), O2.get_state("x"))
+
+
+def test_rotated_soc_is_a_rotation_of_the_soc():
+    """IndRotatedSOC (cones.jl:10; parity unpinned, published algorithm): equals R' P_SOC(R x) for the pi/4
+    rotation R of the first two entries; the result satisfies 2 y1 y2 >= ||w||^2, y1, y2 >= 0."""
+    rng = np.random.default_rng(0)
+    c = np.sqrt(0.5)
+    for _ in range(300):
+        n = int(rng.integers(2, 9))
+        x = rng.standard_normal(n) * rng.choice([0.1, 1, 10])
+        y = fo.prox_cone("SOCRotated", x)
+        R = np.eye(n)
+        R[:2, :2] = [[c, c], [c, -c]]
+        ref = R.T @ fo.prox_cone("SOC", R @ x)
+        assert np.abs(y - ref).max() < 1e-13 * max(1.0, np.abs(x).max())
+        assert y[0] >= -1e-12 and y[1] >= -1e-12
+        assert 2 * y[0] * y[1] - np.sum(y[2:] ** 2) >= -1e-9 * max(1.0, np.abs(x).max()) ** 2
+        yd = fo.prox_cone("SOCRotated", x, dual=True)                      # Moreau (cones.jl:80-85)
+        assert np.abs(yd - (x + fo.prox_cone("SOCRotated", -x))).max() < 1e-15 * max(1.0, np.abs(x).max())
+
+
+def test_exponential_cone_projection_properties():
+    """IndExpPrimal / IndExpDual (cones.jl:12-13; parity unpinned, SCS's published projection restated):
+    the result is in the cone, the map is idempotent to the algorithm's 1e-8 bisection accuracy, P_K(x) and
+    P_K*(-x) are orthogonal and decompose x, and points already inside / in the polar cone are fixed / sent to 0."""
+    rng = np.random.default_rng(0)
+
+    def in_cone(v, tol):
+        r, s, t = v
+        return (s > 0 and s * np.exp(r / s) <= t + tol) or (r <= tol and abs(s) <= tol and t >= -tol)
+
+    for _ in range(500):
+        v = rng.standard_normal(3) * rng.choice([0.3, 1, 5])
+        sc = max(1.0, np.abs(v).max())
+        y = fo.prox_cone("ExpPrimal", v)
+        assert in_cone(y, 1e-4 * sc)
+        assert np.abs(fo.prox_cone("ExpPrimal", y) - y).max() < 1e-5 * sc
+        pd = fo.prox_cone("ExpDual", -v)
+        assert np.abs(y - pd - v).max() < 1e-12 * sc
+        assert abs(np.dot(y, pd)) < 1e-5 * sc * sc
+    np.testing.assert_array_equal(fo.prox_cone("ExpPrimal", np.array([0.0, 1.0, 2.0])), [0.0, 1.0, 2.0])   # inside
+    np.testing.assert_array_equal(fo.prox_cone("ExpPrimal", np.array([-1.0, -1.0, 3.0])), [-1.0, 0.0, 3.0])  # r, s < 0
+    np.testing.assert_array_equal(fo.prox_cone("ExpPrimal", np.array([1.0, -1.0, -5.0])), [0.0, 0.0, 0.0])   # polar
+    with pytest.raises(NotImplementedError):
+        fo.prox_cone("ExpPrimal", np.ones(4))
+
+
+def test_feasibility_with_box():
+    """test/testfeasibility.jl:9-19: S2 = IndBox(0, Inf) -- here through the oracle's box override."""
+    A, b, _ = problems.feasibility_problem(30, 60, seed=4)
+    O = fo.OracleFeasibility(A, b, np.zeros(60), 1, [("Free", 60), ("Zero", 30)])
+    O.set_box(0, 60, 0.0, np.inf)
+    O.set_algorithm("GAP", 0.5, 2.0, 2.0, 0.0, 100)
+    O.set_iterate(O.initial_value())
+    r = O.solve(max_iters=5000, checki=10, eps=1e-8)
+    assert r["status"] == "Optimal"
+    x = r["guess"][:60]
+    assert x.min() > -1e-12 and np.abs(A @ x - b).max() < 1e-6
