@@ -941,6 +941,7 @@ int32_t fos_time_psd(fos_handle_t hh, int64_t d, int64_t ncones, const double *x
     std::vector<ConeSeg> segs;
     for (int64_t k = 0; k < ncones; k++) segs.push_back(ConeSeg{FOS_CONE_SDP, 0, k * seglen, plen});
     K.build(NP, segs);
+    K.psd_warm_enabled = false;  // time COLD projections: repeating the same input would otherwise start converged
     DevBuf<double> din, dout;
     din.alloc((size_t)NP);
     dout.alloc((size_t)NP);

@@ -318,7 +318,8 @@ int32_t fos_time_matvec(fos_handle_t h, int32_t nvec, int32_t reps, double *ms_p
  * doubles, host) onto the PSD cone (IndPSD(scaling=true), cones.jl:11) with CUDA events on the library's
  * stream; returns the average milliseconds per projection call (all cones in one launch), the number
  * of Jacobi sweeps of the last call (cone 0; 0 for the small-cone kernel) and, when y != NULL, the
- * projections.  Stand-alone: needs no loaded problem. */
+ * projections.  Cold start every time (no warm start from the previous call's eigenvectors).  Stand-alone:
+ * needs no loaded problem. */
 int32_t fos_time_psd(fos_handle_t h, int64_t d, int64_t ncones, const double *x, double *y, int32_t reps,
                      double *ms_per_call, int32_t *sweeps);
 

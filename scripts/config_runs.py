@@ -129,7 +129,7 @@ def run_c4(args):
     _, ms_psd2, sweeps = H.time_psd(np.stack([X, -X]), reps=3)
     line = {"config": "C4", "algorithm": "GAP(0.8,1.8,1.8)", "sdp_order": d, "m": P.m, "n": P.n, "iterations_timed": int(done),
             "ms_per_iteration": ms / max(done, 1), "iterations_per_s": done / (ms / 1e3),
-            "cg_iterations_per_step": cgs / max(done, 1), "psd_projection_2x_ms": ms_psd2, "jacobi_sweeps": sweeps,
+            "cg_iterations_per_step": cgs / max(done, 1), "cold_psd_projection_2x_ms": ms_psd2, "cold_jacobi_sweeps": sweeps,
             "status": int(st)}
     if args.cpu:
         from oracle import fos_oracle as fo
