@@ -184,6 +184,7 @@ def main():
     ap.add_argument("--seed", type=int, default=2)
     ap.add_argument("--matvec-impl", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tail-flags", type=int, default=-1, help="N > 1: hand-shake of the fused CG tail (0 block to block, 1 per rank)")
     ap.add_argument("--tail-blocks", type=int, default=0, help="blocks of the fused CG-tail kernel (0 = one per SM)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: fused peer-memory exchange kernel (default) or fold + ncclAllReduce")
@@ -252,6 +253,8 @@ def main():
     H.set_option("matvec_impl", args.matvec_impl)
     if args.tail_blocks:
         H.set_option("tail_blocks", args.tail_blocks)
+    if args.tail_flags >= 0:
+        H.set_option("tail_flags", args.tail_flags)
     if world > 1:
         cid = parallel.exchange_comm_id(rank, parallel.nccl_unique_id, dist)
         parallel.init_comm(H, rank, world, cid)

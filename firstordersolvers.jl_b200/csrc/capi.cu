@@ -94,6 +94,10 @@ int32_t fos_set_option(fos_handle_t hh, const char *key, double value)
         h.cg_batch = (int)value;
     } else if (k == "fuse_rhs") {
         h.fuse_rhs = value != 0;
+    } else if (k == "tail_flags") {
+        FOS_REQUIRE(value == 0 || value == 1, "tail_flags must be 0 (block to block) or 1 (per rank)");
+        h.A.p2p.tail_flag_mode = (int)value;
+        h.tail_flag_mode = (int)value;
     } else if (k == "tail_blocks") {
         FOS_REQUIRE(value >= 0 && value <= 2 * h.num_sms, "tail_blocks out of range");
         h.tail_blocks = (int)value;

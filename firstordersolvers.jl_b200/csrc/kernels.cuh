@@ -916,6 +916,7 @@ struct P2PView {
     unsigned int *epoch;     // local: exchanges completed so far
     unsigned int *tickets;   // local: [0] phase-1 ticket, [1] exit ticket
     unsigned int *error;     // local: set when a peer did not show up within P2P_TIMEOUT_CYCLES
+    int32_t tail_flag_mode;  // fused CG tail hand-shake: 0 = block to block, 1 = one flag per rank (last block publishes)
 };
 
 __device__ __forceinline__ double ld_sys_f64(const double *p)
@@ -1206,18 +1207,43 @@ k_cg_tail_hsde(Lay L, MVView V, P2PView X, const double *__restrict__ c, const d
         }
         // Block i of every rank owns the same entries, so the hand-shake is block to block: publish this
         // block's part of the slot to every peer, wait for the same block of every peer.
-        __syncthreads();
-        if (threadIdx.x == 0) __threadfence_system();  // cumulative: the whole block's slot writes
-        __syncthreads();
-        if (threadIdx.x < X.nranks) {
-            st_release_sys_u32(reinterpret_cast<unsigned int *>(X.peer[threadIdx.x] + X.bflags_off) +
-                                   (size_t)X.rank * P2P_MAX_BLOCKS + blockIdx.x,
-                               epoch);
-            const unsigned int *f = reinterpret_cast<const unsigned int *>(X.peer[X.rank] + X.bflags_off) +
-                                    (size_t)threadIdx.x * P2P_MAX_BLOCKS + blockIdx.x;
-            p2p_wait_flag(f, epoch, X.error);
+        if (X.tail_flag_mode == 0) {
+            __syncthreads();
+            if (threadIdx.x == 0) __threadfence_system();  // cumulative: the whole block's slot writes
+            __syncthreads();
+            if (threadIdx.x < X.nranks) {
+                st_release_sys_u32(reinterpret_cast<unsigned int *>(X.peer[threadIdx.x] + X.bflags_off) +
+                                       (size_t)X.rank * P2P_MAX_BLOCKS + blockIdx.x,
+                                   epoch);
+                const unsigned int *f = reinterpret_cast<const unsigned int *>(X.peer[X.rank] + X.bflags_off) +
+                                        (size_t)threadIdx.x * P2P_MAX_BLOCKS + blockIdx.x;
+                p2p_wait_flag(f, epoch, X.error);
+            }
+            __syncthreads();
+        } else {
+            // one flag per rank: the last block of this rank to finish its fold publishes for the whole rank
+            __shared__ bool s_last;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                __threadfence_system();
+                s_last = (atomicAdd(&X.tickets[0], 1u) == gridDim.x - 1);
+            }
+            __syncthreads();
+            if (s_last) {
+                if (threadIdx.x == 0) __threadfence_system();
+                __syncthreads();
+                if (threadIdx.x < X.nranks)
+                    st_release_sys_u32(reinterpret_cast<unsigned int *>(X.peer[threadIdx.x] + X.flags_off) +
+                                           (size_t)X.rank * P2P_FLAG_STRIDE,
+                                       epoch);
+            }
+            if (threadIdx.x < X.nranks) {
+                const unsigned int *f = reinterpret_cast<const unsigned int *>(X.peer[X.rank] + X.flags_off) +
+                                        (size_t)threadIdx.x * P2P_FLAG_STRIDE;
+                p2p_wait_flag(f, epoch, X.error);
+            }
+            __syncthreads();
         }
-        __syncthreads();
     }
     // ---- Ap = [I Q'; Q -I] p and the dot products (k2_kkt_hsde<K2_AP>) ----
     const double tau1 = p[ot], tau2 = p[LP + ot];
@@ -1358,7 +1384,10 @@ k_cg_tail_hsde(Lay L, MVView V, P2PView X, const double *__restrict__ c, const d
         if (atomicAdd(gb.exit_ticket, 1u) == gridDim.x - 1) {
             *gb.exit_ticket = 0u;
             *gb.base = base + nbar * gridDim.x;
-            if (P2P) *X.epoch = epoch;
+            if (P2P) {
+                X.tickets[0] = 0u;
+                *X.epoch = epoch;
+            }
             __threadfence();
         }
     }

@@ -187,7 +187,9 @@ void MatOp::p2p_export(uint8_t *handle_out)
 void MatOp::p2p_import(const uint8_t *handles)
 {
     FOS_REQUIRE(p2p_region.p != nullptr, "fos_comm_p2p_export must precede fos_comm_p2p_import");
+    const int keep_mode = p2p.tail_flag_mode;
     memset(&p2p, 0, sizeof(p2p));
+    p2p.tail_flag_mode = keep_mode;
     p2p.nranks = nranks;
     p2p.rank = rank;
     p2p.flags_off = p2p_flags_off();

@@ -450,8 +450,11 @@ void Handle::cg_enqueue_iteration()
         const bool p2p = A.nranks > 1 && A.p2p_on;
         MVView V = kkt_pass(p.p, skip, /*defer_exchange=*/p2p);
         // identical on every rank (block i of all ranks owns the same entries); co-resident by construction
+        // single GPU: one block per SM (more blocks do not shorten the latency chain).  Peer exchange: up to two
+        // per SM, so that a thread gathers ONE entry (one NVLink round trip) rather than two in sequence
+        const int64_t auto_blocks = p2p ? 2 * (int64_t)num_sms : (int64_t)num_sms;
         const int grid = (int)std::min<int64_t>((L.LP + VBLOCK - 1) / VBLOCK,
-                                                std::min<int64_t>(tail_blocks > 0 ? tail_blocks : (int64_t)num_sms, P2P_MAX_BLOCKS));
+                                                std::min<int64_t>(tail_blocks > 0 ? tail_blocks : auto_blocks, P2P_MAX_BLOCKS));
         const double *cptr = d_c.p, *bptr = d_b.p;
         double *solp = sol.p, *rp = r.p, *pp = p.p, *App = Ap.p;
         Ctrl *cp = d_ctrl.p;

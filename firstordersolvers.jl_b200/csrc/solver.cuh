@@ -237,7 +237,7 @@ struct Handle {
     int num_sms = 148;
     std::string err;
     // options
-    int matvec_impl = 0, grid_ctas = 0, cg_batch = 0, fuse_rhs = 1, batch_ctas = 0, fuse_tail = 1, batch_hybrid = 1, tail_blocks = 0;
+    int matvec_impl = 0, grid_ctas = 0, cg_batch = 0, fuse_rhs = 1, batch_ctas = 0, fuse_tail = 1, batch_hybrid = 1, tail_blocks = 0, tail_flag_mode = 0;
     // problem
     bool loaded = false;
     Lay L{};
