@@ -46,7 +46,7 @@ enum {
     CONE_EXPDUAL = 8    /* IndExpDual */
 };
 
-/* algorithm codes (solvers/*.jl) */
+/* algorithm codes (solvers/{gap,gapa,fista,dykstra,gapproj}.jl) */
 enum { ALG_GAP = 0, ALG_GAPA = 1, ALG_FISTA = 2, ALG_DYKSTRA = 3, ALG_GAPP = 4 };
 
 /* status codes (HSDEStatus.jl:53-63) */
@@ -533,7 +533,7 @@ static int prox_cone_dual(double *y, int type, const double *x, int64_t len)
     case CONE_NONNEG: return prox_cone(y, CONE_NONNEG, x, len); /* :101 */
     case CONE_NONPOS: return prox_cone(y, CONE_NONPOS, x, len); /* :102 */
     default: {
-        double *neg = (double *)malloc(sizeof(double) * (size_t)(len > 0 ? len : 1));
+        double *neg = (double *)calloc((size_t)(len > 0 ? len : 1), sizeof(double));
         for (int64_t i = 0; i < len; i++) neg[i] = -x[i];
         int rc = prox_cone(y, type, neg, len);                /* :81 */
         for (int64_t i = 0; i < len; i++) y[i] = x[i] + y[i]; /* :82-84 */
@@ -839,7 +839,7 @@ static void direct_prox(model_t *M, double *y, const double *x)
 {
     const linop_t *Q = &M->S1->op;
     int64_t l = Q->an;
-    double *w = (double *)malloc(sizeof(double) * (size_t)l), *t = (double *)malloc(sizeof(double) * (size_t)l);
+    double *w = (double *)calloc((size_t)l, sizeof(double)), *t = (double *)calloc((size_t)l, sizeof(double));
     linop_mul(w, Q, x);
     for (int64_t i = 0; i < l; i++) w[i] -= x[l + i];
     const double *L = M->chol;
