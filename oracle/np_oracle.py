@@ -213,6 +213,22 @@ class AffinePlusLinear:
         return y
 
 
+class IndAffineDirect:
+    """direct = true (HSDE.jl:10-15): S1 = IndAffine([Q -I], 0), exact projection z - B'(B B')^-1 B z through a
+    dense LAPACK solve (independent of the C oracle's hand-written Cholesky)."""
+
+    def __init__(self, op):
+        self.op = op
+        l = op.an
+        Qd = np.column_stack([op.mul(e) for e in np.eye(l)])
+        self.B = np.hstack([Qd, -np.eye(l)])
+        self.G = self.B @ self.B.T
+        self.i, self.cgiter, self.xinit = 1, 0, None
+
+    def prox(self, x):
+        return x - self.B.T @ np.linalg.solve(self.G, self.B @ x)
+
+
 # ---------------------------------------------------------------------------------------
 # models + algorithms
 # ---------------------------------------------------------------------------------------
@@ -232,13 +248,18 @@ class NPModel:
         self.prev = np.full(N, np.nan)
         self.hist = []
         self.i = 0
+        self.lsinterval = 0  # LineSearchWrapper (wrappers/linesearch.jl); 0 = no wrapper
+        self.alphabest = None
 
     @classmethod
-    def conic(cls, c, A, b, constr_cones, var_cones):
+    def conic(cls, c, A, b, constr_cones, var_cones, direct=False):
         A = sp.csc_matrix(A)
         m, n = A.shape
         Q = HSDEQ(A, np.asarray(b, float), np.asarray(c, float))
-        S1 = AffinePlusLinear(Q, None, None, 1, decreasing_accuracy=True)  # HSDE.jl:22
+        if direct:
+            S1 = IndAffineDirect(Q)  # HSDE.jl:10-15
+        else:
+            S1 = AffinePlusLinear(Q, None, None, 1, decreasing_accuracy=True)  # HSDE.jl:22
         M = cls(0, S1, 2 * (m + n + 1), constr_cones, var_cones, A, np.asarray(b, float), np.asarray(c, float))
         M.m, M.n = m, n
         M.x[m + n] = 1.0
@@ -310,9 +331,39 @@ class NPModel:
                               cgiter=self.S1.cgiter, status=st))
         self.status, self.checked = st, True
 
+    def _ls_step(self, a1, a2):
+        """step(::LineSearchWrapper, ...) on a line-search iteration (wrappers/linesearch.jl:42-72)."""
+        def S1(v):
+            return a1 * self.P1(v) + (1 - a1) * v
+
+        x0 = self.x.copy()
+        t2 = S1(x0)
+        y = self.P2(t2)
+        self.check(y)
+        xn = a2 * y + (1 - a2) * t2
+        res = xn - x0
+        best, abest, al = math.inf, 1.0, 0.1
+        for _ in range(31):
+            al = al * 1.8
+            xt = x0 + al * res
+            t2 = S1(xt)
+            t3 = self.P2(t2)
+            t3 = a2 * t3 + (1 - a2) * t2
+            d = xt - t3
+            testres = math.sqrt(float(d @ d))
+            if testres < best:
+                best, abest = testres, al
+        self.alphabest = abest
+        self.x = x0 + abest * res
+
     def step(self):
         name, a, a1, a2, bt, iproj = self.alg
         x = self.x
+        if name in ("GAP", "GAPA") and self.lsinterval > 0 and self.i % self.lsinterval == 0:
+            if name == "GAPA":
+                a1 = a2 = self.alpha12
+            self._ls_step(a1, a2)
+            return
         if name in ("GAP", "GAPA"):
             if name == "GAPA":
                 a1 = a2 = self.alpha12

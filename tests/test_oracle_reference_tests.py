@@ -382,3 +382,44 @@ def test_feasibility_with_box():
     assert r["status"] == "Optimal"
     x = r["guess"][:60]
     assert x.min() > -1e-12 and np.abs(A @ x - b).max() < 1e-6
+
+
+def test_c_and_numpy_oracles_agree_on_direct_and_linesearch():
+    """Two independent restatements (C: hand-written Cholesky / loops; NumPy: LAPACK solve / vector ops) of the
+    8f rows agree: direct = true trajectories to 1e-9 (no truncated CG in the way), LineSearchWrapper picks the
+    same step lengths and stays within the CPU pair's usual drift."""
+    P = problems.nnls_conic(12, 15, seed=2)
+    O = fo.OracleConic(P.c, P.A, P.b, P.constr_cones, P.var_cones, direct=True)
+    M = npo.NPModel.conic(P.c, P.A, P.b, P.constr_cones, P.var_cones, direct=True)
+    for name, args in (("GAP", ("GAP", 0.5, 2.0, 2.0, 0.0, 100)), ("GAPA", ("GAPA", 1.0, 0.0, 0.0, 0.0, 100)),
+                       ("Dykstra", ("Dykstra", 0.0, 0.0, 0.0, 0.0, 100))):
+        O.set_algorithm(*args)
+        M.set_algorithm(*args)
+        O.set_iterate(O.initial_value())
+        M.x = O.initial_value().copy()
+        ro = O.solve(max_iters=60, checki=20, eps=1e-12)
+        rm = M.solve(max_iters=60, checki=20, eps=1e-12)
+        assert np.abs(ro["guess"] - rm["guess"]).max() < 1e-9 * np.abs(ro["guess"]).max(), name
+        np.testing.assert_allclose(ro["history"]["p"], [h["p"] for h in rm["history"]], rtol=1e-7)
+    # LineSearchWrapper(GAP) with the CG-based S1, well-conditioned instance
+    P = problems.nnls_conic(12, 15, seed=2, scale=0.05)
+    O = fo.OracleConic(P.c, P.A, P.b, P.constr_cones, P.var_cones)
+    M = npo.NPModel.conic(P.c, P.A, P.b, P.constr_cones, P.var_cones)
+    args = ("GAP", 0.8, 1.8, 1.8, 0.0, 100)
+    O.set_algorithm(*args)
+    O.set_linesearch(5)
+    M.set_algorithm(*args)
+    M.lsinterval = 5
+    O.set_iterate(O.initial_value())
+    M.x = O.initial_value().copy()
+    M.checki, M.eps = 100, 1e-12
+    for i in range(1, 16):
+        O.run(i, 1, checki=100, eps=1e-12)
+        M.i = i
+        M.step()
+        assert np.abs(M.x - O.get_state("x")).max() < 1e-6 * max(1.0, np.abs(M.x).max()), i
+        assert O.s1_calls == M.S1.i
+    assert fo.lib().fosor_get_alpha12 is not None
+    fo.lib().fosor_get_alphabest.restype = __import__("ctypes").c_double
+    fo.lib().fosor_get_alphabest.argtypes = [__import__("ctypes").c_void_p]
+    assert fo.lib().fosor_get_alphabest(O._h) == M.alphabest
