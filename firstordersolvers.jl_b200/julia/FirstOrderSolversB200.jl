@@ -34,6 +34,9 @@ algparams(a::GAPA)    = (Int32(1), a.α, 0.0, 0.0, a.β, Int64(100))
 algparams(a::FISTA)   = (Int32(2), a.α, 0.0, 0.0, 0.0, Int64(100))
 algparams(a::Dykstra) = (Int32(3), 0.0, 0.0, 0.0, 0.0, Int64(100))
 algparams(a::GAPP)    = (Int32(4), a.α, a.α1, a.α2, 0.0, Int64(a.iproj))
+algparams(a::LineSearchWrapper) = algparams(a.alg)          # wrappers/linesearch.jl:3-7: the inner algorithm's step
+inneralg(a::FOSAlgorithm) = a
+inneralg(a::LineSearchWrapper) = a.alg
 
 conearrays(K::ConeProduct, names) =
     (Int32[CONE_CODE[s] for s in names], Int64[length(r) for r in K.ranges])
@@ -54,15 +57,18 @@ function init_algorithm_b200!(alg::FOSAlgorithm, model::FOSMathProgModel, constr
         h, m, n, A.colptr, A.rowval, A.nzval, 1, model.b, model.c,
         length(t1), t1, l1, length(t2), t2, l2, Int32(0)))
     # HSDE(model, direct=alg.direct) (FOSSolverInterface.jl:77, HSDE.jl:10-15): exact projection on the device
-    alg.direct && fos_check(h, ccall((:fos_set_direct, libfos), Int32, (Ptr{Cvoid}, Int32), h, Int32(1)))
+    inneralg(alg).direct && fos_check(h, ccall((:fos_set_direct, libfos), Int32, (Ptr{Cvoid}, Int32), h, Int32(1)))
     code, a, a1, a2, b, ip = algparams(alg)
     fos_check(h, ccall((:fos_set_algorithm, libfos), Int32,
         (Ptr{Cvoid}, Int32, Float64, Float64, Float64, Float64, Int64), h, code, a, a1, a2, b, ip))
+    # LineSearchWrapper(alg; lsinterval) (wrappers/linesearch.jl:19-33): GAP / GAPA only (support_linesearch)
+    alg isa LineSearchWrapper && fos_check(h, ccall((:fos_set_linesearch, libfos), Int32, (Ptr{Cvoid}, Int64),
+                                                    h, Int64(alg.lsinterval)))
     data = B200Data(h, 0)
     finalizer(d -> ccall((:fos_destroy, libfos), Int32, (Ptr{Cvoid},), d.handle), data)
     m2, n2 = size(model.A)
     status_generator = (mo, checki, eps, verbose, debug) ->
-        HSDEStatus(m2, n2, 0, mo, :Continue, checki, eps, verbose, false, alg.direct, time_ns(), model.init_duration, debug)
+        HSDEStatus(m2, n2, 0, mo, :Continue, checki, eps, verbose, false, inneralg(alg).direct, time_ns(), model.init_duration, debug)
     return data, status_generator
 end
 
