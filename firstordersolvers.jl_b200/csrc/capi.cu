@@ -115,6 +115,9 @@ int32_t fos_set_option(fos_handle_t hh, const char *key, double value)
     } else if (k == "batch_hybrid") {
         FOS_REQUIRE(!(h.batch && h.batch->loaded), "batch_hybrid must be set before loading the batch");
         h.batch_hybrid = value != 0;
+    } else if (k == "hybrid_rows") {
+        FOS_REQUIRE(!h.loaded, "hybrid_rows must be set before loading the problem");
+        h.hybrid_rows = value != 0;
     } else if (k == "batch_ctas") {
         h.batch_ctas = (int)value;
         if (h.batch) h.batch->grid_ctas = (int)value;
@@ -211,7 +214,10 @@ static void load_matrix_csc(Handle &h, int64_t m, int64_t n, const int64_t *colp
                 FOS_REQUIRE(i >= 0 && i < m, "row index out of range in CSC input");
                 D[(size_t)i * (size_t)n + (size_t)j] += nzval[k];
             }
-        h.A.init_dense(m, n, D.data(), n, FOS_MEM_HOST, 0, m, h.grid_ctas, h.stream);
+        if (h.hybrid_rows)
+            h.A.init_hybrid(m, n, D.data(), n, FOS_MEM_HOST, h.grid_ctas, h.stream);
+        else
+            h.A.init_dense(m, n, D.data(), n, FOS_MEM_HOST, 0, m, h.grid_ctas, h.stream);
     } else {
         h.A.init_sparse(m, n, colptr, rowval, nzval, base, h.stream);
     }
@@ -246,7 +252,10 @@ int32_t fos_load_conic_dense(fos_handle_t hh, int64_t m, int64_t n, const double
     // non-blocking stream, so wait for everything the caller has enqueued before reading it
     if (a_location == FOS_MEM_DEVICE) FOS_CUDA(cudaDeviceSynchronize());
     h.A.impl = h.matvec_impl;
-    h.A.init_dense(m, n, A, lda, a_location, row_begin, row_count, h.grid_ctas, h.stream);
+    if (h.hybrid_rows && h.nranks == 1 && row_begin == 0 && row_count == m)
+        h.A.init_hybrid(m, n, A, lda, a_location, h.grid_ctas, h.stream);
+    else
+        h.A.init_dense(m, n, A, lda, a_location, row_begin, row_count, h.grid_ctas, h.stream);
     h.load_conic(m, n, b, c, ncones1, cone_type1, cone_len1, ncones2, cone_type2, cone_len2);
     h.begin_solve();
     FOS_API_END(hh)
@@ -443,6 +452,9 @@ int32_t fos_get_info(fos_handle_t hh, int32_t which, double *out)
     case 15: *out = (double)h.num_sms; break;
     case 16: *out = h.A.prof_ms[0]; break;
     case 17: *out = (double)h.A.prof_n[0]; break;
+    case 18: *out = (double)h.A.kind; break;
+    case 19: *out = h.A.kind == 3 ? (double)h.A.m_local : 0.0; break;
+    case 20: *out = h.A.kind == 3 ? (double)h.A.hyb_sparse_rows : 0.0; break;
     default: throw Error(FOS_ERR_INVALID, "unknown info selector");
     }
     FOS_API_END(hh)

@@ -146,6 +146,165 @@ void MatOp::init_sparse(int64_t m_, int64_t n_, const int64_t *colptr, const int
     d_one_band.upload(std::vector<int32_t>{0, 1});
 }
 
+// ---------------------------------------------------------------------------------------
+// hybrid row storage: dense row block + CSR/CSC remainder (single problem, single rank)
+// ---------------------------------------------------------------------------------------
+namespace {
+
+// non-zeros per row: one warp per row
+__global__ void __launch_bounds__(256) k_rows_nnz(const double *__restrict__ A, int64_t lda, int64_t m, int64_t n,
+                                                  int32_t *__restrict__ nnz)
+{
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= m) return;
+    const int lane = threadIdx.x & 31;
+    const double *r = A + (size_t)row * lda;
+    int c = 0;
+    for (int64_t j = lane; j < n; j += 32) c += r[j] != 0.0 ? 1 : 0;
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) nnz[row] = c;
+}
+
+// CSR of the listed rows: one warp per row, non-zeros compacted in column order (ballot prefix)
+__global__ void __launch_bounds__(32) k_rows_extract(const double *__restrict__ A, int64_t lda, int64_t n,
+                                                     const int32_t *__restrict__ row_id, const int32_t *__restrict__ row_ptr,
+                                                     int32_t *__restrict__ col, double *__restrict__ val)
+{
+    const int sr = blockIdx.x;
+    const int32_t p0 = row_ptr[sr];
+    const int lane = threadIdx.x;
+    const double *r = A + (size_t)row_id[sr] * lda;
+    int32_t pos = p0;
+    for (int64_t j0 = 0; j0 < n; j0 += 32) {
+        const int64_t j = j0 + lane;
+        const double v = j < n ? r[j] : 0.0;
+        const unsigned int msk = __ballot_sync(0xffffffffu, v != 0.0);
+        if (v != 0.0) {
+            const int32_t q = pos + __popc(msk & ((1u << lane) - 1u));
+            col[q] = (int32_t)j;
+            val[q] = v;
+        }
+        pos += __popc(msk);
+    }
+}
+
+// complete results of a hybrid pass: xbuf = [A' W (NV x n_pad) | A X (NV x m_pad)]
+//   A' W = fold of the dense block's column partials + the CSC part;  A X = fold of the dense block's row
+//   partials inside the block, the CSR part outside
+template <int NV>
+__global__ void __launch_bounds__(VBLOCK)
+k_hybrid_combine(MVView V, int64_t n, int64_t n_pad, int64_t m_local, int64_t row_begin, int64_t m_pad,
+                 const double *__restrict__ sp_ax, const double *__restrict__ sp_atw, double *__restrict__ xbuf,
+                 const int32_t *skip_flag)
+{
+    if (skip_flag != nullptr && *skip_flag != 0) return;
+    const int64_t total = n_pad + m_pad;
+    for (int64_t e = (int64_t)blockIdx.x * VBLOCK + threadIdx.x; e < total; e += (int64_t)gridDim.x * VBLOCK) {
+#pragma unroll
+        for (int v = 0; v < NV; v++) {
+            if (e < n_pad) {
+                xbuf[(size_t)v * n_pad + e] = e < n ? add_(mv_atw(V, v, e), sp_atw[(size_t)v * n_pad + e]) : 0.0;
+            } else {
+                const int64_t row = e - n_pad, lr = row - row_begin;
+                xbuf[(size_t)NV * n_pad + (size_t)v * m_pad + row] =
+                    (lr >= 0 && lr < m_local) ? mv_ax(V, v, lr) : sp_ax[(size_t)v * m_pad + row];
+            }
+        }
+    }
+}
+
+}  // namespace
+
+void MatOp::init_hybrid(int64_t m_, int64_t n_, const double *Asrc, int64_t lda_src, int location, int grid_ctas,
+                        cudaStream_t st)
+{
+    FOS_REQUIRE(nranks == 1, "hybrid row storage is not offered with row sharding");
+    init_dense(m_, n_, Asrc, lda_src, location, 0, m_, grid_ctas, st);  // A / lda: the whole matrix on the device
+    hyb_sparse_rows = 0;
+    if (impl != 0 || m < 2 * PAD) return;
+    // 1. classify the rows
+    DevBuf<int32_t> d_nnz;
+    d_nnz.alloc((size_t)m);
+    k_rows_nnz<<<(unsigned)((m + 7) / 8), 256, 0, st>>>(A, lda, m, n, d_nnz.p);
+    FOS_CUDA(cudaStreamSynchronize(st));
+    std::vector<int32_t> rn((size_t)m);
+    FOS_CUDA(cudaMemcpy(rn.data(), d_nnz.p, rn.size() * 4, cudaMemcpyDeviceToHost));
+    const int64_t thr = std::max<int64_t>(1, n / 8);  // rows with <= thr non-zeros may leave the dense block
+    int64_t first = -1, last = -1;
+    for (int64_t i = 0; i < m; i++)
+        if (rn[(size_t)i] > thr) {
+            if (first < 0) first = i;
+            last = i;
+        }
+    if (first < 0) return;  // nothing dense: the caller should have chosen sparse storage
+    const int64_t r0 = (first / PAD) * PAD, r1 = last + 1, md = r1 - r0;
+    std::vector<int32_t> row_id, row_ptr(1, 0);
+    int64_t nz = 0;
+    for (int64_t i = 0; i < m; i++) {
+        if ((i >= r0 && i < r1) || rn[(size_t)i] == 0) continue;
+        row_id.push_back((int32_t)i);
+        nz += rn[(size_t)i];
+        FOS_REQUIRE(nz < (int64_t)2147483647, "sparse remainder out of int32 range");
+        row_ptr.push_back((int32_t)nz);
+    }
+    const double dense_bytes = 8.0 * (double)m * (double)n;
+    const double hybrid_bytes = 8.0 * (double)md * (double)n + 24.0 * (double)nz;
+    if (hybrid_bytes > 0.98 * dense_bytes) return;  // not worth three more launches per pass
+    // 2. CSR of the remainder on the device, CSC on the host (nz entries)
+    const int64_t NS = (int64_t)row_id.size();
+    std::vector<int32_t> h_col((size_t)nz);
+    std::vector<double> h_val((size_t)nz);
+    if (nz > 0) {
+        DevBuf<int32_t> d_id, d_ptr, d_col;
+        DevBuf<double> d_val;
+        d_id.upload(row_id);
+        d_ptr.upload(row_ptr);
+        d_col.alloc((size_t)nz, false);
+        d_val.alloc((size_t)nz, false);
+        k_rows_extract<<<(unsigned)NS, 32, 0, st>>>(A, lda, n, d_id.p, d_ptr.p, d_col.p, d_val.p);
+        FOS_CUDA(cudaStreamSynchronize(st));
+        FOS_CUDA(cudaMemcpy(h_col.data(), d_col.p, h_col.size() * 4, cudaMemcpyDeviceToHost));
+        FOS_CUDA(cudaMemcpy(h_val.data(), d_val.p, h_val.size() * 8, cudaMemcpyDeviceToHost));
+    }
+    // full-size pointer arrays (rows of the dense block and empty rows have no entries): spmv_rows indexes by row
+    std::vector<int32_t> rptr((size_t)m + 1, 0), cptr((size_t)n + 1, 0);
+    for (int64_t s = 0; s < NS; s++) rptr[(size_t)row_id[(size_t)s] + 1] = row_ptr[(size_t)s + 1] - row_ptr[(size_t)s];
+    for (int64_t i = 0; i < m; i++) rptr[(size_t)i + 1] += rptr[(size_t)i];
+    for (int64_t q = 0; q < nz; q++) cptr[(size_t)h_col[(size_t)q] + 1]++;
+    for (int64_t j = 0; j < n; j++) cptr[(size_t)j + 1] += cptr[(size_t)j];
+    std::vector<int32_t> fill(cptr.begin(), cptr.end() - 1), cidx((size_t)nz);
+    std::vector<double> cval((size_t)nz);
+    for (int64_t s = 0; s < NS; s++)  // rows in increasing order: every column's entries end up sorted by row
+        for (int32_t q = row_ptr[(size_t)s]; q < row_ptr[(size_t)s + 1]; q++) {
+            const int32_t pos = fill[(size_t)h_col[(size_t)q]]++;
+            cidx[(size_t)pos] = row_id[(size_t)s];
+            cval[(size_t)pos] = h_val[(size_t)q];
+        }
+    csr_ptr.upload(rptr);
+    csr_idx.upload(h_col);  // the compacted rows are stored in row order: same layout as a CSR over all m rows
+    csr_val.upload(h_val);
+    csc_ptr.upload(cptr);
+    csc_idx.upload(cidx);
+    csc_val.upload(cval);
+    nnz = nz;
+    hyb_sparse_rows = NS;
+    // 3. K1 works on the dense block only
+    row_begin = r0;
+    m_local = md;
+    m_pad_local = ru(md, PAD);
+    A = A + (size_t)r0 * lda;  // A_own (if any) keeps the ownership of the whole allocation
+    make_tmap(&tmap, A, md, n, lda);
+    const int G = grid_ctas > 0 ? grid_ctas : num_sms;
+    plan = k1_make_plan(md, n, G);
+    d_unit_begin.upload(plan.cta_unit_begin);
+    d_slot_base.upload(plan.band_slot_base);
+    d_first_cta.upload(plan.band_first_cta);
+    rowpart.alloc((size_t)plan.NB * 2 * m_pad_local);
+    colpart.alloc((size_t)std::max(plan.nslots, 1) * 2 * K1_BW);
+    xbuf.alloc((size_t)2 * (n_pad + m_pad));
+    kind = 3;
+}
+
 MatOp::~MatOp()
 {
     for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
@@ -285,6 +444,7 @@ void MatOp::prof_reset()
 double MatOp::bytes_per_pass() const
 {
     if (kind == 1) return 8.0 * (double)m_local * (double)n;
+    if (kind == 3) return 8.0 * (double)m_local * (double)n + 2.0 * 12.0 * (double)nnz;
     return 2.0 * 12.0 * (double)nnz;  // CSR pass + CSC pass, 8-byte value + 4-byte index
 }
 
@@ -318,7 +478,7 @@ MVView MatOp::run_t(const double *const *X, const double *const *W, const int32_
     a.n_pad = n_pad;
     a.m_pad_local = m_pad_local;
     MVView V;
-    if (kind == 1 && impl == 0) {
+    if ((kind == 1 && impl == 0) || kind == 3) {
         a.rowpart = rowpart.p;
         a.colpart = colpart.p;
         a.cta_unit_begin = d_unit_begin.p;
@@ -360,6 +520,22 @@ MVView MatOp::run_t(const double *const *X, const double *const *W, const int32_
         spmv_rows<NV><<<(unsigned)((n + wpb - 1) / wpb), 256, 0, st>>>(csc_ptr.p, csc_idx.p, csc_val.p, n, a, 1, n_pad);
         if (stats) stats->launches += 2;
         V = view_full(NV, full_ax.p, full_atw.p);
+    }
+    if (kind == 3) {
+        // the CSR / CSC remainder, then one fold that merges it with the dense block's partials
+        K1Args<NV> sa = a;
+        for (int v = 0; v < NV; v++) sa.W[v] = W[v];  // global rows
+        sa.rowpart = full_ax.p;
+        sa.colpart = full_atw.p;
+        const int wpb = 8;
+        spmv_rows<NV><<<(unsigned)((m + wpb - 1) / wpb), 256, 0, st>>>(csr_ptr.p, csr_idx.p, csr_val.p, m, sa, 0, m_pad);
+        spmv_rows<NV><<<(unsigned)((n + wpb - 1) / wpb), 256, 0, st>>>(csc_ptr.p, csc_idx.p, csc_val.p, n, sa, 1, n_pad);
+        const int64_t total = n_pad + m_pad;
+        const int grid = (int)std::min<int64_t>((total + VBLOCK - 1) / VBLOCK, 4 * (int64_t)num_sms);
+        k_hybrid_combine<NV><<<grid, VBLOCK, 0, st>>>(V, n, n_pad, m_local, row_begin, m_pad, full_ax.p, full_atw.p, xbuf.p,
+                                                      skip);
+        if (stats) stats->launches += 3;
+        V = view_full(NV, xbuf.p + (size_t)NV * n_pad, xbuf.p);
     }
     if (stats && skip == nullptr) stats->total_passes++;  // predicated CG launches are counted by cg_solve
     if (nranks > 1 && p2p_on && defer_exchange) {

@@ -84,7 +84,7 @@ NcclApi &nccl_api();  // loads on first use, throws FOS_ERR_COMM if unavailable
 // MatOp: the m x n matrix A on the device and its fused dual mat-vec
 // =======================================================================================
 struct MatOp {
-    int kind = 0;  // 0 none, 1 dense, 2 sparse
+    int kind = 0;  // 0 none, 1 dense, 2 sparse, 3 hybrid (a dense row block [row_begin, row_begin + m_local) + sparse rest)
     int64_t m = 0, n = 0, n_pad = 0, m_pad = 0;
     int64_t m_local = 0, row_begin = 0, m_pad_local = 0;
     // dense
@@ -138,6 +138,13 @@ struct MatOp {
                     int64_t row_count, int grid_ctas, cudaStream_t st);
     void init_sparse(int64_t m_, int64_t n_, const int64_t *colptr, const int64_t *rowval, const double *nzval,
                      int64_t base, cudaStream_t st);
+    // Hybrid row storage ("hybrid_rows"): like init_dense on the whole matrix, then the rows are classified on the
+    // device; the contiguous range that holds every row with more than n/8 non-zeros stays dense (K1 streams only
+    // that block), the other non-empty rows are kept as CSR + CSC.  Falls back to plain dense storage (kind 1) when
+    // that would not save at least 2 % of the bytes of a pass.  Single rank only.
+    void init_hybrid(int64_t m_, int64_t n_, const double *Asrc, int64_t lda_src, int location, int grid_ctas,
+                     cudaStream_t st);
+    int64_t hyb_sparse_rows = 0;  // rows kept as CSR / CSC (kind 3)
     double bytes_per_pass() const;
     // Runs one pass; X[v] have n_pad entries, W[v] have m_pad entries (global rows).
     // defer_exchange: with the peer-memory exchange enabled, return the LOCAL partial view and leave the
@@ -237,7 +244,7 @@ struct Handle {
     int num_sms = 148;
     std::string err;
     // options
-    int matvec_impl = 0, grid_ctas = 0, cg_batch = 0, fuse_rhs = 1, batch_ctas = 0, fuse_tail = 1, batch_hybrid = 1, tail_blocks = 0, tail_flag_mode = 0;
+    int matvec_impl = 0, grid_ctas = 0, cg_batch = 0, fuse_rhs = 1, batch_ctas = 0, fuse_tail = 1, batch_hybrid = 1, tail_blocks = 0, tail_flag_mode = 0, hybrid_rows = 0;
     // problem
     bool loaded = false;
     Lay L{};

@@ -107,6 +107,9 @@ const char *fos_last_error(fos_handle_t h);
  *                  of ~10); 0 = always start from the identity.  Set after loading.
  *   "exchange_impl" multi-GPU: 1 = fused peer-memory exchange (after fos_comm_p2p_import), 0 = NCCL
  *   "profile_matvec" 1 = CUDA events around every mat-vec launch (read back with fos_get_info)
+ *   "hybrid_rows"  1 = single-problem dense loads classify the rows on the device and keep only the contiguous block
+ *                  that holds every row with more than n/8 non-zeros as dense tiles; the other non-empty rows are
+ *                  stored as CSR + CSC (default 0 this round: opt-in; set before loading; single rank only)
  *   "batch_hybrid" 1 (default) = batch mode keeps rows with <= n/8 non-zeros out of the dense tiles (CSR + CSC) and
  *                  skips empty rows; 0 = every row is streamed as dense FP64.  Set before loading the batch.
  *   "batch_ctas"   persistent CTAs of the batch kernel (default = #SMs)
@@ -202,7 +205,9 @@ int32_t fos_set_state(fos_handle_t h, int32_t which, const double *buf, int64_t 
  * 7 kernel launches so far, 8 GAPP alpha_best of the last projected step; with the option
  * "profile_matvec" = 1: 9 / 10 summed milliseconds / count of 2-RHS mat-vec launches, 11 / 12 the
  * same for 1-RHS launches, 13 predicated no-op launches; 14 algorithmic bytes of one pass over A,
- * 15 number of SMs, 16 / 17 summed milliseconds / count of executed fused CG-tail launches. */
+ * 15 number of SMs, 16 / 17 summed milliseconds / count of executed fused CG-tail launches,
+ * 18 storage of A (1 dense, 2 sparse, 3 hybrid), 19 / 20 rows of the dense block / rows kept sparse
+ * under hybrid row storage (0 otherwise). */
 int32_t fos_get_info(fos_handle_t h, int32_t which, double *out);
 /* Restores a scalar: which = 0 (S1.i), 2 (alpha12) or 3 (FISTA t). */
 int32_t fos_set_info(fos_handle_t h, int32_t which, double value);

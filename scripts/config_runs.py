@@ -201,6 +201,8 @@ def run_c3(args):
     c[0] = 1.0
     cones1, cones2 = [("SOC", md + 1), ("SOC", nx + 1)], [("Free", n)]
     H = fos.Handle(local)
+    if getattr(args, "hybrid", False) and world == 1:
+        H.set_option("hybrid_rows", 1)   # dense block of the D rows through K1, the -I rows as CSR + CSC
     if world > 1:
         cid = parallel.exchange_comm_id(rank, parallel.nccl_unique_id, dist)
         parallel.init_comm(H, rank, world, cid)
@@ -230,7 +232,8 @@ def run_c3(args):
     gbs = passes * bytes_pass / (ms / 1e3) / 1e9
     if rank == 0:
         print(json.dumps({"config": "C3", "algorithm": "GAPA()", "n_gpus": world, "exchange": args.exchange if world > 1 else None,
-                          "m": m, "n": n, "matrix_gb": bytes_pass / 1e9,
+                          "m": m, "n": n, "matrix_gb": bytes_pass / 1e9, "storage_kind": int(H.info("storage_kind")),
+                          "bytes_streamed_per_pass_gb": H.info("bytes_per_pass") * (world if world > 1 else 1) / 1e9,
                           "iterations_timed": int(done), "ms_per_iteration": ms / max(done, 1),
                           "iterations_per_s": done / (ms / 1e3), "cg_iterations_per_step": cgs / max(done, 1),
                           "passes_over_A_per_step": passes / max(done, 1), "aggregate_gbs": gbs,
@@ -254,6 +257,7 @@ def main():
     ap.add_argument("--batch-ctas", type=int, default=0, help="c5: persistent CTAs of the batch kernel (0 = default)")
     ap.add_argument("--dense-batch", action="store_true", help="c5: stream every row as dense FP64 (batch_hybrid = 0)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"])
+    ap.add_argument("--hybrid", action="store_true", help="c3, one GPU: hybrid row storage (option hybrid_rows = 1)")
     args = ap.parse_args()
     {"c3": run_c3, "c4": run_c4, "c5": run_c5}[args.config](args)
 
