@@ -82,6 +82,7 @@ SIGNATURES = {
     "fos_get_stream": (C.c_int32, [_h, C.POINTER(C.c_uint64)]),
     "fos_k1_plan": (C.c_int32, [C.c_int64, C.c_int64, C.c_int32, _i32p, _i32p, C.c_int64, _i32p, _i32p, C.c_int64]),
     "fos_batch_plan": (C.c_int32, [C.c_int64, C.c_int64, _i64p]),
+    "fos_hybrid_plan": (C.c_int32, [C.c_int64, C.c_int64, _i32p, _i64p]),
     "fos_time_matvec": (C.c_int32, [_h, C.c_int32, C.c_int32, _dp, _dp]),
     "fos_time_psd": (C.c_int32, [_h, C.c_int64, C.c_int64, _dp, _dp, C.c_int32, _dp, _i32p]),
 }

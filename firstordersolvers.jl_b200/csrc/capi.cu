@@ -918,6 +918,24 @@ int32_t fos_batch_plan(int64_t m, int64_t n, int64_t *out)
     }
 }
 
+int32_t fos_hybrid_plan(int64_t m, int64_t n, const int32_t *row_nnz, int64_t *out)
+{
+    try {
+        FOS_REQUIRE(m > 0 && n > 0 && row_nnz && out, "bad arguments");
+        const HybridPlan hp = hybrid_row_plan(row_nnz, m, n);
+        out[0] = hp.use ? 1 : 0;
+        out[1] = hp.r0;
+        out[2] = hp.md;
+        out[3] = hp.sparse_rows;
+        out[4] = hp.sparse_nnz;
+        return FOS_OK;
+    } catch (const Error &e) {
+        return fail(nullptr, e.code, e.what());
+    } catch (const std::exception &e) {
+        return fail(nullptr, FOS_ERR_INVALID, e.what());
+    }
+}
+
 int32_t fos_time_matvec(fos_handle_t hh, int32_t nvec, int32_t reps, double *ms_per_launch, double *bytes_per_launch)
 {
     FOS_API_BEGIN(hh)

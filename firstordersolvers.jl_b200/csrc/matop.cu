@@ -215,6 +215,35 @@ k_hybrid_combine(MVView V, int64_t n, int64_t n_pad, int64_t m_local, int64_t ro
 
 }  // namespace
 
+// Host-only decision of the hybrid row storage (unit-tested on CPU through fos_hybrid_plan): the dense block is
+// [r0, r0 + md), r0 a multiple of 16 (the W slice K1 reads must stay 128-byte aligned), and holds every row with
+// more than n/8 non-zeros; rows outside it with at least one entry go to CSR + CSC.
+HybridPlan hybrid_row_plan(const int32_t *row_nnz, int64_t m, int64_t n)
+{
+    HybridPlan hp{};
+    if (m < 2 * PAD || n < 1) return hp;
+    const int64_t thr = std::max<int64_t>(1, n / 8);
+    int64_t first = -1, last = -1;
+    for (int64_t i = 0; i < m; i++)
+        if (row_nnz[i] > thr) {
+            if (first < 0) first = i;
+            last = i;
+        }
+    if (first < 0) return hp;  // nothing dense: the caller should have chosen sparse storage
+    hp.r0 = (first / PAD) * PAD;
+    hp.md = last + 1 - hp.r0;
+    for (int64_t i = 0; i < m; i++) {
+        if ((i >= hp.r0 && i < hp.r0 + hp.md) || row_nnz[i] == 0) continue;
+        hp.sparse_rows++;
+        hp.sparse_nnz += row_nnz[i];
+    }
+    if (hp.sparse_nnz >= (int64_t)2147483647) return hp;
+    const double dense_bytes = 8.0 * (double)m * (double)n;
+    const double hybrid_bytes = 8.0 * (double)hp.md * (double)n + 24.0 * (double)hp.sparse_nnz;
+    hp.use = hybrid_bytes <= 0.98 * dense_bytes;  // otherwise not worth three more launches per pass
+    return hp;
+}
+
 void MatOp::init_hybrid(int64_t m_, int64_t n_, const double *Asrc, int64_t lda_src, int location, int grid_ctas,
                         cudaStream_t st)
 {
@@ -229,27 +258,19 @@ void MatOp::init_hybrid(int64_t m_, int64_t n_, const double *Asrc, int64_t lda_
     FOS_CUDA(cudaStreamSynchronize(st));
     std::vector<int32_t> rn((size_t)m);
     FOS_CUDA(cudaMemcpy(rn.data(), d_nnz.p, rn.size() * 4, cudaMemcpyDeviceToHost));
-    const int64_t thr = std::max<int64_t>(1, n / 8);  // rows with <= thr non-zeros may leave the dense block
-    int64_t first = -1, last = -1;
-    for (int64_t i = 0; i < m; i++)
-        if (rn[(size_t)i] > thr) {
-            if (first < 0) first = i;
-            last = i;
-        }
-    if (first < 0) return;  // nothing dense: the caller should have chosen sparse storage
-    const int64_t r0 = (first / PAD) * PAD, r1 = last + 1, md = r1 - r0;
+    HybridPlan hp = hybrid_row_plan(rn.data(), m, n);
+    if (!hp.use) return;  // nothing to gain: the matrix stays dense (kind 1)
+    const int64_t r0 = hp.r0, r1 = hp.r0 + hp.md, md = hp.md, nz = hp.sparse_nnz;
     std::vector<int32_t> row_id, row_ptr(1, 0);
-    int64_t nz = 0;
-    for (int64_t i = 0; i < m; i++) {
-        if ((i >= r0 && i < r1) || rn[(size_t)i] == 0) continue;
-        row_id.push_back((int32_t)i);
-        nz += rn[(size_t)i];
-        FOS_REQUIRE(nz < (int64_t)2147483647, "sparse remainder out of int32 range");
-        row_ptr.push_back((int32_t)nz);
+    {
+        int64_t acc = 0;
+        for (int64_t i = 0; i < m; i++) {
+            if ((i >= r0 && i < r1) || rn[(size_t)i] == 0) continue;
+            row_id.push_back((int32_t)i);
+            acc += rn[(size_t)i];
+            row_ptr.push_back((int32_t)acc);
+        }
     }
-    const double dense_bytes = 8.0 * (double)m * (double)n;
-    const double hybrid_bytes = 8.0 * (double)md * (double)n + 24.0 * (double)nz;
-    if (hybrid_bytes > 0.98 * dense_bytes) return;  // not worth three more launches per pass
     // 2. CSR of the remainder on the device, CSC on the host (nz entries)
     const int64_t NS = (int64_t)row_id.size();
     std::vector<int32_t> h_col((size_t)nz);

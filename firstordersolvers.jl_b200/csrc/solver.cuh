@@ -83,6 +83,13 @@ NcclApi &nccl_api();  // loads on first use, throws FOS_ERR_COMM if unavailable
 // =======================================================================================
 // MatOp: the m x n matrix A on the device and its fused dual mat-vec
 // =======================================================================================
+struct HybridPlan {
+    bool use = false;
+    int64_t r0 = 0, md = 0;  // dense block = rows [r0, r0 + md)
+    int64_t sparse_rows = 0, sparse_nnz = 0;
+};
+HybridPlan hybrid_row_plan(const int32_t *row_nnz, int64_t m, int64_t n);  // host only
+
 struct MatOp {
     int kind = 0;  // 0 none, 1 dense, 2 sparse, 3 hybrid (a dense row block [row_begin, row_begin + m_local) + sparse rest)
     int64_t m = 0, n = 0, n_pad = 0, m_pad = 0;

@@ -309,6 +309,11 @@ int32_t fos_k1_plan(int64_t m_local, int64_t n, int32_t ctas, int32_t *dims_out,
  * SM, dynamic shared memory bytes, doubles of A per problem}.  FOS_ERR_UNSUPPORTED for shapes outside batch mode. */
 int32_t fos_batch_plan(int64_t m, int64_t n, int64_t *out /* 8 */);
 
+/* Host-only: the decision of the hybrid row storage ("hybrid_rows") from the non-zeros per row (needs no GPU;
+ * unit-tested on CPU).  out = {1 if the hybrid layout is used, first row of the dense block (a multiple of 16),
+ * rows of the dense block, rows kept as CSR + CSC, their non-zeros}. */
+int32_t fos_hybrid_plan(int64_t m, int64_t n, const int32_t *row_nnz, int64_t *out /* 5 */);
+
 /* ====================================================================================== */
 /* measurement helpers (bench.py)                                                         */
 /* ====================================================================================== */

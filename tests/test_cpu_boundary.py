@@ -172,3 +172,37 @@ def test_batch_mode_geometry(fos):
     assert L.fos_batch_plan(100, 1281, out) == -3            # FOS_ERR_UNSUPPORTED: n > 1280
     assert L.fos_batch_plan(4000, 700, out) == -3            # the A X / W staging of m = 4000 rows does not fit an SM
     assert L.fos_batch_plan(0, 5, out) != 0
+
+
+def test_hybrid_row_plan(fos):
+    """fos_hybrid_plan (host only): which rows stay in the dense block K1 streams under "hybrid_rows"."""
+    import ctypes as C
+    L = fos._lib.load()
+    out = (C.c_int64 * 5)()
+
+    def plan(rn, n):
+        rn = np.ascontiguousarray(rn, dtype=np.int32)
+        assert L.fos_hybrid_plan(rn.size, n, rn.ctypes.data_as(C.POINTER(C.c_int32)), out) == 0
+        return list(out)
+
+    # config 3 at test scale: row 0 one entry, rows 1..md dense, one empty row, nx rows of -I
+    md, nx = 300, 200
+    rn = np.concatenate([[1], np.full(md, nx), [0], np.ones(nx)])
+    use, r0, rows, srows, snnz = plan(rn, nx + 1)
+    assert (use, r0, rows, srows, snnz) == (1, 0, md + 1, nx, nx)     # row 0 rides along in the block (r0 rounds DOWN to 16)
+    # dense rows starting at 37: the block starts at 32, rows 0..31 with entries go to CSR
+    rn = np.concatenate([np.ones(37), np.full(500, 64), np.zeros(3), np.full(400, 2)])
+    use, r0, rows, srows, snnz = plan(rn, 64)
+    assert (use, r0, rows) == (1, 32, 537 - 32)
+    assert srows == 32 + 400 and snnz == 32 + 800                      # empty rows are stored nowhere
+    # nothing to gain: less than 2 % of the bytes saved / all rows dense / nothing dense / tiny matrices
+    assert plan(np.concatenate([[1], np.full(2100, 40), [0], np.ones(40)]), 41)[0] == 0
+    assert plan(np.full(100, 50), 50)[0] == 0
+    assert plan(np.ones(100), 50)[0] == 0
+    assert plan(np.full(20, 50), 50)[0] == 0
+    # a sparse row INSIDE the dense range stays in the block
+    rn = np.full(160, 100)
+    rn[80] = 1
+    rn = np.concatenate([rn, np.ones(160)])
+    use, r0, rows, srows, snnz = plan(rn, 100)
+    assert (use, r0, rows, srows, snnz) == (1, 0, 160, 160, 160)
