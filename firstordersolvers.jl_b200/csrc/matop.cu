@@ -522,7 +522,7 @@ MVView MatOp::run_t(const double *const *X, const double *const *W, const int32_
         V.cp_sv = K1_BW;
     } else if (kind == 1) {
         // plain path: complete results for the local rows
-        a.rowpart = full_ax.p + (nranks > 1 ? 0 : 0);
+        a.rowpart = full_ax.p;
         a.colpart = full_atw.p;
         a.m_pad_local = m_pad_local;
         const int wpb = 8;

@@ -171,8 +171,6 @@ def run_c3(args):
     BLK = 1000
     x0 = torch.randn(nx, dtype=torch.float64, device=dev, generator=torch.Generator(device=dev).manual_seed(33))
     dloc = torch.zeros(m, dtype=torch.float64, device=dev)   # D x0 on the D rows owned here
-    for gi in range(r0, r0 + cnt):
-        pass  # (rows are filled block-wise below)
     # global row 0: [-1 0]; rows 1..md: [0 -D]; row md+1: zeros; rows md+2..: [0 -I]
     lo, hi = max(r0, 1), min(r0 + cnt, md + 1)      # D rows in this shard (global indices)
     b0 = ((lo - 1) // BLK) * BLK
