@@ -8,7 +8,7 @@ Two kinds of fixture, and the difference matters:
   row strings of test/testprint.jl:15-19, the constructor defaults of solvers/*.jl, and the optimum
   recorded in test/testDRandGAPA.jl:12,15 (kept for the day a Julia RNG is available; it cannot be
   reproduced here because it depends on Julia's `randn` stream).
-* lockstep_<problem>_<algorithm>.npz -- trajectories of the CPU oracle (oracle/fos_oracle.c) on
+* lockstep_[direct_]<problem>_<algorithm>.npz -- trajectories of the CPU oracle (oracle/fos_oracle.c) on
   seeded, well-conditioned instances: the complete solver state before every iteration and the
   oracle's result after it.  THESE ARE ORACLE OUTPUTS, NOT REFERENCE OUTPUTS: the reference is Julia
   and cannot run in this environment.  They freeze the oracle (a change of the restatement shows up as
@@ -35,12 +35,14 @@ N_ITER, CHECKI, EPS = 20, 5, 1e-12
 CASES = [("nnls", "DR"), ("nnls", "GAP"), ("nnls", "AP"), ("nnls", "GAPA_b"), ("nnls", "FISTA"), ("nnls", "Dykstra"),
          ("nnls", "GAPP"), ("lasso", "DR"), ("sdp", "GAP"), ("socls", "GAPA")]
 WELL = {"nnls": 0.02, "lasso": 0.1, "socls": 0.02, "sdp": 1.0}  # as tests/test_gpu_solvers.py
+# direct = true (HSDE.jl:10-15) on the UNSCALED instances: no truncated CG, nothing amplifies rounding
+DIRECT_CASES = [("nnls", "DR"), ("nnls", "GAPP"), ("sdp", "GAP")]
 
 
-def build_problem(kind):
+def build_problem(kind, direct=False):
     from fos_b200 import problems
     if kind == "nnls":
-        return problems.nnls_conic(40, 50, seed=1, scale=WELL[kind])
+        return problems.nnls_conic(40, 50, seed=1, scale=1.0 if direct else WELL[kind])
     if kind == "lasso":
         return problems.lasso_like(60, 130, seed=2, scale=WELL[kind])
     if kind == "socls":
@@ -56,11 +58,11 @@ def snapshot(O):
             "s1_calls": O.s1_calls, "alpha12": O.alpha12, "fista_t": O.fista_t}
 
 
-def make_lockstep(kind, alg):
+def make_lockstep(kind, alg, direct=False):
     from helpers import ALG_SETUPS
     from oracle import fos_oracle
-    P = build_problem(kind)
-    O = fos_oracle.OracleConic(P.c, P.A, P.b, P.constr_cones, P.var_cones)
+    P = build_problem(kind, direct)
+    O = fos_oracle.OracleConic(P.c, P.A, P.b, P.constr_cones, P.var_cones, direct=direct)
     O.set_algorithm(*ALG_SETUPS[alg][0])
     O.set_iterate(O.initial_value())
     before, after_x, after_tmp1, cgiter, s1_after, a12_after, recs = [], [], [], [], [], [], []
@@ -87,7 +89,7 @@ def make_lockstep(kind, alg):
         "A_shape": np.array(A.shape, dtype=np.int64),
         "cones": np.array(json.dumps({"constr": [[n, int(k)] for n, k in P.constr_cones],
                                       "var": [[n, int(k)] for n, k in P.var_cones]})),
-        "alg": np.array(alg), "n_iter": np.int64(N_ITER), "checki": np.int64(CHECKI), "eps": np.float64(EPS),
+        "alg": np.array(alg), "direct": np.int64(1 if direct else 0), "n_iter": np.int64(N_ITER), "checki": np.int64(CHECKI), "eps": np.float64(EPS),
         "after_x": np.array(after_x), "after_tmp1": np.array(after_tmp1), "cgiter": np.array(cgiter, dtype=np.int64),
         "after_s1_calls": np.array(s1_after, dtype=np.int64), "after_alpha12": np.array(a12_after, float),
         "records": np.array(recs, float),
@@ -99,7 +101,7 @@ def make_lockstep(kind, alg):
     data["before_s1_calls"] = np.array([s["s1_calls"] for s in before], dtype=np.int64)
     data["before_alpha12"] = np.array([s["alpha12"] for s in before], float)
     data["before_fista_t"] = np.array([s["fista_t"] for s in before], float)
-    path = HERE / f"lockstep_{kind}_{alg}.npz"
+    path = HERE / (f"lockstep_direct_{kind}_{alg}.npz" if direct else f"lockstep_{kind}_{alg}.npz")
     np.savez_compressed(path, **data)
     return path
 
@@ -139,8 +141,9 @@ def make_literals():
 if __name__ == "__main__":
     make_literals()
     total = 0
-    for kind, alg in CASES:
-        p = make_lockstep(kind, alg)
-        total += p.stat().st_size
-        print(p.name, p.stat().st_size)
+    for direct, cases in ((False, CASES), (True, DIRECT_CASES)):
+        for kind, alg in cases:
+            p = make_lockstep(kind, alg, direct)
+            total += p.stat().st_size
+            print(p.name, p.stat().st_size)
     print("total bytes", total)
