@@ -106,6 +106,52 @@ def make_lockstep(kind, alg, direct=False):
     return path
 
 
+FEAS_CASES = ["DR", "GAPA", "FISTA", "Dykstra"]
+
+
+def make_feasibility(alg):
+    """Feasibility form (Feasibility.jl:2-6): find x in {A x = b} and x >= 0, posed as AffinePlusLinear(A, b, 0, 1)
+    on [x; z] with z in Zero (test/testfeasibility.jl:5-19 shape); instance of tests/test_gpu_solvers.py::
+    test_feasibility_lockstep."""
+    from helpers import ALG_SETUPS
+    from fos_b200 import problems
+    from oracle import fos_oracle
+    A, b, cones = problems.feasibility_problem(30, 70, seed=5)
+    A = A * 0.05
+    b = b * 0.05
+    q = np.zeros(70)
+    O = fos_oracle.OracleFeasibility(A, b, q, 1, cones)
+    O.set_algorithm(*ALG_SETUPS[alg][0])
+    O.set_iterate(O.initial_value())
+    n_iter, checki = 21, 7
+    before, after_x, cgiter, errs = [], [], [], []
+    for i in range(1, n_iter + 1):
+        before.append(snapshot(O))
+        out = O.run(i, 1, checki=checki, eps=EPS)
+        after_x.append(O.get_state("x"))
+        cgiter.append(O.cgiter)
+        if i % checki == 0:
+            errs.append([out["history"]["i"][0], out["history"]["p"][0], out["history"]["status"][0]])
+    Ac = sp.csc_matrix(A)
+    Ac.sort_indices()
+    data = {"form": np.array("feasibility"), "alg": np.array(alg), "b": np.asarray(b, float), "q": q, "beta": np.int64(1),
+            "A_data": Ac.data.astype(float), "A_indices": Ac.indices.astype(np.int64), "A_indptr": Ac.indptr.astype(np.int64),
+            "A_shape": np.array(Ac.shape, dtype=np.int64),
+            "cones": np.array(json.dumps([[n, int(k)] for n, k in cones])),
+            "n_iter": np.int64(n_iter), "checki": np.int64(checki), "eps": np.float64(EPS),
+            "after_x": np.array(after_x), "cgiter": np.array(cgiter, dtype=np.int64), "records": np.array(errs, float)}
+    for key in ("x", "xinit", "fista_y", "dykstra_p", "dykstra_q"):
+        arr = np.array([s_[key] for s_ in before])
+        if key in ("x", "xinit") or np.any(arr != 0.0):
+            data["before_" + key] = arr
+    data["before_s1_calls"] = np.array([s_["s1_calls"] for s_ in before], dtype=np.int64)
+    data["before_alpha12"] = np.array([s_["alpha12"] for s_ in before], float)
+    data["before_fista_t"] = np.array([s_["fista_t"] for s_ in before], float)
+    path = HERE / f"feasibility_{alg}.npz"
+    np.savez_compressed(path, **data)
+    return path
+
+
 def make_literals():
     # test/testPSD.jl:3-4: ys = [-0.0064709 -0.22443; -0.22443 -1.02411] has the eigenvalues -1.0714074874680
     # and +0.0408265874680; its projection onto the PSD cone (what IndPSD returns and what SCS returns for the
@@ -146,4 +192,8 @@ if __name__ == "__main__":
             p = make_lockstep(kind, alg, direct)
             total += p.stat().st_size
             print(p.name, p.stat().st_size)
+    for alg in FEAS_CASES:
+        p = make_feasibility(alg)
+        total += p.stat().st_size
+        print(p.name, p.stat().st_size)
     print("total bytes", total)

@@ -208,3 +208,85 @@ def test_gpu_lockstep_on_golden(fos, name):
         else:
             assert len(rec) == 0
     print(f"{name}: worst one-step relative deviation {worst:.2e}")
+
+
+# ---------------------------------------------------------------------------------------------
+# Feasibility form (Feasibility.jl, FeasibilityStatus.jl): frozen oracle trajectories
+# ---------------------------------------------------------------------------------------------
+FEAS_FIXTURES = sorted(p.name for p in GOLDEN.glob("feasibility_*.npz"))
+
+
+def _load_feas(name):
+    z = np.load(GOLDEN / name, allow_pickle=False)
+    shape = tuple(int(v) for v in z["A_shape"])
+    A = sp.csc_matrix((z["A_data"], z["A_indices"], z["A_indptr"]), shape=shape).toarray()
+    cones = [(n, k) for n, k in json.loads(str(z["cones"]))]
+    return z, A, z["b"], z["q"], int(z["beta"]), cones, str(z["alg"])
+
+
+def test_feasibility_fixtures_are_present():
+    assert len(FEAS_FIXTURES) >= 4
+
+
+@pytest.mark.parametrize("name", FEAS_FIXTURES)
+def test_c_oracle_regenerates_feasibility_golden(oracle, name):
+    z, A, b, q, beta, cones, alg = _load_feas(name)
+    O = oracle.OracleFeasibility(A, b, q, beta, cones)
+    O.set_algorithm(*ALG_SETUPS[alg][0])
+    O.set_iterate(O.initial_value())
+    checki, k = int(z["checki"]), 0
+    for i in range(1, int(z["n_iter"]) + 1):
+        np.testing.assert_allclose(O.get_state("x"), z["before_x"][i - 1], rtol=1e-12, atol=1e-300)
+        out = O.run(i, 1, checki=checki, eps=float(z["eps"]))
+        assert O.cgiter == z["cgiter"][i - 1]
+        np.testing.assert_allclose(O.get_state("x"), z["after_x"][i - 1], rtol=1e-12, atol=1e-300)
+        if i % checki == 0:
+            h = out["history"]
+            np.testing.assert_allclose([h["i"][0], h["p"][0], h["status"][0]], z["records"][k], rtol=1e-10, equal_nan=True)
+            k += 1
+    assert k == len(z["records"])
+
+
+@pytest.mark.parametrize("name", FEAS_FIXTURES)
+def test_numpy_restatement_lockstep_on_feasibility_golden(name):
+    from oracle import np_oracle as npo
+    z, A, b, q, beta, cones, alg = _load_feas(name)
+    M = npo.NPModel.feasibility(A, b, q, beta, cones)
+    M.set_algorithm(*ALG_SETUPS[alg][0])
+    M.checki, M.eps = 10 ** 6, float(z["eps"])
+    worst = 0.0
+    for i in range(1, int(z["n_iter"]) + 1):
+        M.x = z["before_x"][i - 1].copy()
+        if z["before_s1_calls"][i - 1] > 1:
+            M.S1.xinit = z["before_xinit"][i - 1].copy()
+        M.S1.i = int(z["before_s1_calls"][i - 1])
+        M.alpha12, M.t = float(z["before_alpha12"][i - 1]), float(z["before_fista_t"][i - 1])
+        for attr, key in (("y", "before_fista_y"), ("p", "before_dykstra_p"), ("q", "before_dykstra_q")):
+            setattr(M, attr, z[key][i - 1].copy() if key in z.files else np.zeros(M.N))
+        M.i = i
+        M.step()
+        assert M.S1.cgiter == z["cgiter"][i - 1], f"iteration {i}: CG count"
+        worst = max(worst, rel_err(M.x, z["after_x"][i - 1]))
+    assert worst < STEP_TOL, f"{name}: NumPy restatement deviates by {worst:.2e}"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", FEAS_FIXTURES)
+def test_gpu_lockstep_on_feasibility_golden(fos, name):
+    """fos_load_affine_csc + one iteration from the stored state: iterate to 1e-10, CG count, err record
+    (FeasibilityStatus.jl:32-72)."""
+    from helpers import load_affine
+    z, A, b, q, beta, cones, alg = _load_feas(name)
+    H = load_affine(fos, A, b, q, beta, cones)
+    H.set_algorithm(ALG_SETUPS[alg][1](fos))
+    H.ck(H.L.fos_begin_solve(H.h))
+    checki, k = int(z["checki"]), 0
+    for i in range(1, int(z["n_iter"]) + 1):
+        _sync_state_from_golden(H, z, i - 1, alg)
+        done, st, rec, _ = H.run(i, 1, checki, float(z["eps"]))
+        assert H.info("cgiter") == z["cgiter"][i - 1], f"iteration {i}: CG count"
+        e = rel_err(H.get_iterate(), z["after_x"][i - 1])
+        assert e < STEP_TOL, f"iteration {i}: iterate differs by {e:.3e}"
+        if i % checki == 0:
+            np.testing.assert_allclose(rec[0, 1], z["records"][k][1], rtol=1e-9, equal_nan=True)  # err
+            k += 1
