@@ -453,14 +453,23 @@ void Handle::cg_enqueue_iteration()
         // single GPU: one block per SM (more blocks do not shorten the latency chain).  Peer exchange: up to two
         // per SM, so that a thread gathers ONE entry (one NVLink round trip) rather than two in sequence
         const int64_t auto_blocks = p2p ? 2 * (int64_t)num_sms : (int64_t)num_sms;
-        const int grid = (int)std::min<int64_t>((L.LP + VBLOCK - 1) / VBLOCK,
-                                                std::min<int64_t>(tail_blocks > 0 ? tail_blocks : auto_blocks, P2P_MAX_BLOCKS));
+        const void *fn = p2p ? (const void *)k_cg_tail_hsde<true> : (const void *)k_cg_tail_hsde<false>;
+        // a cooperative grid must be co-resident: never ask for more blocks than the kernel's occupancy allows
+        // (same binary and same GPU model on every rank, so the clamp is identical everywhere)
+        int &occ = tail_occ[p2p ? 1 : 0];
+        if (occ == 0) {
+            FOS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, VBLOCK, 0));
+            FOS_REQUIRE(occ >= 1, "the fused CG tail does not fit on an SM");
+        }
+        const int64_t resident = (int64_t)occ * num_sms;
+        const int grid = (int)std::min<int64_t>(
+            std::min<int64_t>((L.LP + VBLOCK - 1) / VBLOCK, resident),
+            std::min<int64_t>(tail_blocks > 0 ? tail_blocks : auto_blocks, P2P_MAX_BLOCKS));
         const double *cptr = d_c.p, *bptr = d_b.p;
         double *solp = sol.p, *rp = r.p, *pp = p.p, *App = Ap.p;
         Ctrl *cp = d_ctrl.p;
         void *args[] = {(void *)&L, (void *)&V, (void *)&A.p2p, (void *)&cptr, (void *)&bptr, (void *)&solp,
                         (void *)&rp,  (void *)&pp, (void *)&App, (void *)&cp, (void *)&gbar};
-        const void *fn = p2p ? (const void *)k_cg_tail_hsde<true> : (const void *)k_cg_tail_hsde<false>;
         A.prof_begin(0, stream);
         FOS_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(VBLOCK), args, 0, stream));
         A.prof_end(stream);
