@@ -182,6 +182,33 @@ def psd_projection_problem(ys) -> ConicProblem:
     return ConicProblem(c, A, b, [("SOC", k + 1), ("SDP", k)], [("Free", n)], f"psdproj{d}")
 
 
+def infeasible_lp(m=30, n=12, seed=7) -> ConicProblem:
+    """An LP  min c'x s.t. b - A x >= 0  with a Farkas certificate built in: y > 0 with A'y = 0 and b'y = -1, so no
+    x is feasible.  Drives the :Infeasible branch of checkstatus (HSDEStatus.jl:62-63)."""
+    rng = np.random.default_rng(seed)
+    y = np.abs(rng.standard_normal(m)) + 0.1
+    A = rng.standard_normal((m, n))
+    A = A - np.outer(y, A.T @ y) / (y @ y)          # A'y = 0
+    b = rng.standard_normal(m)
+    b = b - y * (b @ y) / (y @ y) - y / (y @ y)       # b'y = -1
+    c = rng.standard_normal(n)
+    return ConicProblem(c, sp.csc_matrix(A), b, [("NonNeg", m)], [("Free", n)], f"infeasible_lp{m}x{n}")
+
+
+def unbounded_lp(m=30, n=12, seed=8) -> ConicProblem:
+    """An LP  min c'x s.t. b - A x >= 0  that is feasible (x = 0, b > 0) and has a recession direction d with
+    A d <= 0 and c'd < 0.  Drives the :Unbounded branch of checkstatus (HSDEStatus.jl:60-61)."""
+    rng = np.random.default_rng(seed)
+    d = rng.standard_normal(n)
+    A = rng.standard_normal((m, n))
+    A = A * (-np.sign(A @ d))[:, None]               # A d = -|A d| <= 0
+    b = np.abs(rng.standard_normal(m)) + 0.5
+    c = -d + 0.1 * rng.standard_normal(n)
+    if c @ d >= 0:
+        c = -d
+    return ConicProblem(c, sp.csc_matrix(A), b, [("NonNeg", m)], [("Free", n)], f"unbounded_lp{m}x{n}")
+
+
 def feasibility_problem(am=50, an=100, seed=2):
     """test/testfeasibility.jl shape: find x >= 0 with A x = b (b = A*xsol, xsol >= 0 here so that it
     is feasible), posed on [x; z] as S1 = AffinePlusLinear(A, b, 0, 1) and

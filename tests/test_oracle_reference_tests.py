@@ -423,3 +423,56 @@ def test_c_and_numpy_oracles_agree_on_direct_and_linesearch():
     fo.lib().fosor_get_alphabest.restype = __import__("ctypes").c_double
     fo.lib().fosor_get_alphabest.argtypes = [__import__("ctypes").c_void_p]
     assert fo.lib().fosor_get_alphabest(O._h) == M.alphabest
+
+
+# ---------------------------------------------------------------------------------------------
+# :Infeasible / :Unbounded branches of checkstatus (HSDEStatus.jl:57-66) -- no reference test reaches them
+# ---------------------------------------------------------------------------------------------
+STATUS_ALGS = {"DR": ("GAP", 0.5, 2.0, 2.0, 0.0, 100), "GAP": ("GAP", 0.8, 1.8, 1.8, 0.0, 100),
+               "GAPA": ("GAPA", 1.0, 0.0, 0.0, 0.0, 100), "FISTA": ("FISTA", 1.0, 0.0, 0.0, 0.0, 100),
+               "Dykstra": ("Dykstra", 0.0, 0.0, 0.0, 0.0, 100)}
+
+
+@pytest.mark.parametrize("alg", sorted(STATUS_ALGS))
+def test_infeasible_lp_is_reported_with_a_farkas_certificate(alg):
+    P = problems.infeasible_lp()
+    O = fo.OracleConic(P.c, P.A, P.b, P.constr_cones, P.var_cones)
+    O.set_algorithm(*STATUS_ALGS[alg])
+    O.set_iterate(O.initial_value())
+    r = O.solve(max_iters=3000, checki=50, eps=1e-6)
+    assert r["status"] == "Infeasible"
+    M = npo.NPModel.conic(P.c, P.A, P.b, P.constr_cones, P.var_cones)
+    M.set_algorithm(*STATUS_ALGS[alg])
+    rn = M.solve(max_iters=3000, checki=50, eps=1e-6)
+    assert (rn["status"], rn["iterations"]) == (r["status"], r["iterations"])
+    # the certificate behind the decision (HSDEStatus.jl:62): A'y ~ 0 with b'y < 0, y in the dual cone
+    l = P.m + P.n + 1
+    y = r["guess"][P.n:P.n + P.m]
+    assert y.min() >= 0 and P.b @ y < 0
+    assert np.linalg.norm(P.A.T @ y) <= 1e-6 * (-(P.b @ y) / np.linalg.norm(P.b)) * 1.0001
+    assert r["guess"][l - 1] < 1e-6          # tau -> 0
+
+
+@pytest.mark.parametrize("alg", sorted(STATUS_ALGS))
+def test_unbounded_lp_status_matches_between_restatements(alg):
+    """GAP, GAPA, FISTA and Dykstra report :Unbounded with a recession direction.  DR(0.5) reports :Infeasible at
+    its first check: the projected y is EXACTLY zero there, so the reference's test `norm(A'y) <= eps*(-b'y/norm(b))`
+    reads `0.0 <= -0.0`, which is true (HSDEStatus.jl:62 evaluated literally).  Both restatements reproduce that."""
+    P = problems.unbounded_lp()
+    O = fo.OracleConic(P.c, P.A, P.b, P.constr_cones, P.var_cones)
+    O.set_algorithm(*STATUS_ALGS[alg])
+    O.set_iterate(O.initial_value())
+    r = O.solve(max_iters=3000, checki=50, eps=1e-6)
+    M = npo.NPModel.conic(P.c, P.A, P.b, P.constr_cones, P.var_cones)
+    M.set_algorithm(*STATUS_ALGS[alg])
+    rn = M.solve(max_iters=3000, checki=50, eps=1e-6)
+    assert (rn["status"], rn["iterations"]) == (r["status"], r["iterations"])
+    if alg == "DR":
+        assert r["status"] == "Infeasible" and r["iterations"] == 50
+        assert r["history"]["bty"][-1] == 0.0 and r["history"]["tau"][-1] == 0.0
+    else:
+        assert r["status"] == "Unbounded"
+        x = r["guess"][:P.n]
+        s = r["guess"][P.m + P.n + 1 + P.n:P.m + P.n + 1 + P.n + P.m]
+        assert P.c @ x < 0                                                       # improving direction
+        assert np.linalg.norm(P.A @ x + s) <= 1e-6 * (-(P.c @ x) / np.linalg.norm(P.c)) * 1.0001   # HSDEStatus.jl:60
