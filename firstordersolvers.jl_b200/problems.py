@@ -209,6 +209,19 @@ def unbounded_lp(m=30, n=12, seed=8) -> ConicProblem:
     return ConicProblem(c, sp.csc_matrix(A), b, [("NonNeg", m)], [("Free", n)], f"unbounded_lp{m}x{n}")
 
 
+def stiff_feasibility_problem(am=60, an=120, seed=11, decades=3):
+    """A Feasibility instance on which the CG of AffinePlusLinear cannot reach its ABSOLUTE tolerance n*eps
+    (affinepluslinear.jl:108-112): singular values of A from 1 to 10^decades.  With decades = 3 the solve stops at
+    the max_iters = 1000 cap (affinepluslinear.jl:115) and raises the @warn of :120 / conjugategradients.jl:53."""
+    rng = np.random.default_rng(seed)
+    U, _ = np.linalg.qr(rng.standard_normal((am, am)))
+    V, _ = np.linalg.qr(rng.standard_normal((an, am)))
+    A = U @ np.diag(np.logspace(0, decades, am)) @ V.T
+    b = A @ np.abs(rng.standard_normal(an))
+    z = rng.standard_normal(an + am) * 10.0 ** decades
+    return A, b, [("NonNeg", an), ("Zero", am)], z
+
+
 def feasibility_problem(am=50, an=100, seed=2):
     """test/testfeasibility.jl shape: find x >= 0 with A x = b (b = A*xsol, xsol >= 0 here so that it
     is feasible), posed on [x; z] as S1 = AffinePlusLinear(A, b, 0, 1) and

@@ -63,3 +63,24 @@ def test_status_branches_free_running(fos, oracle, kind, alg):
     done, st, rec, guess = H.solve(MAX_ITERS, CHECKI, EPS)
     assert fos.model.STATUS_SYMBOLS[st] == ro["status"]
     assert abs(done - ro["iterations"]) <= CHECKI
+
+
+def test_cg_iteration_cap_sets_the_warning(fos, oracle):
+    """affinepluslinear.jl:115-120 / conjugategradients.jl:43,53: the solve stops at max_iters = 1000, S.cgiter is
+    1000 and the @warn is raised (fos_get_info 4); a well-scaled instance leaves the flag alone."""
+    from fos_b200 import problems
+    from helpers import load_affine
+    A, b, cones, z = problems.stiff_feasibility_problem()
+    O = oracle.OracleFeasibility(A, b, np.zeros(A.shape[1]), 1, cones)
+    yo = O.affine_prox(z)
+    assert O.cgiter == 1000
+    H = load_affine(fos, A, b, np.zeros(A.shape[1]), 1, cones)
+    y = H.affine_prox(z)
+    assert H.info("cgiter") == 1000
+    assert H.info("cg_warned") == 1
+    assert rel_err(y, yo) < 1e-2       # 1000 unconverged CG iterations: two CPU restatements drift to 4e-6
+    A2, b2, cones2, z2 = problems.stiff_feasibility_problem(decades=0)
+    H2 = load_affine(fos, A2, b2, np.zeros(A2.shape[1]), 1, cones2)
+    O2 = oracle.OracleFeasibility(A2, b2, np.zeros(A2.shape[1]), 1, cones2)
+    assert rel_err(H2.affine_prox(z2), O2.affine_prox(z2)) < 1e-10
+    assert H2.info("cgiter") == O2.cgiter and H2.info("cg_warned") == 0

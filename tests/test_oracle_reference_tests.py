@@ -476,3 +476,20 @@ def test_unbounded_lp_status_matches_between_restatements(alg):
         s = r["guess"][P.m + P.n + 1 + P.n:P.m + P.n + 1 + P.n + P.m]
         assert P.c @ x < 0                                                       # improving direction
         assert np.linalg.norm(P.A @ x + s) <= 1e-6 * (-(P.c @ x) / np.linalg.norm(P.c)) * 1.0001   # HSDEStatus.jl:60
+
+
+def test_cg_iteration_cap_and_warning():
+    """affinepluslinear.jl:115-120: max_iters = 1000; reaching it raises the @warn and S.cgiter == 1000."""
+    A, b, cones, z = problems.stiff_feasibility_problem()
+    O = fo.OracleFeasibility(A, b, np.zeros(A.shape[1]), 1, cones)
+    y = O.affine_prox(z)
+    assert O.cgiter == 1000 and fo.lib().fosor_get_cg_warned(O._h) == 1
+    M = npo.NPModel.feasibility(A, b, np.zeros(A.shape[1]), 1, cones)
+    yn = M.S1.prox(z)
+    assert M.S1.cgiter == 1000
+    assert np.abs(yn - y).max() < 1e-3 * np.abs(y).max()      # 1000 unconverged iterations: restatements drift to ~4e-6
+    # a well-scaled instance stays far below the cap and leaves the flag alone
+    A2, b2, cones2, z2 = problems.stiff_feasibility_problem(decades=0)
+    O2 = fo.OracleFeasibility(A2, b2, np.zeros(A2.shape[1]), 1, cones2)
+    O2.affine_prox(z2)
+    assert O2.cgiter < 100 and fo.lib().fosor_get_cg_warned(O2._h) == 0
