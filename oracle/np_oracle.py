@@ -369,6 +369,7 @@ class NPModel:
                 a1 = a2 = self.alpha12
             t1 = self.P1(x)
             t1 = a1 * t1 + (1 - a1) * x
+            self.tmp1 = t1  # gap.jl:48 / gapa.jl:74: the relaxed S1 output (data.tmp1)
             t2 = self.P2(t1)
             self.check(t2)
             t2 = a2 * t2 + (1 - a2) * t1
@@ -410,11 +411,13 @@ class NPModel:
                     if nt < best:
                         abest, best = at, nt
                 t1 = t1 + abest * res
+                self.tmp1 = t1
                 t2 = self.P2(t1)
                 self.check(t2)
                 self.x = a2 * t2 + (1 - a2) * t1
             else:
                 t1 = a1 * t1 + (1 - a1) * x
+                self.tmp1 = t1
                 t2 = self.P2(t1)
                 self.check(t2)
                 t2 = a2 * t2 + (1 - a2) * t1
