@@ -36,7 +36,24 @@ class StandInHandle:
     def set_algorithm(self, alg):
         code, a, a1, a2, b, ip = alg._params()
         self._alg = (ALG_NAMES[code], a, a1, a2, b, ip)
-        self.M.set_algorithm(*self._alg)
+        for m in ([self.M] if self.M is not None else []) + getattr(self, "Ms", []):
+            m.set_algorithm(*self._alg)
+
+    # batch mode: B independent models
+    def load_conic_batch(self, A, b, c, constr_cones, var_cones, device_ptr=None):
+        self.Ms = [npo.NPModel.conic(c[j], A[j], b[j], constr_cones, var_cones) for j in range(len(A))]
+
+    def solve_batch(self, max_iters, checki, eps):
+        done, st, recs, guess = [], [], [], []
+        for m in self.Ms:
+            r = m.solve(max_iters=max_iters, checki=checki, eps=eps)
+            self.M = m
+            done.append(r["iterations"])
+            st.append(STATUS_CODES[r["status"]])
+            recs.append(self._records())
+            guess.append(r["guess"])
+        self.M = None
+        return np.array(done), np.array(st), recs, np.array(guess)
 
     def set_direct(self, on=True):
         self.M = self._build(bool(on))

@@ -84,3 +84,29 @@ def test_cg_iteration_cap_sets_the_warning(fos, oracle):
     O2 = oracle.OracleFeasibility(A2, b2, np.zeros(A2.shape[1]), 1, cones2)
     assert rel_err(H2.affine_prox(z2), O2.affine_prox(z2)) < 1e-10
     assert H2.info("cgiter") == O2.cgiter and H2.info("cg_warned") == 0
+
+
+@pytest.mark.parametrize("alg", ["DR", "GAPA", "Dykstra"])
+def test_status_branches_batch_mode(fos, oracle, alg):
+    """Batch mode (one persistent CTA per problem, bt_check of csrc/batch.cu): a batch that mixes infeasible and
+    unbounded LPs of one shape reports, per problem, the oracle's status within one check interval -- problems
+    stop independently."""
+    from fos_b200 import problems
+    plist = [problems.infeasible_lp(seed=7), problems.unbounded_lp(seed=8), problems.infeasible_lp(seed=9),
+             problems.unbounded_lp(seed=14)]
+    A = np.stack([np.asarray(P.A.todense()) for P in plist])
+    b = np.stack([P.b for P in plist])
+    c = np.stack([P.c for P in plist])
+    H = fos.Handle(0)
+    H.load_conic_batch(A, b, c, plist[0].constr_cones, plist[0].var_cones)
+    oargs, fac = ALG_SETUPS[alg]
+    H.set_algorithm(fac(fos))
+    done, st, recs, guess = H.solve_batch(MAX_ITERS, CHECKI, EPS)
+    for j, P in enumerate(plist):
+        O = oracle.OracleConic(P.c, P.A, P.b, P.constr_cones, P.var_cones)
+        O.set_algorithm(*oargs)
+        O.set_iterate(O.initial_value())
+        ro = O.solve(max_iters=MAX_ITERS, checki=CHECKI, eps=EPS)
+        assert ro["status"] in ("Infeasible", "Unbounded"), (j, ro["status"])
+        assert fos.model.STATUS_SYMBOLS[st[j]] == ro["status"], j
+        assert abs(done[j] - ro["iterations"]) <= CHECKI, (j, done[j], ro["iterations"])

@@ -42,3 +42,8 @@ def test_body_of_status_branches_free_running(fake, oracle, kind, alg):
 
 def test_body_of_cg_iteration_cap(fake, oracle):
     tz.test_cg_iteration_cap_sets_the_warning(fake, oracle)
+
+
+@pytest.mark.parametrize("alg", ["DR", "GAPA", "Dykstra"])
+def test_body_of_status_branches_batch_mode(fake, oracle, alg):
+    tz.test_status_branches_batch_mode(fake, oracle, alg)
