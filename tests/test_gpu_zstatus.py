@@ -92,8 +92,9 @@ def test_status_branches_batch_mode(fos, oracle, alg):
     unbounded LPs of one shape reports, per problem, the oracle's status within one check interval -- problems
     stop independently."""
     from fos_b200 import problems
-    plist = [problems.infeasible_lp(seed=7), problems.unbounded_lp(seed=8), problems.infeasible_lp(seed=9),
-             problems.unbounded_lp(seed=14)]
+    # m = 91, n = 51: the shape of config 1 / the batch lock-step tests (tests/test_gpu_batch.py)
+    plist = [problems.infeasible_lp(91, 51, seed=7), problems.unbounded_lp(91, 51, seed=8),
+             problems.infeasible_lp(91, 51, seed=9), problems.unbounded_lp(91, 51, seed=14)]
     A = np.stack([np.asarray(P.A.todense()) for P in plist])
     b = np.stack([P.b for P in plist])
     c = np.stack([P.c for P in plist])
