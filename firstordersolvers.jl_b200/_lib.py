@@ -83,6 +83,7 @@ SIGNATURES = {
     "fos_k1_plan": (C.c_int32, [C.c_int64, C.c_int64, C.c_int32, _i32p, _i32p, C.c_int64, _i32p, _i32p, C.c_int64]),
     "fos_batch_plan": (C.c_int32, [C.c_int64, C.c_int64, _i64p]),
     "fos_hybrid_plan": (C.c_int32, [C.c_int64, C.c_int64, _i32p, _i64p]),
+    "fos_get_tail_trace": (C.c_int32, [_h, _dp]),
     "fos_time_matvec": (C.c_int32, [_h, C.c_int32, C.c_int32, _dp, _dp]),
     "fos_time_psd": (C.c_int32, [_h, C.c_int64, C.c_int64, _dp, _dp, C.c_int32, _dp, _i32p]),
 }

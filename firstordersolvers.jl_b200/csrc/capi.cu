@@ -121,6 +121,13 @@ int32_t fos_set_option(fos_handle_t hh, const char *key, double value)
     } else if (k == "batch_ctas") {
         h.batch_ctas = (int)value;
         if (h.batch) h.batch->grid_ctas = (int)value;
+    } else if (k == "tail_trace") {
+        if (value != 0) {
+            h.tail_trace.alloc(48);
+            h.gbar.trace = h.tail_trace.p;
+        } else {
+            h.gbar.trace = nullptr;
+        }
     } else if (k == "use_graphs") {
         // reserved
     } else {
@@ -457,6 +464,19 @@ int32_t fos_get_info(fos_handle_t hh, int32_t which, double *out)
     case 20: *out = h.A.kind == 3 ? (double)h.A.hyb_sparse_rows : 0.0; break;
     default: throw Error(FOS_ERR_INVALID, "unknown info selector");
     }
+    FOS_API_END(hh)
+}
+
+int32_t fos_get_tail_trace(fos_handle_t hh, double *out)
+{
+    FOS_API_BEGIN(hh)
+    Handle &h = hh->h;
+    FOS_REQUIRE(out != nullptr, "null output");
+    FOS_REQUIRE(h.gbar.trace != nullptr, "set the option \"tail_trace\" first");
+    FOS_CUDA(cudaStreamSynchronize(h.stream));
+    unsigned long long t[48];
+    FOS_CUDA(cudaMemcpy(t, h.tail_trace.p, sizeof(t), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 48; k++) out[k] = (double)t[k];
     FOS_API_END(hh)
 }
 

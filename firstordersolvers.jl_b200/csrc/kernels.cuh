@@ -889,20 +889,28 @@ k1_finalize_local(MVView V, int64_t n, int64_t n_pad, int64_t m_local, int64_t r
 
 // ---------------------------------------------------------------------------------------
 // K7, fused exchange over NVLink peer memory (one process per GPU, CUDA IPC): replaces
-// k1_finalize_local + ncclAllReduce with ONE kernel.
-//   phase 1  every block folds its slice of the local K1 partials into this rank's exchange slot
-//            buf[parity] = [NV][n_pad] A' partial sums | [NV][m_pad] own rows of A X;
-//            the last block to finish publishes the epoch in every peer's flag array (st.release.sys).
-//   phase 2  every block waits until all ranks have published the epoch (ld.acquire.sys on its OWN
-//            flag array), then gathers its slice straight from the peers' slots: column entries are
-//            summed over ranks in rank order (identical bits on every rank -> identical stop tests),
-//            row entries are copied from their owner.  Result: complete A X / A' W in xbuf.
-// Slots are double buffered by epoch parity: a slot is rewritten two exchanges later, after every
-// peer has passed the intermediate exchange (which it enters only after finishing this one's reads).
+// k1_finalize_local + ncclAllReduce with ONE kernel, and is the first phase of the fused CG tail.
+//
+// Protocol ("self-validating 8-byte pushes"): every rank owns a receive area
+//     recv[parity][source rank][vector 0..1][entry 0 .. n_pad+m_pad)
+// that is filled with a SENTINEL bit pattern (all ones: a NaN no arithmetic produces).
+//   push  a thread folds its entries of the local K1 partials -- column entries (A' partial sums) on every
+//         rank, row entries (A X) on the rank that owns the row -- and stores each value straight into the
+//         receive area of EVERY rank (its own included) with one 8-byte system-scope store per destination.
+//         Remote stores are posted: nothing waits for them.
+//   poll  the same thread then reads the same entries of its OWN receive area until they differ from the
+//         sentinel, adds the sources in rank order (identical bits on every rank -> identical stop tests) and
+//         puts the sentinel back.
+// An aligned 8-byte store is indivisible, so a value is its own "ready" flag: there is no flag, no fence and no
+// round trip on the critical path (the previous flag protocol spent 3 system-scope fences, ~4 us each, and a
+// remote-load round trip per exchange: profiles/r2_tail_trace.md).  Areas are double buffered by exchange
+// parity: a rank writes parity p again two exchanges later, after it has consumed the intermediate exchange, which
+// the receiver only feeds after its own kernel of exchange p -- and with it every reset -- has completed.
 // ---------------------------------------------------------------------------------------
-constexpr int P2P_MAX_RANKS = 16;
-constexpr int P2P_FLAG_STRIDE = 32;  // uint32 per rank slot (128 B apart)
+constexpr int P2P_MAX_RANKS = 8;   // one NVSwitch domain
 constexpr int P2P_MAX_BLOCKS = 512;  // grid limit of k_cg_tail_hsde<true>
+constexpr unsigned long long P2P_SENTINEL = 0xFFFFFFFFFFFFFFFFull;
+constexpr unsigned long long P2P_CANONICAL_NAN = 0x7FF8000000000000ull;
 struct P2PHeader {  // first bytes of every rank's region
     int64_t row_begin, m_local;
     int64_t reserved[14];
@@ -911,77 +919,141 @@ struct P2PView {
     unsigned char *peer[P2P_MAX_RANKS];  // base of every rank's region (own region included), mapped here
     int64_t row_begin[P2P_MAX_RANKS], m_local[P2P_MAX_RANKS];
     int32_t nranks, rank;
-    int64_t flags_off, buf_off, slot_doubles;  // byte offsets inside a region; doubles per slot
-    int64_t bflags_off;      // per-block flags [nranks][P2P_MAX_BLOCKS] of the fused CG tail
+    int64_t recv_off;        // byte offset of the receive area inside a region
+    int64_t E;               // entries per vector: n_pad + m_pad
     unsigned int *epoch;     // local: exchanges completed so far
-    unsigned int *tickets;   // local: [0] phase-1 ticket, [1] exit ticket
+    unsigned int *tickets;   // local: [0] exit ticket of k1_exchange_p2p
     unsigned int *error;     // local: set when a peer did not show up within P2P_TIMEOUT_CYCLES
-    int32_t tail_flag_mode;  // fused CG tail hand-shake: 0 = block to block, 1 = one flag per rank (last block publishes)
+    int32_t tail_flag_mode;  // unused (kept so that the option "tail_flags" stays accepted)
 };
 
-__device__ __forceinline__ double ld_sys_f64(const double *p)
-{
-    double v;
-    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ unsigned int ld_acquire_sys_u32(const unsigned int *p)
-{
-    unsigned int v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys_u32(unsigned int *p, unsigned int v)
-{
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-// A peer that died (or never launched the matching kernel) must not hang this GPU: the waits give up after
+// A peer that died (or never launched the matching kernel) must not hang this GPU: the polls give up after
 // ~30 s of SM clock, raise the error flag (the host turns it into FOS_ERR_COMM at the next synchronisation) and
 // let the kernel finish with whatever it has.
 constexpr long long P2P_TIMEOUT_CYCLES = 60000000000LL;
-__device__ __forceinline__ void p2p_wait_flag(const unsigned int *f, unsigned int epoch, unsigned int *error)
-{
-    // poll with relaxed system-scope loads (an acquire per poll would invalidate L1 every iteration) and
-    // acquire once, after the flag has been seen
-    const long long t0 = clock64();
-    for (;;) {
-        unsigned int v;
-        asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-        if ((int)(v - epoch) >= 0) break;
-        if (clock64() - t0 > P2P_TIMEOUT_CYCLES) {
-            atomicExch(error, 1u);
-            break;
-        }
-    }
-    asm volatile("fence.acq_rel.sys;" ::: "memory");
-}
 
-// Sum over ranks (rank order) of NV entries `off + v*vstride` of every rank's slot.  All remote loads of a
-// group of eight ranks are issued before the first add, so the NVLink round trips overlap instead of
-// queueing behind each other (an in-order `acc += load` chain costs nranks round trips).
-template <int NV>
-__device__ __forceinline__ void p2p_gather_sum(const P2PView &X, int par, int64_t off, int64_t vstride, double (&acc)[NV])
+__device__ __forceinline__ unsigned long long *p2p_recv(const P2PView &X, int dst_rank, int par, int src_rank, int v,
+                                                        int64_t e)
 {
+    return reinterpret_cast<unsigned long long *>(X.peer[dst_rank] + X.recv_off) +
+           ((((size_t)par * X.nranks + src_rank) * 2 + v) * (size_t)X.E + (size_t)e);
+}
+// store `val` as entry e / vector v of this rank into the receive area of every rank
+__device__ __forceinline__ void p2p_push(const P2PView &X, int par, int v, int64_t e, double val)
+{
+    unsigned long long bits = (unsigned long long)__double_as_longlong(val);
+    if (bits == P2P_SENTINEL) bits = P2P_CANONICAL_NAN;
+    for (int r = 0; r < X.nranks; r++)
+        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p2p_recv(X, r, par, X.rank, v, e)), "l"(bits) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// Waits for NV values of entry e from every source in [r0, r1) (all first loads in flight together), returns
+// them and re-arms the slots.  out[k][v], k = source - r0.
+template <int NV>
+__device__ __forceinline__ void p2p_poll(const P2PView &X, int par, int64_t e, int r0, int r1,
+                                         double (&out)[P2P_MAX_RANKS][NV])
+{
+    unsigned long long bits[P2P_MAX_RANKS][NV];
+#pragma unroll
+    for (int k = 0; k < P2P_MAX_RANKS; k++)
+        if (r0 + k < r1)
+#pragma unroll
+            for (int v = 0; v < NV; v++) bits[k][v] = ld_sys_u64(p2p_recv(X, X.rank, par, r0 + k, v, e));
+    long long t0 = 0;
+    bool timing = false;
+#pragma unroll
+    for (int k = 0; k < P2P_MAX_RANKS; k++)
+        if (r0 + k < r1)
+#pragma unroll
+            for (int v = 0; v < NV; v++) {
+                unsigned long long *slot = p2p_recv(X, X.rank, par, r0 + k, v, e);
+                while (bits[k][v] == P2P_SENTINEL) {
+                    if (!timing) {
+                        timing = true;
+                        t0 = clock64();
+                    } else if (clock64() - t0 > P2P_TIMEOUT_CYCLES) {
+                        atomicExch(X.error, 1u);
+                        bits[k][v] = P2P_CANONICAL_NAN;
+                        break;
+                    }
+                    bits[k][v] = ld_sys_u64(slot);
+                }
+                asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(slot), "l"(P2P_SENTINEL) : "memory");
+                out[k][v] = __longlong_as_double((long long)bits[k][v]);
+            }
+}
+// Sum over ranks (rank order) of the NV values of column entry e.
+template <int NV>
+__device__ __forceinline__ void p2p_poll_sum(const P2PView &X, int par, int64_t e, double (&acc)[NV])
+{
+    double t[P2P_MAX_RANKS][NV];
+    p2p_poll<NV>(X, par, e, 0, X.nranks, t);
 #pragma unroll
     for (int v = 0; v < NV; v++) acc[v] = 0.0;
-    for (int r0 = 0; r0 < X.nranks; r0 += 8) {
-        double t[8][NV];
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            if (r0 + k < X.nranks) {
-                const double *src =
-                    reinterpret_cast<const double *>(X.peer[r0 + k] + X.buf_off) + (size_t)par * X.slot_doubles + off;
-#pragma unroll
-                for (int v = 0; v < NV; v++) t[k][v] = ld_sys_f64(src + (size_t)v * vstride);
-            } else {
-#pragma unroll
-                for (int v = 0; v < NV; v++) t[k][v] = 0.0;
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 8; k++)
+    for (int k = 0; k < P2P_MAX_RANKS; k++)
+        if (k < X.nranks)
 #pragma unroll
             for (int v = 0; v < NV; v++) acc[v] += t[k][v];
+}
+__device__ __forceinline__ int p2p_row_owner(const P2PView &X, int64_t row)
+{
+    int owner = -1;
+    for (int r = 0; r < X.nranks; r++)
+        if (row >= X.row_begin[r] && row < X.row_begin[r] + X.m_local[r]) owner = r;
+    return owner;
+}
+// the NV values of row entry `row` from its owner
+template <int NV>
+__device__ __forceinline__ void p2p_poll_row(const P2PView &X, int par, int64_t n_pad, int64_t row, double (&val)[NV])
+{
+    const int owner = p2p_row_owner(X, row);
+    if (owner < 0) {
+#pragma unroll
+        for (int v = 0; v < NV; v++) val[v] = 0.0;
+        return;
+    }
+    double t[P2P_MAX_RANKS][NV];
+    p2p_poll<NV>(X, par, n_pad + row, owner, owner + 1, t);
+#pragma unroll
+    for (int v = 0; v < NV; v++) val[v] = t[0][v];
+}
+// push phase of one exchange: the thread's entries e0, e0 + stride, ... of [0, n_pad + m_pad)
+template <int NV>
+__device__ __forceinline__ void p2p_push_all(const MVView &V, const P2PView &X, int par, int64_t n, int64_t n_pad,
+                                             int64_t m_pad, int64_t e0, int64_t stride)
+{
+    const int64_t rb = X.row_begin[X.rank], ml = X.m_local[X.rank];
+    for (int64_t e = e0; e < n_pad + m_pad; e += stride) {
+        if (e < n_pad) {
+            if (e < n) {
+                if (NV == 2) {
+                    double w0, w1;
+                    mv_atw2(V, e, w0, w1);
+                    p2p_push(X, par, 0, e, w0);
+                    p2p_push(X, par, 1, e, w1);
+                } else {
+                    p2p_push(X, par, 0, e, mv_atw(V, 0, e));
+                }
+            }
+        } else {
+            const int64_t lr = e - n_pad - rb;
+            if (lr >= 0 && lr < ml) {
+                if (NV == 2) {
+                    double a0, a1;
+                    mv_ax2(V, lr, a0, a1);
+                    p2p_push(X, par, 0, e, a0);
+                    p2p_push(X, par, 1, e, a1);
+                } else {
+                    p2p_push(X, par, 0, e, mv_ax(V, 0, lr));
+                }
+            }
+        }
     }
 }
 
@@ -991,76 +1063,33 @@ k1_exchange_p2p(MVView V, P2PView X, int64_t n, int64_t n_pad, int64_t m_pad, do
                 const int32_t *skip_flag)
 {
     if (skip_flag != nullptr && *skip_flag != 0) return;
-    __shared__ bool s_last;
     const unsigned int epoch = *X.epoch + 1u;
     const int par = (int)(epoch & 1u);
     const int64_t total = n_pad + m_pad;
-    double *mine = reinterpret_cast<double *>(X.peer[X.rank] + X.buf_off) + (size_t)par * X.slot_doubles;
-    const int64_t rb = X.row_begin[X.rank], ml = X.m_local[X.rank];
-    // ---- phase 1: local fold ----
-    for (int64_t e = (int64_t)blockIdx.x * VBLOCK + threadIdx.x; e < total; e += (int64_t)gridDim.x * VBLOCK) {
+    const int64_t e0 = (int64_t)blockIdx.x * VBLOCK + threadIdx.x, stride = (int64_t)gridDim.x * VBLOCK;
+    p2p_push_all<NV>(V, X, par, n, n_pad, m_pad, e0, stride);
+    for (int64_t e = e0; e < total; e += stride) {
+        double val[NV];
 #pragma unroll
-        for (int v = 0; v < NV; v++) {
-            if (e < n_pad) {
-                mine[(size_t)v * n_pad + e] = e < n ? mv_atw(V, v, e) : 0.0;
-            } else {
-                const int64_t row = e - n_pad, lr = row - rb;
-                if (lr >= 0 && lr < ml) mine[(size_t)NV * n_pad + (size_t)v * m_pad + row] = mv_ax(V, v, lr);
-            }
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence_system();  // cumulative: publishes the whole block's slot writes
-        const unsigned int t = atomicAdd(&X.tickets[0], 1u);
-        s_last = (t == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (s_last) {
-        __threadfence_system();
-        if (threadIdx.x < X.nranks)
-            st_release_sys_u32(reinterpret_cast<unsigned int *>(X.peer[threadIdx.x] + X.flags_off) +
-                                   (size_t)X.rank * P2P_FLAG_STRIDE,
-                               epoch);
-    }
-    // ---- phase 2: wait for every rank, gather ----
-    if (threadIdx.x < X.nranks) {
-        const unsigned int *f = reinterpret_cast<const unsigned int *>(X.peer[X.rank] + X.flags_off) +
-                                (size_t)threadIdx.x * P2P_FLAG_STRIDE;
-        p2p_wait_flag(f, epoch, X.error);
-    }
-    __syncthreads();
-    for (int64_t e = (int64_t)blockIdx.x * VBLOCK + threadIdx.x; e < total; e += (int64_t)gridDim.x * VBLOCK) {
+        for (int v = 0; v < NV; v++) val[v] = 0.0;
         if (e < n_pad) {
-            double acc[NV];
-            p2p_gather_sum<NV>(X, par, e, n_pad, acc);
+            if (e < n) p2p_poll_sum<NV>(X, par, e, val);
 #pragma unroll
-            for (int v = 0; v < NV; v++) xbuf[(size_t)v * n_pad + e] = acc[v];
+            for (int v = 0; v < NV; v++) xbuf[(size_t)v * n_pad + e] = val[v];
         } else {
             const int64_t row = e - n_pad;
-            int owner = -1;
-            for (int r = 0; r < X.nranks; r++)
-                if (row >= X.row_begin[r] && row < X.row_begin[r] + X.m_local[r]) owner = r;
+            p2p_poll_row<NV>(X, par, n_pad, row, val);
 #pragma unroll
-            for (int v = 0; v < NV; v++) {
-                double val = 0.0;
-                if (owner >= 0) {
-                    const double *src =
-                        reinterpret_cast<const double *>(X.peer[owner] + X.buf_off) + (size_t)par * X.slot_doubles;
-                    val = ld_sys_f64(src + (size_t)NV * n_pad + (size_t)v * m_pad + row);
-                }
-                xbuf[(size_t)NV * n_pad + (size_t)v * m_pad + row] = val;
-            }
+            for (int v = 0; v < NV; v++) xbuf[(size_t)NV * n_pad + (size_t)v * m_pad + row] = val[v];
         }
     }
-    // ---- exit: the last block advances the epoch and re-arms the tickets ----
+    // ---- exit: the last block advances the epoch and re-arms the ticket ----
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
-        const unsigned int t = atomicAdd(&X.tickets[1], 1u);
+        const unsigned int t = atomicAdd(&X.tickets[0], 1u);
         if (t == gridDim.x - 1) {
             X.tickets[0] = 0u;
-            X.tickets[1] = 0u;
             *X.epoch = epoch;
             __threadfence();
         }
@@ -1085,7 +1114,18 @@ struct GridBar {
     unsigned int *base;   // value of *count when the current launch started
     unsigned int *exit_ticket;
     double *part;         // [2][gridDim.x][8] block partials of the two reductions
+    unsigned long long *trace;  // optional ("tail_trace"): [3 blocks][16] summed SM cycles per phase, [..][15] = launches
 };
+// phase timing of the fused CG tail (debug option "tail_trace"): thread 0 of the first, middle and last block adds
+// the SM cycles since its previous mark to trace[block slot][phase]
+#define FOS_TAIL_MARK(PH)                                                                \
+    do {                                                                                 \
+        if (tr_slot >= 0) {                                                              \
+            const long long tnow_ = clock64();                                           \
+            atomicAdd(gb.trace + tr_slot * 16 + (PH), (unsigned long long)(tnow_ - tr_last)); \
+            tr_last = tnow_;                                                             \
+        }                                                                                \
+    } while (0)
 __device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int *p)
 {
     unsigned int v;
@@ -1175,6 +1215,12 @@ k_cg_tail_hsde(Lay L, MVView V, P2PView X, const double *__restrict__ c, const d
                Ctrl *ctrl, GridBar gb)
 {
     if (cg_skip(ctrl)) return;
+    int tr_slot = -1;
+    long long tr_last = 0;
+    if (gb.trace != nullptr && threadIdx.x == 0) {
+        tr_slot = blockIdx.x == 0 ? 0 : (blockIdx.x == gridDim.x / 2 ? 1 : (blockIdx.x == gridDim.x - 1 ? 2 : -1));
+        tr_last = clock64();
+    }
     const unsigned int base = *gb.base;
     unsigned int nbar = 0;
     const int64_t LP = L.LP, oy = L.n_pad, ot = L.n_pad + L.m_pad;
@@ -1184,66 +1230,11 @@ k_cg_tail_hsde(Lay L, MVView V, P2PView X, const double *__restrict__ c, const d
     unsigned int epoch = 0;
     int par = 0;
     if (P2P) {
-        // ---- exchange, phase 1: fold the local partials into this rank's slot, publish, wait for the peers ----
+        // ---- exchange, push phase: fold the local partials, store them into every rank's receive area ----
         epoch = *X.epoch + 1u;
         par = (int)(epoch & 1u);
-        double *mine = reinterpret_cast<double *>(X.peer[X.rank] + X.buf_off) + (size_t)par * X.slot_doubles;
-        const int64_t rb = X.row_begin[X.rank], ml = X.m_local[X.rank];
-        for (int64_t e = e0; e < ot; e += stride) {
-            if (e < oy) {
-                double w0 = 0.0, w1 = 0.0;
-                if (e < L.n) mv_atw2(V, e, w0, w1);
-                mine[e] = w0;
-                mine[(size_t)L.n_pad + e] = w1;
-            } else {
-                const int64_t row = e - oy, lr = row - rb;
-                if (lr >= 0 && lr < ml) {
-                    double a0, a1;
-                    mv_ax2(V, lr, a0, a1);
-                    mine[(size_t)2 * L.n_pad + row] = a0;
-                    mine[(size_t)2 * L.n_pad + (size_t)L.m_pad + row] = a1;
-                }
-            }
-        }
-        // Block i of every rank owns the same entries, so the hand-shake is block to block: publish this
-        // block's part of the slot to every peer, wait for the same block of every peer.
-        if (X.tail_flag_mode == 0) {
-            __syncthreads();
-            if (threadIdx.x == 0) __threadfence_system();  // cumulative: the whole block's slot writes
-            __syncthreads();
-            if (threadIdx.x < X.nranks) {
-                st_release_sys_u32(reinterpret_cast<unsigned int *>(X.peer[threadIdx.x] + X.bflags_off) +
-                                       (size_t)X.rank * P2P_MAX_BLOCKS + blockIdx.x,
-                                   epoch);
-                const unsigned int *f = reinterpret_cast<const unsigned int *>(X.peer[X.rank] + X.bflags_off) +
-                                        (size_t)threadIdx.x * P2P_MAX_BLOCKS + blockIdx.x;
-                p2p_wait_flag(f, epoch, X.error);
-            }
-            __syncthreads();
-        } else {
-            // one flag per rank: the last block of this rank to finish its fold publishes for the whole rank
-            __shared__ bool s_last;
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                __threadfence_system();
-                s_last = (atomicAdd(&X.tickets[0], 1u) == gridDim.x - 1);
-            }
-            __syncthreads();
-            if (s_last) {
-                if (threadIdx.x == 0) __threadfence_system();
-                __syncthreads();
-                if (threadIdx.x < X.nranks)
-                    st_release_sys_u32(reinterpret_cast<unsigned int *>(X.peer[threadIdx.x] + X.flags_off) +
-                                           (size_t)X.rank * P2P_FLAG_STRIDE,
-                                       epoch);
-            }
-            if (threadIdx.x < X.nranks) {
-                const unsigned int *f = reinterpret_cast<const unsigned int *>(X.peer[X.rank] + X.flags_off) +
-                                        (size_t)threadIdx.x * P2P_FLAG_STRIDE;
-                p2p_wait_flag(f, epoch, X.error);
-            }
-            __syncthreads();
-        }
+        p2p_push_all<2>(V, X, par, L.n, L.n_pad, L.m_pad, e0, stride);
+        FOS_TAIL_MARK(0);  // fold + push
     }
     // ---- Ap = [I Q'; Q -I] p and the dot products (k2_kkt_hsde<K2_AP>) ----
     const double tau1 = p[ot], tau2 = p[LP + ot];
@@ -1256,7 +1247,7 @@ k_cg_tail_hsde(Lay L, MVView V, P2PView X, const double *__restrict__ c, const d
                 double w0, w1;
                 if (P2P) {
                     double acc[2];
-                    p2p_gather_sum<2>(X, par, e, L.n_pad, acc);
+                    p2p_poll_sum<2>(X, par, e, acc);
                     w0 = acc[0];
                     w1 = acc[1];
                 } else {
@@ -1275,13 +1266,10 @@ k_cg_tail_hsde(Lay L, MVView V, P2PView X, const double *__restrict__ c, const d
             if (i < L.m) {
                 double a0, a1;
                 if (P2P) {
-                    int owner = 0;
-                    for (int rk = 0; rk < X.nranks; rk++)
-                        if (i >= X.row_begin[rk] && i < X.row_begin[rk] + X.m_local[rk]) owner = rk;
-                    const double *src =
-                        reinterpret_cast<const double *>(X.peer[owner] + X.buf_off) + (size_t)par * X.slot_doubles;
-                    a0 = ld_sys_f64(src + 2 * L.n_pad + i);
-                    a1 = ld_sys_f64(src + 2 * L.n_pad + L.m_pad + i);
+                    double av[2];
+                    p2p_poll_row<2>(X, par, L.n_pad, i, av);
+                    a0 = av[0];
+                    a1 = av[1];
                 } else {
                     mv_ax2(V, i, a0, a1);
                 }
@@ -1299,7 +1287,9 @@ k_cg_tail_hsde(Lay L, MVView V, P2PView X, const double *__restrict__ c, const d
         q[4] = fma(o1, i1, q[4]);
         q[4] = fma(o2, i2, q[4]);
     }
+    FOS_TAIL_MARK(3);  // gather / fold + Ap
     grid_allreduce<5>(q, gb.part, gb, nbar, base);
+    FOS_TAIL_MARK(4);  // first grid all-reduce
     const double q1t = sub_(-q[0], q[1]);  // HSDEAffine.jl:57
     const double q2t = sub_(-q[2], q[3]);
     const double o1t = add_(-q2t, tau1);
@@ -1334,7 +1324,9 @@ k_cg_tail_hsde(Lay L, MVView V, P2PView X, const double *__restrict__ c, const d
             }
         }
     }
+    FOS_TAIL_MARK(5);  // x, r update
     grid_allreduce<1>(q2r, gb.part + (size_t)gridDim.x * 8, gb, nbar, base);
+    FOS_TAIL_MARK(6);  // second grid all-reduce
     const double rr = q2r[0];
     const double rnorm = sqrt(rr);
     const bool stop = rnorm <= tol || iter >= max_iters;  // cg :42
@@ -1377,6 +1369,8 @@ k_cg_tail_hsde(Lay L, MVView V, P2PView X, const double *__restrict__ c, const d
             ctrl->iter = iter + 1;
         }
     }
+    FOS_TAIL_MARK(7);  // direction update
+    if (tr_slot >= 0) atomicAdd(gb.trace + tr_slot * 16 + 15, 1ull);
     // ---- exit: the last block re-arms the barrier base (and the exchange epoch / tickets) ----
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -1384,10 +1378,7 @@ k_cg_tail_hsde(Lay L, MVView V, P2PView X, const double *__restrict__ c, const d
         if (atomicAdd(gb.exit_ticket, 1u) == gridDim.x - 1) {
             *gb.exit_ticket = 0u;
             *gb.base = base + nbar * gridDim.x;
-            if (P2P) {
-                X.tickets[0] = 0u;
-                *X.epoch = epoch;
-            }
+            if (P2P) *X.epoch = epoch;
             __threadfence();
         }
     }

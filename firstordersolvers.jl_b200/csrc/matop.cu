@@ -333,14 +333,9 @@ MatOp::~MatOp()
 }
 
 // ---------------------------------------------------------------------------------------
-// fused exchange over peer memory: region = header | flags[nranks] | slot[2]
+// fused exchange over peer memory: region = header | receive area [2 parities][nranks sources][2 vectors][n_pad+m_pad]
 // ---------------------------------------------------------------------------------------
-static int64_t p2p_flags_off() { return (int64_t)sizeof(P2PHeader); }
-static int64_t p2p_bflags_off(int nranks) { return ru(p2p_flags_off() + (int64_t)nranks * P2P_FLAG_STRIDE * 4, 256); }
-static int64_t p2p_buf_off(int nranks)
-{
-    return ru(p2p_bflags_off(nranks) + (int64_t)nranks * P2P_MAX_BLOCKS * 4, 256);
-}
+static int64_t p2p_recv_off() { return ru((int64_t)sizeof(P2PHeader), 256); }
 
 void MatOp::p2p_export(uint8_t *handle_out)
 {
@@ -349,9 +344,12 @@ void MatOp::p2p_export(uint8_t *handle_out)
     FOS_REQUIRE(nranks <= P2P_MAX_RANKS, "too many ranks for the peer-memory exchange");
     static_assert(sizeof(cudaIpcMemHandle_t) == FOS_IPC_HANDLE_BYTES, "IPC handle size");
     p2p_close();
-    const int64_t slot = 2 * (n_pad + m_pad);
-    const size_t bytes = (size_t)p2p_buf_off(nranks) + (size_t)2 * slot * 8;
-    p2p_region.alloc(bytes);  // zeroed
+    const size_t recv_bytes = (size_t)2 * nranks * 2 * (size_t)(n_pad + m_pad) * 8;
+    const size_t bytes = (size_t)p2p_recv_off() + recv_bytes;
+    p2p_region.alloc(bytes, false);
+    // every receive slot starts as the sentinel (all ones): "nothing has arrived"
+    FOS_CUDA(cudaMemset(p2p_region.p, 0xFF, bytes));
+    FOS_SYNC_LEGACY();
     P2PHeader hd;
     memset(&hd, 0, sizeof(hd));
     hd.row_begin = row_begin;
@@ -372,10 +370,8 @@ void MatOp::p2p_import(const uint8_t *handles)
     p2p.tail_flag_mode = keep_mode;
     p2p.nranks = nranks;
     p2p.rank = rank;
-    p2p.flags_off = p2p_flags_off();
-    p2p.buf_off = p2p_buf_off(nranks);
-    p2p.bflags_off = p2p_bflags_off(nranks);
-    p2p.slot_doubles = 2 * (n_pad + m_pad);
+    p2p.recv_off = p2p_recv_off();
+    p2p.E = n_pad + m_pad;
     p2p.epoch = p2p_local.p;
     p2p.tickets = p2p_local.p + 1;
     p2p.error = p2p_local.p + 3;

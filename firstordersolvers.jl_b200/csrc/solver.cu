@@ -42,6 +42,7 @@ void Handle::create(int dev)
     gbar.exit_ticket = gb_ctr.p + 2;
     gbar.flag = gb_ctr.p + 64;
     gbar.part = gb_part.p;
+    gbar.trace = nullptr;
 }
 
 Handle::~Handle()

@@ -284,6 +284,7 @@ struct Handle {
     DevBuf<unsigned int> gb_ctr;  // fused CG tail: grid-barrier counters {count, base, exit ticket}
     DevBuf<double> gb_part;
     GridBar gbar{};
+    DevBuf<unsigned long long> tail_trace;  // option "tail_trace": [3][16] phase cycle sums of k_cg_tail_hsde
     int tail_occ[2] = {0, 0};  // co-resident blocks per SM of k_cg_tail_hsde<false / true> (queried once)
     int tail_grid = 0;
     DevBuf<double> d_recs;

@@ -365,6 +365,13 @@ class _Handle:
         self.ck(self.L.fos_time_psd(self.h, d, nc, _d(X), _d(Y), int(reps), C.byref(ms), C.byref(sw)))
         return Y, ms.value, int(sw.value)
 
+    def tail_trace(self):
+        """Phase timing of the fused CG tail (option "tail_trace" = 1): (3 blocks, 16) summed SM cycles;
+        column 15 = launches counted (fos_get_tail_trace)."""
+        out = np.zeros(48)
+        self.ck(self.L.fos_get_tail_trace(self.h, _d(out)))
+        return out.reshape(3, 16)
+
     def time_matvec(self, nvec=2, reps=10):
         ms = C.c_double(0)
         by = C.c_double(0)

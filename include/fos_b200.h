@@ -113,6 +113,7 @@ const char *fos_last_error(fos_handle_t h);
  *   "batch_hybrid" 1 (default) = batch mode keeps rows with <= n/8 non-zeros out of the dense tiles (CSR + CSC) and
  *                  skips empty rows; 0 = every row is streamed as dense FP64.  Set before loading the batch.
  *   "batch_ctas"   persistent CTAs of the batch kernel (default = #SMs)
+ *   "tail_trace"   1 = the fused CG tail records the SM cycles of each of its phases (fos_get_tail_trace)
  *   "use_graphs"   reserved                                                                */
 int32_t fos_set_option(fos_handle_t h, const char *key, double value);
 
@@ -323,6 +324,11 @@ int32_t fos_get_stream(fos_handle_t h, uint64_t *stream_out);
 /* Times `reps` launches of the fused dual mat-vec (nvec = 1 or 2 right-hand sides per
  * direction) on the loaded matrix with CUDA events on the library's stream; returns the
  * average milliseconds per launch and the algorithmic bytes one launch streams. */
+/* With the option "tail_trace" = 1: summed SM cycles per phase of the fused CG-tail kernel, for its first, middle
+ * and last block: out[16*b + k], k = 0 fold of the local partials, 1 block sync + system fence, 2 flags published
+ * and peers seen (0..2 only with the peer-memory exchange), 3 gather + KKT epilogue, 4 first grid all-reduce,
+ * 5 x / r update, 6 second grid all-reduce, 7 direction update; out[16*b + 15] = launches counted. */
+int32_t fos_get_tail_trace(fos_handle_t h, double *out /* 48 */);
 int32_t fos_time_matvec(fos_handle_t h, int32_t nvec, int32_t reps, double *ms_per_launch, double *bytes_per_launch);
 /* Times `reps` projections of `ncones` packed symmetric matrices of order d (x: ncones * d(d+1)/2
  * doubles, host) onto the PSD cone (IndPSD(scaling=true), cones.jl:11) with CUDA events on the library's

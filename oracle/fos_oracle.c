@@ -22,6 +22,17 @@
  *
  * Single-threaded by construction: the reference's mat-vecs and broadcasts are serial
  * (SURVEY.md F6).
+ *
+ * Build variants of this one file (oracle/Makefile):
+ *   libfos_oracle.so      the restatement proper: FP64 throughout, sequential sums in the reference's order.
+ *   libfos_oracle_hp.so   -DFOS_ORACLE_HP: every REDUCTION (dot, norm, the sums of a sparse product) is
+ *                         accumulated in long double (64-bit mantissa) and rounded to FP64 once; element-wise
+ *                         operations round exactly like the restatement.  This is the "exact" yardstick of the
+ *                         parity tests: the distance of any FP64 implementation from it is that implementation's
+ *                         own accumulated summation error (tests/test_gpu_exact.py).
+ *   libfos_oracle_mt.so   -DFOS_ORACLE_MT -fopenmp: the sparse products and the CG sweeps are spread over the
+ *                         host threads (bench.py --impl reference: "with all the host threads it can use").
+ *                         Same algorithm, different summation order; used for TIMING only, never as a checker.
  */
 #include <math.h>
 #include <stdint.h>
@@ -30,6 +41,18 @@
 #include <string.h>
 
 #define FOSOR_API __attribute__((visibility("default")))
+
+#ifdef FOS_ORACLE_HP
+typedef long double acc_t; /* accumulator of every reduction */
+#else
+typedef double acc_t;
+#endif
+#ifdef FOS_ORACLE_MT
+#include <omp.h>
+#define PFOR _Pragma("omp parallel for schedule(static)")
+#else
+#define PFOR
+#endif
 
 /* ------------------------------------------------------------------------------------
  * cone type codes (cones.jl:4-14, conemap)
@@ -57,9 +80,16 @@ enum { ST_CONTINUE = 0, ST_OPTIMAL = 1, ST_UNBOUNDED = 2, ST_INFEASIBLE = 3, ST_
  * ---------------------------------------------------------------------------------- */
 static double vdot(const double *a, const double *b, int64_t n)
 {
-    double s = 0.0;
-    for (int64_t i = 0; i < n; i++) s += a[i] * b[i];
-    return s;
+#ifdef FOS_ORACLE_MT
+    double sm = 0.0;
+#pragma omp parallel for schedule(static) reduction(+ : sm)
+    for (int64_t i = 0; i < n; i++) sm += a[i] * b[i];
+    return sm;
+#else
+    acc_t s = 0.0;
+    for (int64_t i = 0; i < n; i++) s += (acc_t)a[i] * (acc_t)b[i];
+    return (double)s;
+#endif
 }
 static double vnorm(const double *a, int64_t n) { return sqrt(vdot(a, a, n)); }
 
@@ -71,6 +101,7 @@ typedef struct {
     int64_t *colptr; /* n+1 */
     int64_t *rowval; /* nnz */
     double *nzval;   /* nnz */
+    int borrowed;    /* arrays belong to the caller (fosor_create_conic_borrowed: no 12.8 GB copy at config 2) */
 } csc_t;
 
 static csc_t *csc_new(int64_t m, int64_t n, const int64_t *colptr, const int64_t *rowval,
@@ -90,31 +121,78 @@ static csc_t *csc_new(int64_t m, int64_t n, const int64_t *colptr, const int64_t
     }
     return A;
 }
+static csc_t *csc_borrow(int64_t m, int64_t n, int64_t *colptr, int64_t *rowval, double *nzval)
+{
+    csc_t *A = (csc_t *)calloc(1, sizeof(csc_t));
+    A->m = m;
+    A->n = n;
+    A->colptr = colptr; /* 0-based */
+    A->rowval = rowval;
+    A->nzval = nzval;
+    A->borrowed = 1;
+    return A;
+}
 static void csc_free(csc_t *A)
 {
     if (!A) return;
-    free(A->colptr);
-    free(A->rowval);
-    free(A->nzval);
+    if (!A->borrowed) {
+        free(A->colptr);
+        free(A->rowval);
+        free(A->nzval);
+    }
     free(A);
 }
 
 /* y = A*x, Julia SparseArrays.mul!(y, A, x): zero y, then scatter column by column. */
 static void csc_mul(double *y, const csc_t *A, const double *x)
 {
+#if defined(FOS_ORACLE_MT)
+    /* column ranges per thread, private result vectors, added in thread order */
+    const int64_t m = A->m, n = A->n;
+    int nt = omp_get_max_threads();
+    double *priv = (double *)calloc((size_t)nt * (size_t)(m > 0 ? m : 1), sizeof(double));
+#pragma omp parallel num_threads(nt)
+    {
+        const int t = omp_get_thread_num();
+        double *yt = priv + (size_t)t * (size_t)m;
+        const int64_t j0 = n * t / nt, j1 = n * (t + 1) / nt;
+        for (int64_t j = j0; j < j1; j++) {
+            const double xj = x[j];
+            for (int64_t k = A->colptr[j]; k < A->colptr[j + 1]; k++) yt[A->rowval[k]] += A->nzval[k] * xj;
+        }
+#pragma omp barrier
+#pragma omp for schedule(static)
+        for (int64_t i = 0; i < m; i++) {
+            double sm = 0.0;
+            for (int q = 0; q < nt; q++) sm += priv[(size_t)q * (size_t)m + (size_t)i];
+            y[i] = sm;
+        }
+    }
+    free(priv);
+#elif defined(FOS_ORACLE_HP)
+    acc_t *acc = (acc_t *)calloc((size_t)(A->m > 0 ? A->m : 1), sizeof(acc_t));
+    for (int64_t j = 0; j < A->n; j++) {
+        acc_t xj = x[j];
+        for (int64_t k = A->colptr[j]; k < A->colptr[j + 1]; k++) acc[A->rowval[k]] += (acc_t)A->nzval[k] * xj;
+    }
+    for (int64_t i = 0; i < A->m; i++) y[i] = (double)acc[i];
+    free(acc);
+#else
     for (int64_t i = 0; i < A->m; i++) y[i] = 0.0;
     for (int64_t j = 0; j < A->n; j++) {
         double xj = x[j];
         for (int64_t k = A->colptr[j]; k < A->colptr[j + 1]; k++) y[A->rowval[k]] += A->nzval[k] * xj;
     }
+#endif
 }
 /* y = A'*x, Julia SparseArrays.mul!(y, transpose(A), x): one dot product per column. */
 static void csc_mul_t(double *y, const csc_t *A, const double *x)
 {
+    PFOR
     for (int64_t j = 0; j < A->n; j++) {
-        double t = 0.0;
-        for (int64_t k = A->colptr[j]; k < A->colptr[j + 1]; k++) t += A->nzval[k] * x[A->rowval[k]];
-        y[j] = t;
+        acc_t t = 0.0;
+        for (int64_t k = A->colptr[j]; k < A->colptr[j + 1]; k++) t += (acc_t)A->nzval[k] * (acc_t)x[A->rowval[k]];
+        y[j] = (double)t;
     }
 }
 
@@ -140,8 +218,11 @@ static void hsdeq_mul(double *Y, const linop_t *Q, const double *B)
     double b3 = B[n + m];
     csc_mul_t(y1, A, b2);                                      /* :51 */
     csc_mul(y2, A, b1);                                        /* :52 */
+    PFOR
     for (int64_t j = 0; j < n; j++) y1[j] += b3 * Q->c[j];     /* :54 */
+    PFOR
     for (int64_t i = 0; i < m; i++) y2[i] -= b3 * Q->b[i];     /* :55 */
+    PFOR
     for (int64_t i = 0; i < m; i++) y2[i] = -y2[i];            /* :56 */
     Y[n + m] = -vdot(Q->c, b1, n) - vdot(Q->b, b2, m);         /* :57 */
 }
@@ -158,6 +239,7 @@ static void linop_mul_t(double *y, const linop_t *Op, const double *x)
     if (Op->kind == 0) csc_mul_t(y, Op->A, x);
     else {
         hsdeq_mul(y, Op, x);
+        PFOR
         for (int64_t i = 0; i < Op->an; i++) y[i] = -y[i];
     }
 }
@@ -169,8 +251,10 @@ static void kkt_mul(double *y, const linop_t *Op, const double *x)
     const double *x1 = x, *x2 = x + an;
     double *y1 = y, *y2 = y + an;
     linop_mul_t(y1, Op, x2);                               /* :45 */
+    PFOR
     for (int64_t i = 0; i < an; i++) y1[i] += x1[i];       /* :46 */
     linop_mul(y2, Op, x1);                                 /* :47 */
+    PFOR
     for (int64_t i = 0; i < am; i++) y2[i] -= x2[i];       /* :48 */
 }
 
@@ -191,20 +275,26 @@ static int64_t conjgrad(double *x, mulfn_t mul, const void *ctx, const double *b
                         double *Ap, int64_t N, double tol, int64_t max_iters)
 {
     mul(Ap, ctx, x);                                         /* :32 */
+    PFOR
     for (int64_t i = 0; i < N; i++) r[i] = b[i] - Ap[i];     /* :33 */
+    PFOR
     for (int64_t i = 0; i < N; i++) p[i] = r[i];             /* :34 */
     double rn = vdot(r, r, N);                               /* :35 */
     int64_t iter = 1;                                        /* :36 */
     for (;;) {
         mul(Ap, ctx, p);                                     /* :38 */
         double alpha = rn / vdot(Ap, p, N);                  /* :39 */
+        PFOR
         for (int64_t i = 0; i < N; i++) x[i] += alpha * p[i];   /* :40 */
+        PFOR
         for (int64_t i = 0; i < N; i++) r[i] -= alpha * Ap[i];  /* :41 */
         if (vnorm(r, N) <= tol || iter >= max_iters) break;  /* :42 */
         double rnold = rn;                                   /* :45 */
         rn = vdot(r, r, N);                                  /* :46 */
         double beta = rn / rnold;                            /* :47 */
+        PFOR
         for (int64_t i = 0; i < N; i++) p[i] *= beta;        /* :49 */
+        PFOR
         for (int64_t i = 0; i < N; i++) p[i] += r[i];        /* :50 */
         iter += 1;                                           /* :51 */
     }
@@ -700,6 +790,74 @@ FOSOR_API void *fosor_create_conic(int64_t m, int64_t n, const int64_t *colptr, 
 }
 
 /* Feasibility(S1 = AffinePlusLinear(A,b,q,beta; decreasing_accuracy), S2 = ConeProduct, N = an+am) */
+/* Same model on CSC arrays that stay with the caller (0-based, must outlive the model): a dense 20000 x 40000
+ * matrix is 12.8 GB as SparseMatrixCSC{Float64,Int64} (types.jl:35) and is not copied a second time. */
+FOSOR_API void *fosor_create_conic_borrowed(int64_t m, int64_t n, int64_t *colptr, int64_t *rowval, double *nzval,
+                                            const double *b, const double *c, int64_t nc1, const int32_t *types1,
+                                            const int64_t *lens1, int64_t nc2, const int32_t *types2,
+                                            const int64_t *lens2)
+{
+    model_t *M = (model_t *)calloc(1, sizeof(model_t));
+    M->form = 0;
+    M->A = csc_borrow(m, n, colptr, rowval, nzval);
+    M->b = (double *)malloc(sizeof(double) * (size_t)(m > 0 ? m : 1));
+    M->c = (double *)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+    memcpy(M->b, b, sizeof(double) * (size_t)m);
+    memcpy(M->c, c, sizeof(double) * (size_t)n);
+    M->K1 = coneprod_new(nc1, types1, lens1);
+    M->K2 = coneprod_new(nc2, types2, lens2);
+    if (M->K1.total != m || M->K2.total != n) {
+        csc_free(M->A); free(M->b); free(M->c); coneprod_free(&M->K1); coneprod_free(&M->K2); free(M);
+        return NULL;
+    }
+    linop_t Q;
+    Q.kind = 1; Q.A = M->A; Q.b = M->b; Q.c = M->c; Q.am = m + n + 1; Q.an = m + n + 1;
+    M->S1 = apl_new(Q, NULL, NULL, 1, 1);
+    M->N = 2 * (m + n + 1);
+    model_alloc_vectors(M);
+    int64_t l = m + n + 1;
+    M->x[l - 1] = 1.0;
+    M->x[2 * l - 1] = 1.0;
+    return M;
+}
+
+/* Synthetic dense matrix of bench.py's config 2 written straight into CSC arrays (every entry stored, row
+ * indices 0..m-1 per column): A[i,j] = scale * N(0,1), counter-based generator (splitmix64 + Box-Muller) so that
+ * the fill can run on all host threads.  Not part of the reference: input synthesis for the CPU baseline. */
+static inline uint64_t splitmix64(uint64_t x)
+{
+    x += 0x9E3779B97F4A7C15ULL;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+    return x ^ (x >> 31);
+}
+FOSOR_API void fosor_gen_dense_csc(int64_t m, int64_t n, uint64_t seed, double scale, int64_t *colptr,
+                                   int64_t *rowval, double *nzval)
+{
+    for (int64_t j = 0; j <= n; j++) colptr[j] = j * m;
+    PFOR
+    for (int64_t j = 0; j < n; j++) {
+        for (int64_t i = 0; i < m; i++) {
+            const uint64_t ctr = (uint64_t)(j * m + i);
+            const uint64_t u1 = splitmix64(seed * 0x100000001B3ULL + 2 * ctr);
+            const uint64_t u2 = splitmix64(seed * 0x100000001B3ULL + 2 * ctr + 1);
+            const double a = ((double)(u1 >> 11) + 1.0) * (1.0 / 9007199254740993.0); /* (0,1) */
+            const double b = (double)(u2 >> 11) * (1.0 / 9007199254740992.0);
+            nzval[j * m + i] = scale * sqrt(-2.0 * log(a)) * cos(6.283185307179586 * b);
+            rowval[j * m + i] = i;
+        }
+    }
+}
+/* y = A x (transpose = 0) or A' x (transpose = 1) on caller-owned 0-based CSC arrays */
+FOSOR_API void fosor_csc_mul(int64_t m, int64_t n, int64_t *colptr, int64_t *rowval, double *nzval, const double *x,
+                             double *y, int32_t transpose)
+{
+    csc_t A;
+    A.m = m; A.n = n; A.colptr = colptr; A.rowval = rowval; A.nzval = nzval; A.borrowed = 1;
+    if (transpose) csc_mul_t(y, &A, x);
+    else csc_mul(y, &A, x);
+}
+
 FOSOR_API void *fosor_create_feasibility(int64_t am, int64_t an, const int64_t *colptr, const int64_t *rowval,
                                          const double *nzval, int64_t index_base, const double *b,
                                          const double *q, int64_t beta, int32_t decreasing, int64_t nc,
@@ -800,6 +958,41 @@ FOSOR_API void fosor_get_state(void *h, int32_t which, double *out)
 {
     model_t *M = (model_t *)h;
     memcpy(out, state_ptr(M, which), sizeof(double) * (size_t)M->N);
+}
+/* Restores a persistent vector / scalar (lock-step tests put several restatements into one common state):
+ * which as in fosor_get_state; setting 3 (xinit) also clears S1's first-run flag (affinepluslinear.jl:101-104). */
+FOSOR_API void fosor_set_state(void *h, int32_t which, const double *in)
+{
+    model_t *M = (model_t *)h;
+    memcpy(state_ptr(M, which), in, sizeof(double) * (size_t)M->N);
+    if (which == 3) M->S1->firstrun = 0;
+}
+/* which: 0 S1.i, 2 alpha12, 3 FISTA t */
+FOSOR_API void fosor_set_scalar(void *h, int32_t which, double v)
+{
+    model_t *M = (model_t *)h;
+    if (which == 0) M->S1->i = (int64_t)v;
+    else if (which == 2) M->alpha12 = v;
+    else if (which == 3) M->fista_t = v;
+}
+/* 0 = restatement, 1 = long-double reductions (FOS_ORACLE_HP), 2 = threaded (FOS_ORACLE_MT) */
+FOSOR_API int32_t fosor_variant(void)
+{
+#if defined(FOS_ORACLE_HP)
+    return 1;
+#elif defined(FOS_ORACLE_MT)
+    return 2;
+#else
+    return 0;
+#endif
+}
+FOSOR_API int32_t fosor_threads(void)
+{
+#ifdef FOS_ORACLE_MT
+    return (int32_t)omp_get_max_threads();
+#else
+    return 1;
+#endif
 }
 FOSOR_API double fosor_get_fista_t(void *h) { return ((model_t *)h)->fista_t; }
 FOSOR_API int64_t fosor_get_s1_calls(void *h) { return ((model_t *)h)->S1->i; }
@@ -973,12 +1166,12 @@ static int checkstatus_feas(model_t *M, const double *z, int override)
 {
     int64_t N = M->N;
     if (M->cur_i % M->checki == 0 || override) {
-        double s = 0.0;
+        acc_t s = 0.0;
         for (int64_t i = 0; i < N; i++) {
             double dlt = M->prev[i] - z[i];
-            s += dlt * dlt;
+            s += (acc_t)dlt * (acc_t)dlt;
         }
-        double err = sqrt(s); /* :39 */
+        double err = sqrt((double)s); /* :39 */
         int status = ST_CONTINUE;
         if (err <= M->eps) status = ST_OPTIMAL; /* :55 */
         double rec[REC_LEN] = {(double)M->cur_i, err, 0, 0, 0, 0, 0, 0, (double)M->S1->cgiter, (double)status};
@@ -1025,14 +1218,15 @@ static void step_gapa(model_t *M)
     double *x = M->x, *t1 = M->tmp1, *t2 = M->tmp2;
     step_gap_like(M, a12, a12);
     /* normedScalar(tmp2,tmp1,tmp1,x) gapa.jl:36-47 */
-    double sum = 0.0, n1 = 0.0, n2 = 0.0;
+    acc_t sum_ = 0.0, n1_ = 0.0, n2_ = 0.0;
     for (int64_t i = 0; i < N; i++) {
         double d1 = t2[i] - t1[i];
         double d2 = t1[i] - x[i];
-        sum += d1 * d2;
-        n1 += d1 * d1;
-        n2 += d2 * d2;
+        sum_ += (acc_t)d1 * (acc_t)d2;
+        n1_ += (acc_t)d1 * (acc_t)d1;
+        n2_ += (acc_t)d2 * (acc_t)d2;
     }
+    double sum = (double)sum_, n1 = (double)n1_, n2 = (double)n2_;
     double scl = fabs(sum) / sqrt(n1 * n2);
     /* clamp(scl, 0, 1) :96 ; isnan -> 0 :97 (clamp propagates NaN) */
     if (scl < 0.0) scl = 0.0;

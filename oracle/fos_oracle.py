@@ -22,6 +22,9 @@ import scipy.sparse as sp
 
 HERE = Path(__file__).resolve().parent
 LIB_PATH = HERE / "libfos_oracle.so"
+# build variants of the one C file (see its header): "" the restatement proper, "hp" long-double reductions
+# (the "exact" yardstick of the parity tests), "mt" OpenMP over the sparse products (timing baseline only)
+VARIANTS = {"": "libfos_oracle.so", "hp": "libfos_oracle_hp.so", "mt": "libfos_oracle_mt.so"}
 
 CONE_CODES = {"Free": 0, "Zero": 1, "NonNeg": 2, "NonPos": 3, "SOC": 4, "SOCRotated": 5, "SDP": 6,
               "ExpPrimal": 7, "ExpDual": 8}
@@ -35,23 +38,36 @@ _ip = C.POINTER(C.c_int64)
 _i32p = C.POINTER(C.c_int32)
 
 
-def build(force: bool = False) -> Path:
-    """Compile ``libfos_oracle.so`` with the committed Makefile (gcc only)."""
+def build(force: bool = False, variant: str = "") -> Path:
+    """Compile ``libfos_oracle[_hp|_mt].so`` with the committed Makefile (gcc only)."""
     src = HERE / "fos_oracle.c"
-    if force or not LIB_PATH.exists() or LIB_PATH.stat().st_mtime < src.stat().st_mtime:
-        subprocess.run(["make", "-s", "-C", str(HERE), "libfos_oracle.so"], check=True)
-    return LIB_PATH
+    path = HERE / VARIANTS[variant]
+    if force or not path.exists() or path.stat().st_mtime < src.stat().st_mtime:
+        subprocess.run(["make", "-s", "-C", str(HERE), VARIANTS[variant]], check=True)
+    return path
 
 
-_lib = None
+def build_all(force: bool = False):
+    """All three variants; the threaded one is optional (needs libgomp) and its absence is reported, not fatal."""
+    out = {}
+    for v in VARIANTS:
+        try:
+            out[v] = build(force, v)
+        except subprocess.CalledProcessError:
+            if v != "mt":
+                raise
+            out[v] = None
+    return out
 
 
-def lib():
-    global _lib
-    if _lib is not None:
-        return _lib
-    build()
-    L = C.CDLL(str(LIB_PATH))
+_libs = {}
+
+
+def lib(variant: str = ""):
+    if variant in _libs:
+        return _libs[variant]
+    path = build(variant=variant)
+    L = C.CDLL(str(path))
     L.fosor_create_conic.restype = C.c_void_p
     L.fosor_create_conic.argtypes = [C.c_int64, C.c_int64, _ip, _ip, _dp, C.c_int64, _dp, _dp,
                                      C.c_int64, _i32p, _ip, C.c_int64, _i32p, _ip]
@@ -99,7 +115,16 @@ def lib():
     L.fosor_cg_csc.argtypes = [C.c_int64, _ip, _ip, _dp, C.c_int64, _dp, _dp, C.c_double, C.c_int64]
     L.fosor_prox_cone.restype = C.c_int32
     L.fosor_prox_cone.argtypes = [C.c_int32, C.c_int32, _dp, _dp, C.c_int64]
-    _lib = L
+    L.fosor_set_state.argtypes = [C.c_void_p, C.c_int32, _dp]
+    L.fosor_set_scalar.argtypes = [C.c_void_p, C.c_int32, C.c_double]
+    L.fosor_variant.restype = C.c_int32
+    L.fosor_threads.restype = C.c_int32
+    L.fosor_create_conic_borrowed.restype = C.c_void_p
+    L.fosor_create_conic_borrowed.argtypes = [C.c_int64, C.c_int64, _ip, _ip, _dp, _dp, _dp, C.c_int64, _i32p, _ip,
+                                              C.c_int64, _i32p, _ip]
+    L.fosor_gen_dense_csc.argtypes = [C.c_int64, C.c_int64, C.c_uint64, C.c_double, _ip, _ip, _dp]
+    L.fosor_csc_mul.argtypes = [C.c_int64, C.c_int64, _ip, _ip, _dp, _dp, _dp, C.c_int32]
+    _libs[variant] = L
     return L
 
 
@@ -140,63 +165,77 @@ def records_to_history(rec: np.ndarray) -> dict:
 
 
 class _OracleBase:
-    def __init__(self):
+    def __init__(self, variant=""):
         self._h = None
         self.N = 0
+        self.variant = variant
+        self._L = lib(variant)
 
     def __del__(self):
         try:
             if self._h:
-                lib().fosor_destroy(self._h)
+                self._L.fosor_destroy(self._h)
                 self._h = None
         except Exception:
             pass
 
+    _STATE = {"x": 0, "tmp1": 1, "tmp2": 2, "xinit": 3, "rhs": 4, "fista_y": 6, "dykstra_p": 7, "dykstra_q": 8}
+
+    def set_state(self, which, z):
+        """Restores a persistent vector ("xinit" also clears S1's first-run flag)."""
+        z = _f64(z)
+        assert z.shape == (self.N,)
+        self._L.fosor_set_state(self._h, self._STATE[which], _d(z))
+
+    def set_scalar(self, which, value):
+        """which: "s1_calls", "alpha12" or "fista_t"."""
+        self._L.fosor_set_scalar(self._h, {"s1_calls": 0, "alpha12": 2, "fista_t": 3}[which], float(value))
+
     # -- algorithm (a20) -------------------------------------------------------------
     def set_algorithm(self, name, alpha=0.8, alpha1=1.8, alpha2=1.8, beta=0.0, iproj=100):
-        lib().fosor_set_algorithm(self._h, ALG_CODES[name], alpha, alpha1, alpha2, beta, iproj)
+        self._L.fosor_set_algorithm(self._h, ALG_CODES[name], alpha, alpha1, alpha2, beta, iproj)
 
     def set_box(self, start, length, lo, hi):
         """IndBox(lo, hi) on entries [start, start+length) of the Feasibility iterate (0-based)."""
-        if lib().fosor_set_box(self._h, int(start), int(length), float(lo), float(hi)) != 0:
+        if self._L.fosor_set_box(self._h, int(start), int(length), float(lo), float(hi)) != 0:
             raise ValueError("bad box")
 
     def set_linesearch(self, lsinterval):
         """LineSearchWrapper(alg; lsinterval) (wrappers/linesearch.jl:19-24); 0 removes the wrapper."""
-        if lib().fosor_set_linesearch(self._h, int(lsinterval)) != 0:
+        if self._L.fosor_set_linesearch(self._h, int(lsinterval)) != 0:
             raise ValueError("bad lsinterval")
 
     def set_iterate(self, z):
         z = _f64(z)
         assert z.shape == (self.N,)
-        lib().fosor_set_iterate(self._h, _d(z))
+        self._L.fosor_set_iterate(self._h, _d(z))
 
     def get_iterate(self):
         z = np.empty(self.N)
-        lib().fosor_get_iterate(self._h, _d(z))
+        self._L.fosor_get_iterate(self._h, _d(z))
         return z
 
     def get_state(self, which):
         idx = {"x": 0, "tmp1": 1, "tmp2": 2, "xinit": 3, "rhs": 4, "fista_y": 6, "dykstra_p": 7, "dykstra_q": 8}[which]
         z = np.empty(self.N)
-        lib().fosor_get_state(self._h, idx, _d(z))
+        self._L.fosor_get_state(self._h, idx, _d(z))
         return z
 
     @property
     def s1_calls(self):
-        return lib().fosor_get_s1_calls(self._h)
+        return self._L.fosor_get_s1_calls(self._h)
 
     @property
     def cgiter(self):
-        return lib().fosor_get_cgiter(self._h)
+        return self._L.fosor_get_cgiter(self._h)
 
     @property
     def alpha12(self):
-        return lib().fosor_get_alpha12(self._h)
+        return self._L.fosor_get_alpha12(self._h)
 
     @property
     def fista_t(self):
-        return lib().fosor_get_fista_t(self._h)
+        return self._L.fosor_get_fista_t(self._h)
 
     def run(self, i_start, n_iters, checki=100, eps=1e-5, trace=False):
         """Iterations i_start..i_start+n_iters-1 of solverwrapper.jl:23-29."""
@@ -205,7 +244,7 @@ class _OracleBase:
         hl = C.c_int64(0)
         st = C.c_int32(0)
         tr = np.zeros((n_iters, self.N)) if trace else None
-        done = lib().fosor_run(self._h, i_start, n_iters, checki, eps, _d(hist), cap, C.byref(hl),
+        done = self._L.fosor_run(self._h, i_start, n_iters, checki, eps, _d(hist), cap, C.byref(hl),
                                _d(tr) if trace else None, C.byref(st))
         out = {"done": int(done), "status": STATUS_NAMES[st.value], "history": records_to_history(hist[:hl.value])}
         if trace:
@@ -218,7 +257,7 @@ class _OracleBase:
         hist = np.zeros((1, REC_LEN))
         hl = C.c_int64(0)
         st = C.c_int32(0)
-        lib().fosor_finish(self._h, _d(guess), _d(hist), C.byref(hl), C.byref(st))
+        self._L.fosor_finish(self._h, _d(guess), _d(hist), C.byref(hl), C.byref(st))
         return guess, records_to_history(hist[:hl.value]), STATUS_NAMES[st.value]
 
     def solve(self, max_iters=10000, checki=100, eps=1e-5):
@@ -228,7 +267,7 @@ class _OracleBase:
         hl = C.c_int64(0)
         st = C.c_int32(0)
         guess = np.empty(self.N)
-        done = lib().fosor_solve(self._h, max_iters, checki, eps, _d(guess), _d(hist), cap, C.byref(hl),
+        done = self._L.fosor_solve(self._h, max_iters, checki, eps, _d(guess), _d(hist), cap, C.byref(hl),
                                  C.byref(st))
         status = STATUS_NAMES[st.value]
         if status == "Continue":
@@ -240,44 +279,44 @@ class _OracleBase:
     def kkt_mul(self, x):
         x = _f64(x)
         y = np.empty(self.N)
-        lib().fosor_kkt_mul(self._h, _d(x), _d(y))
+        self._L.fosor_kkt_mul(self._h, _d(x), _d(y))
         return y
 
     def affine_prox(self, x):
         x = _f64(x)
         y = np.empty(self.N)
-        lib().fosor_affine_prox(self._h, _d(x), _d(y))
+        self._L.fosor_affine_prox(self._h, _d(x), _d(y))
         return y
 
     def cone_prox(self, x):
         x = _f64(x)
         y = np.empty(self.N)
-        lib().fosor_cone_prox(self._h, _d(x), _d(y))
+        self._L.fosor_cone_prox(self._h, _d(x), _d(y))
         return y
 
 
 class OracleConic(_OracleBase):
     """HSDE conic model: minimise c'x s.t. b - A x in K1, x in K2 (MathProgBase convention)."""
 
-    def __init__(self, c, A, b, constr_cones, var_cones, direct=False):
-        super().__init__()
+    def __init__(self, c, A, b, constr_cones, var_cones, direct=False, variant=""):
+        super().__init__(variant)
         A, colptr, rowval, nzval = _csc(A)
         self.m, self.n = A.shape
         self.c = _f64(c)
         self.b = _f64(b)
         t1, l1 = _cones(constr_cones)
         t2, l2 = _cones(var_cones)
-        self._h = lib().fosor_create_conic(self.m, self.n, _i(colptr), _i(rowval), _d(nzval), 0, _d(self.b),
+        self._h = self._L.fosor_create_conic(self.m, self.n, _i(colptr), _i(rowval), _d(nzval), 0, _d(self.b),
                                            _d(self.c), len(t1), _i32(t1), _i(l1), len(t2), _i32(t2), _i(l2))
         if not self._h:
             raise ValueError("cones do not cover 1:m / 1:n (cones.jl:66-72)")
-        self.N = lib().fosor_iterate_length(self._h)
+        self.N = self._L.fosor_iterate_length(self._h)
         self.l = self.m + self.n + 1
         if direct:  # HSDE(model, direct=true): S1 = IndAffine([Q -I], 0)  (HSDE.jl:10-15)
             self.set_direct(True)
 
     def set_direct(self, on=True):
-        if lib().fosor_set_direct(self._h, 1 if on else 0) != 0:
+        if self._L.fosor_set_direct(self._h, 1 if on else 0) != 0:
             raise RuntimeError("factorisation of I + Q Q' failed")
 
     def initial_value(self):
@@ -290,19 +329,19 @@ class OracleConic(_OracleBase):
     def q_mul(self, B, transpose=False):
         B = _f64(B)
         Y = np.empty(self.l)
-        lib().fosor_q_mul(self._h, _d(B), _d(Y), 1 if transpose else 0)
+        self._L.fosor_q_mul(self._h, _d(B), _d(Y), 1 if transpose else 0)
         return Y
 
     def a_mul(self, x, transpose=False):
         x = _f64(x)
         y = np.empty(self.n if transpose else self.m)
-        lib().fosor_a_mul(self._h, _d(x), _d(y), 1 if transpose else 0)
+        self._L.fosor_a_mul(self._h, _d(x), _d(y), 1 if transpose else 0)
         return y
 
     def hsdematrix_prox(self, x):
         x = _f64(x)
         y = np.empty(self.N)
-        lib().fosor_hsdematrix_prox(self._h, _d(x), _d(y))
+        self._L.fosor_hsdematrix_prox(self._h, _d(x), _d(y))
         return y
 
     def populate_solution(self, guess):
@@ -310,26 +349,26 @@ class OracleConic(_OracleBase):
         x = np.empty(self.n)
         y = np.empty(self.m)
         s = np.empty(self.m)
-        lib().fosor_populate_solution(self._h, _d(guess), _d(x), _d(y), _d(s))
+        self._L.fosor_populate_solution(self._h, _d(guess), _d(x), _d(y), _d(s))
         return x, y, s
 
 
 class OracleFeasibility(_OracleBase):
     """Feasibility(S1=AffinePlusLinear(A,b,q,beta), S2=ConeProduct(cones), n=an+am)."""
 
-    def __init__(self, A, b, q, beta, cones, decreasing_accuracy=False):
-        super().__init__()
+    def __init__(self, A, b, q, beta, cones, decreasing_accuracy=False, variant=""):
+        super().__init__(variant)
         A, colptr, rowval, nzval = _csc(A)
         self.am, self.an = A.shape
         b = _f64(b)
         q = _f64(q)
         t, ln = _cones(cones)
-        self._h = lib().fosor_create_feasibility(self.am, self.an, _i(colptr), _i(rowval), _d(nzval), 0, _d(b),
+        self._h = self._L.fosor_create_feasibility(self.am, self.an, _i(colptr), _i(rowval), _d(nzval), 0, _d(b),
                                                  _d(q), int(beta), 1 if decreasing_accuracy else 0, len(t),
                                                  _i32(t), _i(ln))
         if not self._h:
             raise ValueError("cones do not cover 1:(an+am)")
-        self.N = lib().fosor_iterate_length(self._h)
+        self.N = self._L.fosor_iterate_length(self._h)
 
     def initial_value(self):
         return np.zeros(self.N)  # Feasibility.jl:57-58
@@ -354,11 +393,49 @@ def prox_cone(name, x, dual=False):
     return y
 
 
-def host_threads() -> int:
-    return 1  # the restatement is serial, like the reference's mat-vecs and broadcasts
+def host_threads(variant: str = "") -> int:
+    """1 for the restatement proper (serial, like the reference's mat-vecs and broadcasts); the OpenMP thread
+    count for the "mt" timing variant."""
+    return int(lib(variant).fosor_threads()) if variant == "mt" else 1
 
 
-__all__ = ["OracleConic", "OracleFeasibility", "cg_csc", "prox_cone", "build", "lib", "records_to_history",
+class OracleConicDenseBig(_OracleBase):
+    """bench.py's config 2 at FULL size on the host: a dense m x n matrix stored the way the reference stores it
+    (SparseMatrixCSC{Float64,Int64}, every entry present: 16 B per entry), generated in place by the C library
+    (counter-based N(0,1)/sqrt(n)), never copied.  b = A xi + s, c = -A' y with xi, s, y from ``vectors(m, n)``."""
+
+    def __init__(self, m, n, seed, vectors, variant="mt"):
+        super().__init__(variant)
+        L = self._L
+        self.m, self.n = int(m), int(n)
+        self.colptr = np.empty(n + 1, dtype=np.int64)
+        self.rowval = np.empty(m * n, dtype=np.int64)
+        self.nzval = np.empty(m * n, dtype=np.float64)
+        L.fosor_gen_dense_csc(m, n, int(seed), 1.0 / np.sqrt(n), _i(self.colptr), _i(self.rowval), _d(self.nzval))
+        xi, s, y, cones = vectors(m, n, seed)
+        b = np.empty(m)
+        c = np.empty(n)
+        L.fosor_csc_mul(m, n, _i(self.colptr), _i(self.rowval), _d(self.nzval), _d(_f64(xi)), _d(b), 0)
+        L.fosor_csc_mul(m, n, _i(self.colptr), _i(self.rowval), _d(self.nzval), _d(_f64(y)), _d(c), 1)
+        self.b = b + s
+        self.c = -c
+        t1, l1 = _cones(cones)
+        t2, l2 = _cones([("Free", n)])
+        self._h = L.fosor_create_conic_borrowed(m, n, _i(self.colptr), _i(self.rowval), _d(self.nzval), _d(self.b),
+                                                _d(self.c), len(t1), _i32(t1), _i(l1), len(t2), _i32(t2), _i(l2))
+        if not self._h:
+            raise ValueError("cones do not cover 1:m / 1:n")
+        self.N = L.fosor_iterate_length(self._h)
+        self.l = m + n + 1
+
+    def initial_value(self):
+        z = np.zeros(self.N)
+        z[self.l - 1] = 1.0
+        z[2 * self.l - 1] = 1.0
+        return z
+
+
+__all__ = ["OracleConic", "OracleFeasibility", "OracleConicDenseBig", "build_all", "VARIANTS", "cg_csc", "prox_cone", "build", "lib", "records_to_history",
            "CONE_CODES", "ALG_CODES", "STATUS_NAMES", "REC_FIELDS", "host_threads"]
 
 if __name__ == "__main__":

@@ -91,3 +91,60 @@ def sync_state_from_oracle(H, O, alg):
     if alg == "Dykstra":
         H.set_state("dykstra_p", O.get_state("dykstra_p"))
         H.set_state("dykstra_q", O.get_state("dykstra_q"))
+
+
+# ---------------------------------------------------------------------------------------------
+# the "exact" yardstick (tests/test_gpu_exact.py, tests/test_oracle_exact.py)
+# ---------------------------------------------------------------------------------------------
+def sync_oracle_from_oracle(dst, O):
+    """Put the `exact` restatement into the C oracle's state."""
+    dst.set_state("x", O.get_state("x"))
+    if O.s1_calls > 1:
+        dst.set_state("xinit", O.get_state("xinit"))
+    dst.set_scalar("s1_calls", O.s1_calls)
+    dst.set_scalar("alpha12", O.alpha12)
+    dst.set_scalar("fista_t", O.fista_t)
+    dst.set_state("fista_y", O.get_state("fista_y"))
+    dst.set_state("dykstra_p", O.get_state("dykstra_p"))
+    dst.set_state("dykstra_q", O.get_state("dykstra_q"))
+
+
+def three_way(step_other, P, oracle, alg, n_iter):
+    """Runs C / exact / `other` in lock-step; returns (e_c, e_other, flips_c, flips_other) against exact."""
+    oargs = ALG_SETUPS[alg][0]
+    O = oracle.OracleConic(P.c, P.A, P.b, P.constr_cones, P.var_cones)
+    X = oracle.OracleConic(P.c, P.A, P.b, P.constr_cones, P.var_cones, variant="hp")
+    O.set_algorithm(*oargs)
+    X.set_algorithm(*oargs)
+    O.set_iterate(O.initial_value())
+    e_c, e_o, f_c, f_o = [], [], 0, 0
+    for i in range(1, n_iter + 1):
+        sync_oracle_from_oracle(X, O)
+        x_other, cg_other = step_other(O, i)
+        O.run(i, 1, checki=100000, eps=1e-12)
+        X.run(i, 1, checki=100000, eps=1e-12)
+        xx = X.get_state("x")
+        fc, fo_ = O.cgiter != X.cgiter, cg_other != X.cgiter
+        f_c += fc
+        f_o += fo_
+        if not fc and not fo_:
+            e_c.append(max(rel_err(O.get_state("x"), xx), 1e-17))
+            e_o.append(max(rel_err(x_other, xx), 1e-17))
+    return np.array(e_c), np.array(e_o), f_c, f_o
+
+
+def assert_no_worse_than_reference_arithmetic(tag, e_c, e_o, f_c, f_o, min_iters=6, who="GPU"):
+    ratio = e_o / e_c
+    gm = float(np.exp(np.mean(np.log(ratio))))
+    print(f"{tag}: C-vs-exact median {np.median(e_c):.2e} max {e_c.max():.2e} flips {f_c} | "
+          f"{who}-vs-exact median {np.median(e_o):.2e} max {e_o.max():.2e} flips {f_o} | "
+          f"ratio geo-mean {gm:.2f} max {ratio.max():.1f} over {len(ratio)} iterations")
+    assert len(ratio) >= min_iters
+    assert f_o <= f_c + 2, "the CUDA path misses the exact CG count more often than the reference's arithmetic"
+    assert gm <= 1.0, "the CUDA path is farther from the exact iteration than the reference's own arithmetic"
+    assert np.median(e_o) <= 2.0 * np.median(e_c)
+    assert e_o.max() <= 50.0 * e_c.max()
+    # and the premise of the test: the reference's arithmetic is itself NOT within 1e-10 of exact here
+    assert e_c.max() > 1e-10
+
+

@@ -1,0 +1,225 @@
+"""GPU parity at configuration scale (through the C ABI).
+
+* the fused dual mat-vec and the KKT product at BASELINE.json's config 2 itself (20000 x 40000 dense FP64,
+  6.4 GB, resident on the device) against FP64 torch mat-vecs -- torch is the checker only;
+* lock-step against the oracle at 2000 x 4000 and 4000 x 8000 (>= 148 persistent CTAs, >= 2 column bands,
+  ragged last band), strict 1e-10 on well-conditioned instances, with the CG tolerance schedule advanced so that
+  every projection runs several CG iterations;
+* config 5's shape (NNLS 256 x 512 -> m = 769, n = 513) in batch mode against the ORACLE (not against the
+  single-problem device path): strict lock-step on well-conditioned instances, the exact yardstick on the
+  unscaled ones;
+* config 4's cone (SDP, d = 512) inside the solver: GAP iterations against the NumPy / LAPACK restatement.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from helpers import (ALG_SETUPS, assert_no_worse_than_reference_arithmetic, load_conic, rel_err, set_alg_both,
+                     sync_state_from_oracle, three_way)
+
+pytestmark = pytest.mark.gpu
+
+STEP_TOL = 1e-10
+
+
+def test_fused_matvec_and_kkt_at_config2_scale(fos):
+    """K1 (one pass over A: A*[x1 x2] and A'*[y1 y2]) + the Q / KKT epilogues on the named 20000 x 40000 matrix,
+    adopted from a device tensor without a copy, against torch's FP64 mat-vecs (relative 1e-12 of the result's
+    largest entry; the two sides add 40000 / 20000 products in different orders)."""
+    import torch
+    from fos_b200 import model as M
+    m, n = 20000, 40000
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev)
+    g.manual_seed(2)
+    A = torch.randn((m, n), dtype=torch.float64, device=dev, generator=g) / np.sqrt(n)
+    rng = np.random.default_rng(0)
+    b, c = rng.standard_normal(m), rng.standard_normal(n)
+    cones = [("Zero", m // 2), ("NonNeg", m - m // 2)]
+    t1, l1 = M._cone_arrays(cones, m, "constraint")
+    t2, l2 = M._cone_arrays([("Free", n)], n, "variable")
+    H = fos.Handle(0)
+    H.ck(H.L.fos_load_conic_dense(H.h, m, n, C.c_void_p(A.data_ptr()), n, 1, 0, m, M._d(b), M._d(c), len(t1),
+                                  M._i32p(t1), M._i64p(l1), len(t2), M._i32p(t2), M._i64p(l2)))
+    td = lambda v: torch.from_numpy(np.ascontiguousarray(v)).to(dev)
+    x, w = rng.standard_normal(n), rng.standard_normal(m)
+    ax = (A @ td(x)).cpu().numpy()
+    atw = (A.T @ td(w)).cpu().numpy()
+    assert rel_err(H.a_mul(x, m, n), ax) < 1e-12
+    assert rel_err(H.a_mul(w, m, n, transpose=True), atw) < 1e-12
+    # Q = [0 A' c; -A 0 b; -c' -b' 0]   (HSDEAffine.jl:41-59)
+    l = m + n + 1
+
+    def q_mul(v):
+        vx, vy, vt = v[:n], v[n:n + m], v[n + m]
+        return np.concatenate([(A.T @ td(vy)).cpu().numpy() + c * vt, -(A @ td(vx)).cpu().numpy() + b * vt,
+                               [-(c @ vx) - (b @ vy)]])
+
+    u, v = rng.standard_normal(l), rng.standard_normal(l)
+    assert rel_err(H.q_mul(u), q_mul(u)) < 1e-12
+    assert rel_err(H.q_mul(u, transpose=True), -q_mul(u)) < 1e-12
+    # [I Q'; Q -I] [u; v]   (affinepluslinear.jl:37-49)
+    ref = np.concatenate([u - q_mul(v), q_mul(u) - v])
+    assert rel_err(H.kkt_mul(np.concatenate([u, v])), ref) < 1e-12
+    # one pass of the fused kernel is bitwise reproducible
+    assert np.array_equal(H.kkt_mul(np.concatenate([u, v])), H.kkt_mul(np.concatenate([u, v])))
+    del H
+
+
+@pytest.mark.parametrize("m,n", [(2000, 4000), (4000, 8000), (2512, 4100)])
+@pytest.mark.parametrize("alg", ["DR", "GAPA"])
+def test_lockstep_strict_at_scale(fos, oracle, m, n, alg):
+    """Dense C2-shaped instances that fill the machine (one persistent CTA per SM, 2-5 column bands, ragged
+    edges): five iterations in lock-step with the oracle at 1e-10, same CG counts, same records.  S1's call
+    counter starts at 40, so the CG tolerance is 0.2^sqrt(40) = 4e-5 and every projection iterates."""
+    from fos_b200 import problems
+    P = problems.lasso_like(m, n, seed=2, scale=0.1)
+    O = oracle.OracleConic(P.c, P.A, P.b, P.constr_cones, P.var_cones)
+    H = load_conic(fos, P, storage="dense_direct")
+    assert H.info("storage_kind") == 1
+    set_alg_both(fos, H, O, alg)
+    O.set_iterate(O.initial_value())
+    H.ck(H.L.fos_begin_solve(H.h))
+    O.run(1, 1, checki=100000, eps=1e-12)          # first projection initialises the warm start
+    O.set_scalar("s1_calls", 40)
+    worst, cgs = 0.0, []
+    for i in range(2, 7):
+        sync_state_from_oracle(H, O, alg)
+        ro = O.run(i, 1, checki=2, eps=1e-12)
+        done, st, rec, _ = H.run(i, 1, 2, 1e-12)
+        assert done == 1
+        assert H.info("cgiter") == O.cgiter, f"iteration {i}: CG count {H.info('cgiter')} vs {O.cgiter}"
+        cgs.append(O.cgiter)
+        e = rel_err(H.get_iterate(), O.get_state("x"))
+        worst = max(worst, e)
+        assert e < STEP_TOL, f"iteration {i}: iterate differs by {e:.3e}"
+        assert rel_err(H.get_state("tmp1"), O.get_state("tmp1")) < STEP_TOL
+        if i % 2 == 0:
+            ho = ro["history"]
+            assert rec[0, 0] == i and rec[0, 8] == ho["cgiter"][0] and rec[0, 9] == ho["status"][0]
+            for col, key in ((1, "p"), (2, "d"), (3, "g"), (4, "ctx"), (5, "bty"), (6, "kappa"), (7, "tau")):
+                np.testing.assert_allclose(rec[0, col], ho[key][0], rtol=1e-9, atol=1e-12, err_msg=key)
+    assert max(cgs) >= 3
+    print(f"{m}x{n} {alg}: worst one-step deviation {worst:.2e}, CG iterations {cgs}")
+
+
+# ---------------------------------------------------------------------------------------------
+# config 5 shape, batch mode, against the oracle
+# ---------------------------------------------------------------------------------------------
+def _batch(fos, plist):
+    H = fos.Handle(0)
+    A = np.stack([np.asarray(P.A.todense()) for P in plist])
+    H.load_conic_batch(A, np.stack([P.b for P in plist]), np.stack([P.c for P in plist]), plist[0].constr_cones,
+                       plist[0].var_cones)
+    return H
+
+
+def _sync_batch(H, Os, alg):
+    H.set_state_batch("x", np.stack([O.get_state("x") for O in Os]))
+    if Os[0].s1_calls > 1:
+        H.set_state_batch("xinit", np.stack([O.get_state("xinit") for O in Os]))
+    H.set_info_batch("s1_calls", [O.s1_calls for O in Os])
+    if alg == "FISTA":
+        H.set_state_batch("fista_y", np.stack([O.get_state("fista_y") for O in Os]))
+        H.set_info_batch("fista_t", [O.fista_t for O in Os])
+    if alg == "Dykstra":
+        H.set_state_batch("dykstra_p", np.stack([O.get_state("dykstra_p") for O in Os]))
+        H.set_state_batch("dykstra_q", np.stack([O.get_state("dykstra_q") for O in Os]))
+
+
+@pytest.mark.parametrize("alg", ["FISTA", "Dykstra"])
+def test_config5_shape_lockstep_against_oracle(fos, oracle, alg):
+    """NNLS 256 x 512 (m = 769, n = 513) in batch mode, both C5 algorithms: every problem, every iteration,
+    from ITS oracle's state, next iterate within 1e-10 of the oracle with the same CG count and the same record
+    (well-conditioned scaling of the dense block; S1's counter advanced so that CG iterates)."""
+    from fos_b200 import problems
+    B = 4
+    plist = [problems.nnls_conic(256, 512, seed=5 + j, scale=0.02 / np.sqrt(512)) for j in range(B)]
+    Os = [oracle.OracleConic(P.c, P.A, P.b, P.constr_cones, P.var_cones) for P in plist]
+    H = _batch(fos, plist)
+    oargs, fac = ALG_SETUPS[alg]
+    for O in Os:
+        O.set_algorithm(*oargs)
+        O.set_iterate(O.initial_value())
+        O.run(1, 1, checki=100000, eps=1e-12)
+        O.set_scalar("s1_calls", 40)
+    H.set_algorithm(fac(fos))
+    H.ck(H.L.fos_begin_solve_batch(H.h))
+    worst = 0.0
+    for i in range(2, 10):
+        _sync_batch(H, Os, alg)
+        ros = [O.run(i, 1, checki=4, eps=1e-12) for O in Os]
+        done, st, recs = H.run_batch(i, 1, 4, 1e-12)
+        assert list(done) == [1] * B
+        assert list(H.info_batch("cgiter")) == [O.cgiter for O in Os], f"iteration {i}: CG counts differ"
+        X = H.get_iterate_batch()
+        for j, O in enumerate(Os):
+            e = rel_err(X[j], O.get_state("x"))
+            worst = max(worst, e)
+            assert e < STEP_TOL, f"iteration {i}, problem {j}: {e:.3e}"
+            if i % 4 == 0:
+                ho = ros[j]["history"]
+                for col, key in ((1, "p"), (2, "d"), (3, "g"), (4, "ctx"), (5, "bty"), (6, "kappa"), (7, "tau")):
+                    np.testing.assert_allclose(recs[j][0, col], ho[key][0], rtol=1e-9, atol=1e-12, err_msg=key)
+                assert recs[j][0, 8] == ho["cgiter"][0] and recs[j][0, 9] == ho["status"][0]
+    print(f"C5 shape {alg}: worst one-step deviation {worst:.2e}")
+
+
+@pytest.mark.parametrize("alg", ["FISTA", "Dykstra"])
+def test_config5_shape_unscaled_exact_yardstick(fos, oracle, alg):
+    """The unscaled C5 instance (entries N(0,1)/sqrt(512)): the batch kernel is at least as close to the exact
+    iteration as the reference's own arithmetic (see tests/test_gpu_exact.py)."""
+    from fos_b200 import problems
+    P = problems.nnls_conic(256, 512, seed=5, scale=1.0 / np.sqrt(512))
+    H = _batch(fos, [P])
+    H.set_algorithm(ALG_SETUPS[alg][1](fos))
+    H.ck(H.L.fos_begin_solve_batch(H.h))
+
+    def step_batch(O, i):
+        _sync_batch(H, [O], alg)
+        done, _, _ = H.run_batch(i, 1, 100000, 1e-12)
+        assert done[0] == 1
+        return H.get_iterate_batch()[0], H.info_batch("cgiter")[0]
+
+    assert_no_worse_than_reference_arithmetic(f"C5/{alg}", *three_way(step_batch, P, oracle, alg, 30))
+
+
+# ---------------------------------------------------------------------------------------------
+# config 4: PSD cone d = 512 inside the solver
+# ---------------------------------------------------------------------------------------------
+def test_sdp_d512_solver_iterations_against_numpy_oracle(fos):
+    """GAP(0.8, 1.8, 1.8) on the nearest-correlation SDP with d = 512 (n = 131328, K1 = Zero(512) + SDP(131328),
+    two PSD(512) projections per iteration on the cooperative Jacobi kernel, warm-started): four iterations in
+    lock-step with the NumPy restatement (LAPACK eigh), iterate within 1e-10, same CG counts."""
+    from oracle import np_oracle as npo
+    from fos_b200 import problems
+    P = problems.sdp_nearest_correlation(512, seed=4)
+    M = npo.NPModel.conic(P.c, P.A, P.b, P.constr_cones, P.var_cones)
+    M.set_algorithm("GAP", 0.8, 1.8, 1.8, 0.0, 100)
+    M.checki, M.eps = 100000, 1e-12
+    for i in range(1, 36):      # leave the tau = 0 phase of the first iterations behind (CPU, ~0.2 s each)
+        M.i = i
+        M.step()
+    M.checki = 1
+    H = load_conic(fos, P, storage="sparse")
+    H.set_algorithm(fos.GAP(0.8, 1.8, 1.8))
+    H.ck(H.L.fos_begin_solve(H.h))
+    worst = 0.0
+    for i in range(36, 40):
+        H.set_state("x", M.x)
+        H.set_state("xinit", M.S1.xinit)
+        H.set_info("s1_calls", M.S1.i)
+        M.i = i
+        M.step()
+        done, st, rec, _ = H.run(i, 1, 1, 1e-12)
+        assert done == 1
+        assert H.info("cgiter") == M.S1.cgiter
+        e = rel_err(H.get_iterate(), M.x)
+        worst = max(worst, e)
+        assert e < STEP_TOL, f"iteration {i}: {e:.3e}"
+        h = M.hist[-1]
+        assert h["i"] == i and rec[0, 0] == i and h["tau"] > 0
+        np.testing.assert_allclose(rec[0, 1:8], [h[k] for k in ("p", "d", "g", "ctx", "bty", "kappa", "tau")],
+                                   rtol=1e-7, atol=1e-12)
+    print(f"SDP d=512 in-solver: worst one-step deviation {worst:.2e}")
