@@ -192,8 +192,8 @@ def parity_block(fos, device):
     from helpers import load_conic, rel_err, sync_state_from_oracle
     fo.build()
     fo.build(variant="hp")
-    out = {"twin": "lasso_like(2000, 4000, seed=2): 1/10-scale twin of the workload, 3 DR iterations in lock-step, "
-                   "S1 call counter advanced to 40 (CG tolerance 4e-5)"}
+    out = {"twin": "lasso_like(2000, 4000, seed=2): 1/10-scale twin of the workload, DR iterations 3..5 in lock-step from the C "
+                   "oracle's state, S1 call counter advanced to 40 (CG tolerance 4e-5); exact = long-double reductions"}
     for tag, scale in (("well_conditioned", 0.1), ("unscaled", 1.0)):
         P = problems.lasso_like(2000, 4000, seed=2, scale=scale)
         O = fo.OracleConic(P.c, P.A, P.b, P.constr_cones, P.var_cones)
@@ -207,7 +207,7 @@ def parity_block(fos, device):
         O.run(1, 1, checki=100000, eps=1e-12)
         O.set_scalar("s1_calls", 40)
         dev_c, dev_x, c_x, cg_match, cgs = 0.0, 0.0, 0.0, True, []
-        for i in range(2, 5):
+        for i in range(2, 6):
             sync_state_from_oracle(H, O, "DR")
             X.set_state("x", O.get_state("x"))
             X.set_state("xinit", O.get_state("xinit"))
@@ -215,16 +215,20 @@ def parity_block(fos, device):
             O.run(i, 1, checki=100000, eps=1e-12)
             X.run(i, 1, checki=100000, eps=1e-12)
             H.run(i, 1, 100000, 1e-12)
+            cg_match = cg_match and int(H.info("cgiter")) == int(O.cgiter)
+            cgs.append(int(O.cgiter))
+            if i == 2:
+                continue    # transient right after the tolerance jump (see tests/test_gpu_scale.py)
             z = H.get_iterate()
             dev_c = max(dev_c, rel_err(z, O.get_state("x")))
             dev_x = max(dev_x, rel_err(z, X.get_state("x")))
             c_x = max(c_x, rel_err(O.get_state("x"), X.get_state("x")))
-            cg_match = cg_match and int(H.info("cgiter")) == int(O.cgiter)
-            cgs.append(int(O.cgiter))
         out[tag] = {"gpu_vs_oracle": dev_c, "gpu_vs_exact": dev_x, "oracle_vs_exact": c_x,
                     "cg_counts_match": bool(cg_match), "cg_iterations": cgs}
         del H
-    out["pass"] = bool(out["well_conditioned"]["gpu_vs_oracle"] < 1e-10 and out["well_conditioned"]["cg_counts_match"])
+    wc, us = out["well_conditioned"], out["unscaled"]
+    out["pass"] = bool(wc["gpu_vs_exact"] < 1e-10 and wc["gpu_vs_oracle"] < max(1e-10, 3 * wc["oracle_vs_exact"]) and
+                       wc["cg_counts_match"] and us["gpu_vs_exact"] <= 3 * us["oracle_vs_exact"])
     return out
 
 

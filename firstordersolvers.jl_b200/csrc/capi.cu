@@ -83,6 +83,7 @@ int32_t fos_set_option(fos_handle_t hh, const char *key, double value)
     FOS_REQUIRE(key != nullptr, "null key");
     Handle &h = hh->h;
     const std::string k(key);
+    h.drop_graphs();  // most options change kernel arguments or the kernel sequence of the captured iteration
     if (k == "matvec_impl") {
         FOS_REQUIRE(value == 0 || value == 1, "matvec_impl must be 0 or 1");
         h.matvec_impl = (int)value;
@@ -129,7 +130,7 @@ int32_t fos_set_option(fos_handle_t hh, const char *key, double value)
             h.gbar.trace = nullptr;
         }
     } else if (k == "use_graphs") {
-        // reserved
+        h.use_graphs = value != 0;
     } else {
         throw Error(FOS_ERR_INVALID, "unknown option: " + k);
     }
@@ -192,6 +193,7 @@ int32_t fos_comm_p2p_import(fos_handle_t hh, const uint8_t *handles)
     Handle &h = hh->h;
     h.require_loaded();
     FOS_REQUIRE(handles != nullptr, "null handle table");
+    h.drop_graphs();
     h.A.p2p_import(handles);
     FOS_API_END(hh)
 }

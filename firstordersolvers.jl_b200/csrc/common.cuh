@@ -77,6 +77,10 @@ struct Ctrl {
     double ls_alphabest;
     // scratch for scalar hand-off between kernels
     double scal[8];
+    // device-side bookkeeping of the graph path (Handle::run_graph): no host round trip between iterations
+    int64_t s1_calls_dev;   // S1.i (affinepluslinear.jl:66): indexes the tolerance table, advanced by k_iter_begin
+    int64_t cur_i;          // iteration index (solverwrapper.jl:24), advanced by k_iter_begin
+    int64_t total_cg_dev;   // CG iterations executed since the run started
     uint32_t p2p_error;  // host copy only: peer-exchange timeout flag fetched by sync_ctrl
     uint32_t pad_;
 };

@@ -343,6 +343,30 @@ static __global__ void k_cg_begin(Ctrl *ctrl, double tol, int max_iters)
     ctrl->iter = 0;
 }
 
+// Graph path, first kernel of an outer iteration on the conic form (Handle::run_graph): k_fuse_prep + k_cg_begin in
+// one launch, with the per-iteration scalars taken from the DEVICE so that the captured graph never changes:
+//   dvec = [x0_1 ; x0_2 - x_2]                              (k_fuse_prep with beta = 1, q = b = 0; HSDE.jl:22)
+//   tol  = tol_table[S1.i] ; S1.i += 1                      (affinepluslinear.jl:108-114; the table holds the host's
+//                                                            max(0.2^sqrt(i), l*eps) so that both paths compare ||r||
+//                                                            with the same bits)
+//   i += 1 ; done = 0 ; iter = 0
+static __global__ void __launch_bounds__(VBLOCK)
+k_iter_begin(Lay L, const double *__restrict__ x0, const double *__restrict__ xin, double *__restrict__ dvec,
+             Ctrl *ctrl, const double *__restrict__ tol_table, int tbl_n, int max_iters)
+{
+    for (int64_t e = (int64_t)blockIdx.x * VBLOCK + threadIdx.x; e < L.NP; e += (int64_t)gridDim.x * VBLOCK)
+        dvec[e] = e < L.LP ? x0[e] : sub_(x0[e], xin[e]);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const int64_t k = ctrl->s1_calls_dev;
+        ctrl->tol = tol_table[k < tbl_n ? k : tbl_n - 1];
+        ctrl->s1_calls_dev = k + 1;
+        ctrl->cur_i += 1;
+        ctrl->max_iters = max_iters;
+        ctrl->done = 0;
+        ctrl->iter = 0;
+    }
+}
+
 // =======================================================================================
 // generic vector helpers
 // =======================================================================================
@@ -534,13 +558,36 @@ __device__ __forceinline__ void proj_exp_cone(const double (&v)[3], double (&y)[
     y[0] = x[0]; y[1] = x[1]; y[2] = x[2];
 }
 
+// Relaxation fused in front of the cone kernels (graph path): the cone input is not read from memory but formed on the
+// fly as  t1 = a*X + b*Y  (gap.jl:48 / gapa.jl:67 with a = alpha1 or alpha12, X = P1(x), Y = x; three roundings, like
+// k_relax).  Both cone kernels evaluate the same expression, so they see identical bits; k4_cone_apply stores t1.
+struct RelaxArgs {
+    const double *X, *Y;
+    double a, b;
+    int use_a12;     // GAPA: a = ctrl->alpha12, b = 1 - a
+    double *tmp1;    // where k4_cone_apply stores t1
+};
+template <bool RELAX>
+__device__ __forceinline__ double relaxed_in(const double *__restrict__ in, const RelaxArgs &R, double a, double b,
+                                             int64_t e)
+{
+    if (RELAX) return add_(mul_(a, R.X[e]), mul_(b, R.Y[e]));
+    return in[e];
+}
+
 // pass 1: one block per chunk of a SOC tail, squared-norm partial; the last block folds the
 // chunk partials per cone (in chunk order) and classifies each cone.
-static __global__ void __launch_bounds__(VBLOCK)
+template <bool RELAX>
+__global__ void __launch_bounds__(VBLOCK)
 k4_soc_norms(const double *__restrict__ in, const SocCone *__restrict__ cones, int ncones,
              const int32_t *__restrict__ chunk_cone, double *__restrict__ chunk_sum, SocScale *__restrict__ scale,
-             unsigned int *counter)
+             unsigned int *counter, RelaxArgs R, const Ctrl *ctrl)
 {
+    double ra = R.a, rb_ = R.b;
+    if (RELAX && R.use_a12) {
+        ra = ctrl->alpha12;
+        rb_ = 1.0 - ra;
+    }
     __shared__ double s_w[VBLOCK / 32];
     __shared__ bool s_last;
     const int ch = blockIdx.x;
@@ -551,7 +598,7 @@ k4_soc_norms(const double *__restrict__ in, const SocCone *__restrict__ cones, i
     const int64_t k1 = k0 + SOC_CHUNK < tail ? k0 + SOC_CHUNK : tail;
     double acc = 0.0;
     for (int64_t k = k0 + threadIdx.x; k < k1; k += VBLOCK) {
-        const double w = in[C.head + skip + k];
+        const double w = relaxed_in<RELAX>(in, R, ra, rb_, C.head + skip + k);
         acc = fma(w, w, acc);
     }
     acc = warp_sum(acc);
@@ -572,7 +619,14 @@ k4_soc_norms(const double *__restrict__ in, const SocCone *__restrict__ cones, i
         double s = 0.0;
         const volatile double *cs = chunk_sum;
         for (int k = 0; k < K.nchunk; k++) s += cs[K.chunk0 + k];
-        scale[cidx] = soc_classify(K, s, in);
+        if (RELAX) {  // plain SOCs only on this path (ConeSet::fusable): the classification needs the head entry
+            const double head[1] = {relaxed_in<true>(in, R, ra, rb_, K.head)};
+            SocCone K0 = K;
+            K0.head = 0;
+            scale[cidx] = soc_classify(K0, s, head);
+        } else {
+            scale[cidx] = soc_classify(K, s, in);
+        }
     }
     if (threadIdx.x == 0) *counter = 0u;
 }
@@ -665,12 +719,17 @@ struct EpiArgs {
 //   EPI_GAPP_PROJ (gapproj.jl:61-62) tmp2 = a2*proj + (1-a2)*in ; x = tmp2
 //   EPI_LS    (gapproj.jl:49-55)    ||proj - in|| ; last block keeps the strictly smallest
 //   EPI_LSW   (wrappers/linesearch.jl:63-69)  t3 = a2*proj + (1-a2)*in ; ||x - t3|| ; strictly smallest
-template <int EPI>
+template <int EPI, bool RELAX = false>
 __global__ void __launch_bounds__(VBLOCK)
 k4_cone_apply(int64_t NP, const double *__restrict__ in, double *__restrict__ proj, const uint8_t *__restrict__ ops,
               const int32_t *__restrict__ cone_of, const SocScale *__restrict__ scale, const SocCone *__restrict__ soc,
-              const double2 *__restrict__ box, EpiArgs E, Ctrl *ctrl, RedBuf rb)
+              const double2 *__restrict__ box, EpiArgs E, Ctrl *ctrl, RedBuf rb, RelaxArgs R)
 {
+    double ra = R.a, rb_ = R.b;
+    if (RELAX && R.use_a12) {
+        ra = ctrl->alpha12;
+        rb_ = 1.0 - ra;
+    }
     double a2 = E.a2, om_a2 = E.om_a2;
     if (EPI == EPI_GAPA || ((EPI == EPI_GAPP_PROJ || EPI == EPI_LSW) && E.use_a12)) {
         a2 = ctrl->alpha12;
@@ -678,7 +737,8 @@ k4_cone_apply(int64_t NP, const double *__restrict__ in, double *__restrict__ pr
     }
     double q[3] = {0, 0, 0};
     for (int64_t e = (int64_t)blockIdx.x * VBLOCK + threadIdx.x; e < NP; e += (int64_t)gridDim.x * VBLOCK) {
-        const double t1 = in[e];
+        const double t1 = relaxed_in<RELAX>(in, R, ra, rb_, e);
+        if (RELAX) R.tmp1[e] = t1;
         const double pj = cone_project(ops[e], t1, proj, e, cone_of, scale, in, box, soc);
         proj[e] = pj;
         if (EPI == EPI_GAP || EPI == EPI_GAPA) {
@@ -794,7 +854,8 @@ k6_check_hsde(Lay L, MVView V, const double *__restrict__ z, const double *__res
         const int k = ctrl->nrec;
         if (k < rec_cap) {
             double *R = recs + (size_t)k * FOS_REC_LEN;
-            R[0] = (double)iter_i; R[1] = p; R[2] = d; R[3] = g; R[4] = ctx; R[5] = bty; R[6] = kap; R[7] = tau;
+            R[0] = iter_i >= 0 ? (double)iter_i : (double)ctrl->cur_i;  // graph path: the device counts the iterations
+            R[1] = p; R[2] = d; R[3] = g; R[4] = ctx; R[5] = bty; R[6] = kap; R[7] = tau;
             R[8] = cgiter_host >= 0 ? (double)cgiter_host : (double)ctrl->iter;
             R[9] = (double)status;
         }
@@ -1096,6 +1157,76 @@ k1_exchange_p2p(MVView V, P2PView X, int64_t n, int64_t n_pad, int64_t m_pad, do
     }
 }
 
+// Initial CG residual on row shards: k1_exchange_p2p + k2_kkt_hsde<K2_RESID> in ONE kernel (graph path and
+// Handle::cg_solve with the peer exchange).  r = rhs - [I Q'; Q -I] x0, p = r, rn = <r,r>, iter = 1
+// (conjugategradients.jl:32-36).  Blocks wait for their peers only, never for each other: an ordinary launch whose
+// grid is resident (<= 2 blocks per SM) is enough.
+static __global__ void __launch_bounds__(VBLOCK)
+k2_resid_hsde_p2p(Lay L, MVView V, P2PView X, const double *__restrict__ in, const double *__restrict__ c,
+                  const double *__restrict__ b, const double *__restrict__ rhs, double *__restrict__ r,
+                  double *__restrict__ p, Ctrl *ctrl, RedBuf rb)
+{
+    const int64_t LP = L.LP, oy = L.n_pad, ot = L.n_pad + L.m_pad;
+    const int64_t stride = (int64_t)gridDim.x * VBLOCK, e0 = (int64_t)blockIdx.x * VBLOCK + threadIdx.x;
+    const unsigned int epoch = *X.epoch + 1u;
+    const int par = (int)(epoch & 1u);
+    p2p_push_all<2>(V, X, par, L.n, L.n_pad, L.m_pad, e0, stride);
+    const double tau1 = in[ot], tau2 = in[LP + ot];
+    double q[5] = {0, 0, 0, 0, 0};
+    for (int64_t e = e0; e < ot; e += stride) {
+        double o1 = 0.0, o2 = 0.0;
+        const double i1 = in[e], i2 = in[LP + e];
+        if (e < oy) {
+            if (e < L.n) {
+                double w[2];
+                p2p_poll_sum<2>(X, par, e, w);
+                const double cj = c[e];
+                const double q1 = add_(w[0], mul_(tau1, cj));
+                const double q2 = add_(w[1], mul_(tau2, cj));
+                o1 = add_(-q2, i1);
+                o2 = sub_(q1, i2);
+                q[0] = fma(cj, i1, q[0]);
+                q[2] = fma(cj, i2, q[2]);
+            }
+        } else {
+            const int64_t i = e - oy;
+            if (i < L.m) {
+                double a[2];
+                p2p_poll_row<2>(X, par, L.n_pad, i, a);
+                const double bi = b[i];
+                const double q1 = -sub_(a[0], mul_(tau1, bi));
+                const double q2 = -sub_(a[1], mul_(tau2, bi));
+                o1 = add_(-q2, i1);
+                o2 = sub_(q1, i2);
+                q[1] = fma(bi, i1, q[1]);
+                q[3] = fma(bi, i2, q[3]);
+            }
+        }
+        const double r1 = sub_(rhs[e], o1), r2 = sub_(rhs[LP + e], o2);
+        r[e] = r1;
+        r[LP + e] = r2;
+        p[e] = r1;
+        p[LP + e] = r2;
+        q[4] = fma(r1, r1, q[4]);
+        q[4] = fma(r2, r2, q[4]);
+    }
+    double tot[5];
+    if (grid_reduce<5, VBLOCK>(q, tot, rb) && threadIdx.x == 0) {
+        const double q1t = sub_(-tot[0], tot[1]);
+        const double q2t = sub_(-tot[2], tot[3]);
+        const double o1 = add_(-q2t, tau1);
+        const double o2 = sub_(q1t, tau2);
+        const double r1 = sub_(rhs[ot], o1), r2 = sub_(rhs[LP + ot], o2);
+        r[ot] = r1;
+        r[LP + ot] = r2;
+        p[ot] = r1;
+        p[LP + ot] = r2;
+        ctrl->rn = tot[4] + r1 * r1 + r2 * r2;
+        ctrl->iter = 1;
+        *X.epoch = epoch;  // every block has finished its polls before the last one arrives here
+    }
+}
+
 // =======================================================================================
 // Fused CG tail (HSDE form): everything of one CG iteration after the pass over A, in ONE
 // cooperative kernel --  [peer exchange]  ->  Ap = KKT p, <Ap,p>  ->  alpha  ->  x += alpha p,
@@ -1212,8 +1343,10 @@ template <bool P2P>
 __global__ void __launch_bounds__(VBLOCK)
 k_cg_tail_hsde(Lay L, MVView V, P2PView X, const double *__restrict__ c, const double *__restrict__ b,
                double *__restrict__ sol, double *__restrict__ r, double *__restrict__ p, double *__restrict__ Ap,
-               Ctrl *ctrl, GridBar gb)
+               Ctrl *ctrl, GridBar gb, unsigned long long cond)
 {
+    // `cond`: handle of the CUDA-graph WHILE node whose body this launch belongs to (0 outside a graph): the loop
+    // goes round again until the stop test of conjugategradients.jl:42 fires
     if (cg_skip(ctrl)) return;
     int tr_slot = -1;
     long long tr_last = 0;
@@ -1362,12 +1495,14 @@ k_cg_tail_hsde(Lay L, MVView V, P2PView X, const double *__restrict__ c, const d
         ctrl->rnorm = rnorm;
         if (stop) {
             ctrl->done = 1;
+            ctrl->total_cg_dev += iter;
             if (iter >= max_iters) ctrl->warn_maxit = 1;  // :53
         } else {
             ctrl->rn = rr;
             ctrl->beta = beta;
             ctrl->iter = iter + 1;
         }
+        if (cond != 0ull) cudaGraphSetConditional((cudaGraphConditionalHandle)cond, stop ? 0u : 1u);
     }
     FOS_TAIL_MARK(7);  // direction update
     if (tr_slot >= 0) atomicAdd(gb.trace + tr_slot * 16 + 15, 1ull);

@@ -26,6 +26,7 @@ void Handle::create(int dev)
                                       std::to_string(prop.minor) + "; this library is built for sm_100a only");
     num_sms = prop.multiProcessorCount;
     FOS_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    FOS_CUDA(cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking));
     d_ctrl.alloc(1);
     FOS_CUDA(cudaMallocHost((void **)&h_ctrl, sizeof(Ctrl)));
     memset(h_ctrl, 0, sizeof(Ctrl));
@@ -55,8 +56,10 @@ Handle::~Handle()
         } catch (...) {
         }
     }
+    drop_graphs();
     if (h_ctrl) cudaFreeHost(h_ctrl);
     if (h_stage) cudaFreeHost(h_stage);
+    if (stream2) cudaStreamDestroy(stream2);
     if (stream) cudaStreamDestroy(stream);
 }
 
@@ -111,6 +114,7 @@ void Handle::sync_ctrl()
 void Handle::ensure_recs(int cap)
 {
     if (cap <= rec_cap) return;
+    drop_graphs();  // the record buffer is a kernel argument of the captured status check
     d_recs.alloc((size_t)cap * FOS_REC_LEN);
     rec_cap = cap;
 }
@@ -128,7 +132,13 @@ void ConeSet::build(int64_t NP_, const std::vector<ConeSeg> &segs)
     psd.clear();
     psd_large.clear();
     psd_max_d = 0;
+    fusable = true;
     for (const ConeSeg &s : segs) {
+        // cones whose projection reads NEIGHBOURING input entries (or runs its own kernels) cannot take their
+        // input from the fused relaxation (RelaxArgs): rotated SOC, exponential cones, PSD
+        if (s.len > 0 && (s.type == FOS_CONE_SOCROT || s.type == FOS_CONE_EXPPRIMAL || s.type == FOS_CONE_EXPDUAL ||
+                          s.type == FOS_CONE_SDP))
+            fusable = false;
         FOS_REQUIRE(s.off >= 0 && s.off + s.len <= NP && s.len >= 0, "cone segment out of range");
         uint8_t op = OP_ZERO;
         switch (s.type) {
@@ -234,16 +244,17 @@ void ConeSet::set_box(int64_t off, int64_t len, double lo, double hi)
 
 void Handle::cone_project(ConeSet &K, const double *in, double *projbuf, int epi, const EpiArgs &E)
 {
+    const RelaxArgs R{};
     if (K.nsoc > 0)
-        FOS_LAUNCH(this, k4_soc_norms, K.nchunks, VBLOCK, 0, in, K.soc.p, K.nsoc, K.chunk_cone.p, K.chunk_sum.p,
-                   K.soc_scale.p, K.counter.p);
+        FOS_LAUNCH(this, k4_soc_norms<false>, K.nchunks, VBLOCK, 0, in, K.soc.p, K.nsoc, K.chunk_cone.p,
+                   K.chunk_sum.p, K.soc_scale.p, K.counter.p, R, d_ctrl.p);
     if (!K.psd.empty()) psd_project(this, K, in, projbuf);
     if (!K.psd_large.empty()) psd_project_large(this, K, in, projbuf);
     const int g = vgrid(K.NP);
 #define CONE_CASE(EPI)                                                                                            \
     case EPI:                                                                                                     \
         FOS_LAUNCH(this, k4_cone_apply<EPI>, g, VBLOCK, 0, K.NP, in, projbuf, K.ops.p, K.cone_of.p, K.soc_scale.p, \
-                   K.soc.p, K.box.p, E, d_ctrl.p, rb);                                                            \
+                   K.soc.p, K.box.p, E, d_ctrl.p, rb, R);                                                         \
         break;
     switch (epi) {
         CONE_CASE(EPI_NONE)
@@ -285,6 +296,18 @@ void Handle::finish_load_common(const std::vector<ConeSeg> &segs)
                               &w3, &prev})
         b->alloc(NP);
     cones.build(L.NP, segs);
+    drop_graphs();
+    {
+        // the tolerance schedule of affinepluslinear.jl:108-112 for the graph path, from the same host pow() the
+        // legacy path uses; beyond the table the schedule sits on its floor an*eps
+        const double an_ = (double)(L.form == 0 ? (L.n + L.m + 1) : L.n);
+        const double floor_ = an_ * 2.220446049250313e-16;
+        std::vector<double> tt((size_t)TOL_TABLE_N);
+        for (int k = 0; k < TOL_TABLE_N; k++)
+            tt[(size_t)k] = decreasing ? std::max(std::pow(0.2, std::sqrt((double)k)), floor_) : floor_;
+        tt[(size_t)TOL_TABLE_N - 1] = floor_;
+        tol_table.upload(tt);
+    }
     s1_calls = 1;
     cgiter = 0;
     firstrun = true;
@@ -443,9 +466,10 @@ void Handle::q_mul(const double *Bp, double *Yp, bool transpose)
     FOS_LAUNCH(this, k2_q_hsde, vgrid(L.LP), VBLOCK, 0, L, V, Bp, d_c.p, d_b.p, Yp, transpose ? 1 : 0, rb);
 }
 
-void Handle::cg_enqueue_iteration()
+void Handle::cg_enqueue_iteration(unsigned long long cond)
 {
-    const int32_t *skip = &d_ctrl.p->done;
+    // cond != 0: this launch pair is the body of a CUDA-graph WHILE node (run_graph): no predication needed
+    const int32_t *skip = cond != 0ull ? nullptr : &d_ctrl.p->done;
     if (L.form == 0 && fuse_tail) {
         // K1 + ONE cooperative kernel for the rest of the iteration (k_cg_tail_hsde)
         const bool p2p = A.nranks > 1 && A.p2p_on;
@@ -459,6 +483,7 @@ void Handle::cg_enqueue_iteration()
         // (same binary and same GPU model on every rank, so the clamp is identical everywhere)
         int &occ = tail_occ[p2p ? 1 : 0];
         if (occ == 0) {
+            FOS_REQUIRE(!capturing, "internal: occupancy query during graph capture");
             FOS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, VBLOCK, 0));
             FOS_REQUIRE(occ >= 1, "the fused CG tail does not fit on an SM");
         }
@@ -470,7 +495,7 @@ void Handle::cg_enqueue_iteration()
         double *solp = sol.p, *rp = r.p, *pp = p.p, *App = Ap.p;
         Ctrl *cp = d_ctrl.p;
         void *args[] = {(void *)&L, (void *)&V, (void *)&A.p2p, (void *)&cptr, (void *)&bptr, (void *)&solp,
-                        (void *)&rp,  (void *)&pp, (void *)&App, (void *)&cp, (void *)&gbar};
+                        (void *)&rp,  (void *)&pp, (void *)&App, (void *)&cp, (void *)&gbar, (void *)&cond};
         A.prof_begin(0, stream);
         FOS_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(VBLOCK), args, 0, stream));
         A.prof_end(stream);
@@ -614,6 +639,7 @@ void Handle::set_algorithm(int alg_, double a, double a1, double a2, double bA, 
 {
     FOS_REQUIRE(alg_ >= FOS_ALG_GAP && alg_ <= FOS_ALG_GAPP, "unknown algorithm code");
     FOS_REQUIRE(ip >= 1, "iproj must be >= 1");
+    drop_graphs();  // alpha, alpha1, alpha2, beta are arguments of the captured kernels
     alg = alg_;
     alpha = a;
     alpha1 = a1;
@@ -782,14 +808,21 @@ int64_t Handle::run(int64_t i_start, int64_t n_iters, int64_t checki, double eps
     sync_ctrl();
     h_ctrl->nrec = 0;
     h_ctrl->status = status;
+    h_ctrl->s1_calls_dev = s1_calls;
+    h_ctrl->cur_i = i_start - 1;
+    h_ctrl->total_cg_dev = 0;
     FOS_CUDA(cudaMemcpyAsync(d_ctrl.p, h_ctrl, sizeof(Ctrl), cudaMemcpyHostToDevice, stream));
     int64_t done = 0;
-    for (int64_t i = i_start; i < i_start + n_iters; i++) {
-        cur_i = i;  // solverwrapper.jl:24
-        step(i);    // :25
-        if (trace) unpack_to_host(x.p, trace + done * N);
-        done++;
-        if (status != FOS_STATUS_CONTINUE) break;  // :26-28
+    if (!trace && graph_ok()) {
+        done = run_graph(i_start, n_iters);
+    } else {
+        for (int64_t i = i_start; i < i_start + n_iters; i++) {
+            cur_i = i;  // solverwrapper.jl:24
+            step(i);    // :25
+            if (trace) unpack_to_host(x.p, trace + done * N);
+            done++;
+            if (status != FOS_STATUS_CONTINUE) break;  // :26-28
+        }
     }
     sync_ctrl();
     const int64_t nrec = h_ctrl->nrec;
@@ -817,6 +850,198 @@ void Handle::finish(double *guess, double *record, int64_t *n_rec)
     if (n_rec) *n_rec = nrec;
     if (guess) unpack_to_host(proj.p, guess);
     else FOS_CUDA(cudaStreamSynchronize(stream));
+}
+
+
+// =======================================================================================
+// graph path: one CUDA graph per outer iteration, the CG loop as a WHILE node
+// =======================================================================================
+bool Handle::graph_ok() const
+{
+    return use_graphs && loaded && L.form == 0 && (alg == FOS_ALG_GAP || alg == FOS_ALG_GAPA) && lsinterval == 0 &&
+           !direct && fuse_rhs && fuse_tail && A.kind == 1 && A.impl == 0 && cones.fusable && !A.profile &&
+           (A.nranks == 1 || A.p2p_on) && L.NP > 0;
+}
+
+void Handle::drop_graphs()
+{
+    for (IterGraph &g : graphs) {
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+        if (g.graph) cudaGraphDestroy(g.graph);
+        g.exec = nullptr;
+        g.graph = nullptr;
+        g.fixed_launches = 0;
+    }
+}
+
+void Handle::build_iter_graph(bool with_check)
+{
+    IterGraph &G = graphs[with_check ? 1 : 0];
+    const bool p2p = A.nranks > 1 && A.p2p_on;
+    const bool ada = alg == FOS_ALG_GAPA;
+    {   // everything that may not happen while the stream is capturing
+        int &occ = tail_occ[p2p ? 1 : 0];
+        if (occ == 0) {
+            const void *fn = p2p ? (const void *)k_cg_tail_hsde<true> : (const void *)k_cg_tail_hsde<false>;
+            FOS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, VBLOCK, 0));
+            FOS_REQUIRE(occ >= 1, "the fused CG tail does not fit on an SM");
+        }
+        FOS_CUDA(cudaStreamSynchronize(stream));
+    }
+    const Stats saved = stats;  // launches made while capturing are recorded, not executed
+    cudaStream_t main_stream = stream;
+    cudaGraph_t graph = nullptr;
+    capturing = true;
+    try {
+        FOS_CUDA(cudaStreamBeginCapture(main_stream, cudaStreamCaptureModeThreadLocal));
+        const int64_t l0 = stats.launches;
+        // ---- AffinePlusLinear.prox!, first part: right-hand side folded into the initial residual ----
+        FOS_LAUNCH(this, k_iter_begin, vgrid(L.NP), VBLOCK, 0, L, sol.p, x.p, Ap.p, d_ctrl.p, tol_table.p, TOL_TABLE_N,
+                   1000);
+        MVView V = kkt_pass(Ap.p, nullptr, /*defer_exchange=*/p2p);
+        if (p2p) {
+            const int grid = (int)std::min<int64_t>((L.LP + VBLOCK - 1) / VBLOCK, 2 * (int64_t)num_sms);
+            FOS_LAUNCH(this, k2_resid_hsde_p2p, grid, VBLOCK, 0, L, V, A.p2p, Ap.p, d_c.p, d_b.p, x.p, r.p, p.p,
+                       d_ctrl.p, rb);
+        } else {
+            FOS_LAUNCH(this, k2_kkt_hsde<K2_RESID>, vgrid(L.LP), VBLOCK, 0, L, V, Ap.p, d_c.p, d_b.p, nullptr, x.p, r.p,
+                       p.p, d_ctrl.p, rb, 0);
+        }
+        // ---- conjugategradient!'s loop (conjugategradients.jl:37-52) as a WHILE node; always >= 1 trip ----
+        cudaStreamCaptureStatus cst;
+        unsigned long long cid = 0;
+        cudaGraph_t cgraph = nullptr;
+        const cudaGraphNode_t *deps = nullptr;
+        size_t ndeps = 0;
+        FOS_CUDA(cudaStreamGetCaptureInfo(main_stream, &cst, &cid, &cgraph, &deps, &ndeps));
+        cudaGraphConditionalHandle cond;
+        FOS_CUDA(cudaGraphConditionalHandleCreate(&cond, cgraph, 1, cudaGraphCondAssignDefault));
+        cudaGraphNodeParams np = {};
+        np.type = cudaGraphNodeTypeConditional;
+        np.conditional.handle = cond;
+        np.conditional.type = cudaGraphCondTypeWhile;
+        np.conditional.size = 1;
+        cudaGraphNode_t wnode;
+        FOS_CUDA(cudaGraphAddNode(&wnode, cgraph, deps, ndeps, &np));
+        cudaGraph_t body = np.conditional.phGraph_out[0];
+        FOS_CUDA(cudaStreamBeginCaptureToGraph(stream2, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+        stream = stream2;
+        const int64_t lb = stats.launches;
+        try {
+            cg_enqueue_iteration((unsigned long long)cond);
+        } catch (...) {
+            stream = main_stream;
+            cudaGraph_t dummy = nullptr;
+            cudaStreamEndCapture(stream2, &dummy);
+            throw;
+        }
+        stream = main_stream;
+        const int64_t body_launches = stats.launches - lb;
+        FOS_CUDA(cudaStreamEndCapture(stream2, nullptr));
+        FOS_CUDA(cudaStreamUpdateCaptureDependencies(main_stream, &wnode, 1, cudaStreamSetCaptureDependencies));
+        // ---- S1 relaxation + S2 = DualConeProduct + S2 relaxation + averaging, one kernel (two with SOC cones) ----
+        EpiArgs E{};
+        E.tmp2 = tmp2.p;
+        E.x = x.p;
+        E.betaA = betaA;
+        E.a2 = alpha2;
+        E.om_a2 = 1.0 - alpha2;
+        E.a = alpha;
+        E.om_a = 1.0 - alpha;
+        RelaxArgs R{};
+        R.X = sol.p;
+        R.Y = x.p;
+        R.a = alpha1;
+        R.b = 1.0 - alpha1;
+        R.use_a12 = ada ? 1 : 0;
+        R.tmp1 = tmp1.p;
+        ConeSet &K = cones;
+        if (K.nsoc > 0)
+            FOS_LAUNCH(this, k4_soc_norms<true>, K.nchunks, VBLOCK, 0, nullptr, K.soc.p, K.nsoc, K.chunk_cone.p,
+                       K.chunk_sum.p, K.soc_scale.p, K.counter.p, R, d_ctrl.p);
+        if (ada)
+            FOS_LAUNCH(this, (k4_cone_apply<EPI_GAPA, true>), vgrid(K.NP), VBLOCK, 0, K.NP, nullptr, proj.p, K.ops.p,
+                       K.cone_of.p, K.soc_scale.p, K.soc.p, K.box.p, E, d_ctrl.p, rb, R);
+        else
+            FOS_LAUNCH(this, (k4_cone_apply<EPI_GAP, true>), vgrid(K.NP), VBLOCK, 0, K.NP, nullptr, proj.p, K.ops.p,
+                       K.cone_of.p, K.soc_scale.p, K.soc.p, K.box.p, E, d_ctrl.p, rb, R);
+        // ---- checkstatus on the unrelaxed projection (gap.jl:56; HSDEStatus.jl:27-71) ----
+        if (with_check) {
+            const double *X1[1] = {proj.p};
+            const double *W1[1] = {proj.p + L.n_pad};
+            MVView Vc = A.run(1, X1, W1, nullptr, main_stream);
+            FOS_LAUNCH(this, k6_check_hsde, vgrid(L.LP), VBLOCK, 0, L, Vc, proj.p, d_c.p, d_b.p, nb, ncn, cur_eps,
+                       (int64_t)-1, -1, d_ctrl.p, d_recs.p, rec_cap, rb);
+        }
+        G.fixed_launches = (int)(stats.launches - l0 - body_launches);
+        FOS_CUDA(cudaStreamEndCapture(main_stream, &graph));
+    } catch (...) {
+        stream = main_stream;
+        capturing = false;
+        stats = saved;
+        cudaStreamCaptureStatus cst = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(main_stream, &cst) == cudaSuccess && cst != cudaStreamCaptureStatusNone) {
+            cudaGraph_t dummy = nullptr;
+            cudaStreamEndCapture(main_stream, &dummy);
+            if (dummy) cudaGraphDestroy(dummy);
+        }
+        cudaGetLastError();
+        throw;
+    }
+    capturing = false;
+    stats = saved;
+    G.graph = graph;
+    FOS_CUDA(cudaGraphInstantiate(&G.exec, graph, 0));
+    if (with_check) graph_eps = cur_eps;
+}
+
+// iterations i_start .. i_start+n_iters-1 of solverwrapper.jl:23-29; the host synchronises on check iterations only
+int64_t Handle::run_graph(int64_t i_start, int64_t n_iters)
+{
+    if (graphs[1].exec && graph_eps != cur_eps) {  // eps is an argument of the captured check kernel
+        cudaGraphExecDestroy(graphs[1].exec);
+        cudaGraphDestroy(graphs[1].graph);
+        graphs[1] = IterGraph();
+    }
+    int64_t done = 0, since_iters = 0, since_checks = 0, absorbed = 0;
+    auto absorb = [&]() {
+        sync_ctrl();
+        const int64_t delta = h_ctrl->total_cg_dev - absorbed;
+        absorbed += delta;
+        stats.total_cg += delta;
+        stats.total_passes += delta + since_iters + since_checks;  // k CG passes + the initial residual (+ the check)
+        stats.launches += (since_iters - since_checks) * graphs[0].fixed_launches +
+                          since_checks * graphs[1].fixed_launches + 2 * delta;
+        cgiter = h_ctrl->iter;
+        if (h_ctrl->warn_maxit) warn_maxit = true;
+        since_iters = 0;
+        since_checks = 0;
+    };
+    for (int64_t i = i_start; i < i_start + n_iters; i++) {
+        if (firstrun) {  // affinepluslinear.jl:101-104
+            FOS_CUDA(cudaMemcpyAsync(sol.p, x.p, (size_t)L.NP * 8, cudaMemcpyDeviceToDevice, stream));
+            firstrun = false;
+        }
+        const bool chk = (i % cur_checki) == 0;
+        IterGraph &G = graphs[chk ? 1 : 0];
+        if (!G.exec) build_iter_graph(chk);
+        FOS_CUDA(cudaGraphLaunch(G.exec, stream));
+        cur_i = i;
+        s1_calls += 1;
+        done++;
+        since_iters++;
+        if (chk) {
+            since_checks++;
+            absorb();
+            status = h_ctrl->status;
+            checked = true;
+            if (status != FOS_STATUS_CONTINUE) break;
+        } else {
+            checked = false;
+        }
+    }
+    absorb();
+    return done;
 }
 
 }  // namespace fos

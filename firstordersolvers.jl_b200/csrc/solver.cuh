@@ -202,6 +202,7 @@ struct ConeSet {
     DevBuf<double> psd_vstore;   // eigenvector bases of the previous projection (warm start of K5L)
     bool psd_warm = false, psd_warm_enabled = true;
     int psd_max_d = 0;
+    bool fusable = true;  // every cone projects entry by entry from (x_e, per-cone scalars): RelaxArgs may feed it
     void build(int64_t NP_, const std::vector<ConeSeg> &segs);
 };
 
@@ -301,6 +302,26 @@ struct Handle {
     // run parameters remembered for finish()
     int64_t cur_i = 0, cur_checki = 100;
     double cur_eps = 1e-5;
+    // graph path (option "use_graphs", default 1): one CUDA graph per outer iteration of GAP / DR / AP / GAPA on the
+    // conic form -- [k_iter_begin, K1, initial residual] -> WHILE(!done){K1, fused CG tail} -> [cone projection fused
+    // with both relaxations and the averaging] (+ [K1, k6] on check iterations) -- launched back to back with no host
+    // synchronisation between iterations; the CG loop is a conditional graph node driven by the tail's stop test
+    struct IterGraph {
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        int fixed_launches = 0;  // kernels outside the CG loop
+    };
+    IterGraph graphs[2];  // [0] plain iteration, [1] iteration with a status check
+    int use_graphs = 1;
+    bool capturing = false;
+    double graph_eps = -1.0;
+    cudaStream_t stream2 = nullptr;  // captures the body of the WHILE node
+    DevBuf<double> tol_table;        // max(0.2^sqrt(i), l*eps) for S1.i = 0 .. TOL_TABLE_N-1 (host pow, like the legacy path)
+    static constexpr int TOL_TABLE_N = 512;
+    bool graph_ok() const;
+    void drop_graphs();
+    void build_iter_graph(bool with_check);
+    int64_t run_graph(int64_t i_start, int64_t n_iters);
     // batch mode
     std::unique_ptr<BatchSolver> batch;
     // direct = true (direct.cu): W = (I + Q Q')^-1 on the device, streamed by its own MatOp
@@ -330,7 +351,7 @@ struct Handle {
     void q_mul(const double *Bp, double *Yp, bool transpose);
     void s1_prox(const double *xin);
     void cg_solve(double tol, int max_iters, const double *x0 = nullptr, const double *rhs_ = nullptr);
-    void cg_enqueue_iteration();
+    void cg_enqueue_iteration(unsigned long long cond = 0ull);
     void sol_scaled_to(double *dst);
     void cone_project(ConeSet &K, const double *in, double *projbuf, int epi, const EpiArgs &E);
     void check(const double *z, int64_t i, bool override_);
