@@ -245,8 +245,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip time-to-eps, the parity block and the N=1 replay")
     ap.add_argument("--tte-max-iters", type=int, default=2000, help="iteration cap of the time-to-eps solve")
-    ap.add_argument("--tail-flags", type=int, default=-1, help="N > 1: hand-shake of the fused CG tail (0 block to block, 1 per rank)")
     ap.add_argument("--tail-blocks", type=int, default=0, help="blocks of the fused CG-tail kernel (0 = one per SM)")
+    ap.add_argument("--no-graphs", action="store_true", help="kernel-per-launch path with host synchronisation per CG batch")
     ap.add_argument("--tail-trace", action="store_true", help="phase timing of the fused CG tail (extra key tail_trace_us)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: fused peer-memory exchange kernel (default) or fold + ncclAllReduce")
@@ -312,12 +312,15 @@ def main():
     del xi_d, y_d, b_full, c_full
     torch.cuda.synchronize()
 
+    def apply_options(Hx):
+        Hx.set_option("matvec_impl", args.matvec_impl)
+        if args.tail_blocks:
+            Hx.set_option("tail_blocks", args.tail_blocks)
+        if args.no_graphs:
+            Hx.set_option("use_graphs", 0)
+
     H = fos.Handle(local_rank)
-    H.set_option("matvec_impl", args.matvec_impl)
-    if args.tail_blocks:
-        H.set_option("tail_blocks", args.tail_blocks)
-    if args.tail_flags >= 0:
-        H.set_option("tail_flags", args.tail_flags)
+    apply_options(H)
     if world > 1:
         cid = parallel.exchange_comm_id(rank, parallel.nccl_unique_id, dist)
         parallel.init_comm(H, rank, world, cid)
@@ -334,6 +337,9 @@ def main():
     H.ck(H.L.fos_begin_solve(H.h))
     stream = torch.cuda.ExternalStream(H.stream(), device=dev)
 
+    def stream_of(Hx):
+        return torch.cuda.ExternalStream(Hx.stream(), device=dev)
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -342,7 +348,7 @@ def main():
     def make_handle():
         """A fresh solver handle on the same device-resident matrix (shard), DR(0.5), initial iterate."""
         Hn = fos.Handle(local_rank)
-        Hn.set_option("matvec_impl", args.matvec_impl)
+        apply_options(Hn)
         if world > 1:
             cidn = parallel.exchange_comm_id(rank, parallel.nccl_unique_id, dist)
             parallel.init_comm(Hn, rank, world, cidn)
@@ -358,13 +364,11 @@ def main():
     # ---- warm-up -----------------------------------------------------------------------------------
     if W > 0:
         H.run(1, W, 100, 1e-5)
-    H.set_option("profile_matvec", 1)
-    if args.tail_trace:
-        H.set_option("tail_trace", 1)
     launches0 = H.info("launches")
     cg0, passes0 = H.info("total_cg"), H.info("total_passes")
 
     # ---- timed region: K iterations, inputs resident in HBM -----------------------------------------
+    # (the library's default path: one CUDA graph per outer iteration, no host synchronisation in between)
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
@@ -385,28 +389,46 @@ def main():
     launches = H.info("launches") - launches0
     cg_iters = H.info("total_cg") - cg0
     passes = H.info("total_passes") - passes0   # executed passes over A (predicated no-op launches excluded)
-    mv2_ms, mv2_n = H.info("mv2_ms"), H.info("mv2_n")
-    mv1_ms, mv1_n = H.info("mv1_ms"), H.info("mv1_n")
     bytes_pass = H.info("bytes_per_pass")
-    tail_ms, tail_n = H.info("tail_ms"), H.info("tail_n")
-    H.set_option("profile_matvec", 0)
     value = K / (ms_total / 1e3)
+
+    # ---- roofline pass: the SAME iterations W+1..W+K on a fresh handle, every launch of the dominant kernel
+    # bracketed by CUDA events on the library's stream ("profile_matvec": kernel-per-launch path, since events
+    # cannot be recorded inside a graph's WHILE body) ------------------------------------------------------
+    Hp = make_handle()
+    if W > 0:
+        Hp.run(1, W, 100, 1e-5)
+    Hp.set_option("profile_matvec", 1)
+    if args.tail_trace:
+        Hp.set_option("tail_trace", 1)
+    barrier()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record(stream_of(Hp))
+    Hp.run(W + 1, K, 100, 1e-5)
+    p1.record(stream_of(Hp))
+    barrier()
+    prof_ms_total = p0.elapsed_time(p1)
+    mv2_ms, mv2_n = Hp.info("mv2_ms"), Hp.info("mv2_n")
+    mv1_ms, mv1_n = Hp.info("mv1_ms"), Hp.info("mv1_n")
+    tail_ms, tail_n = Hp.info("tail_ms"), Hp.info("tail_n")
+    Hp.set_option("profile_matvec", 0)
     tail_trace = None
     if args.tail_trace:
-        tt_ = H.tail_trace()
+        tt_ = Hp.tail_trace()
         mhz = clocks.get("sm_mhz") or 1900.0
-        tail_trace = {"phases": ["fold", "fence", "flags", "gather+Ap", "allreduce1", "update", "allreduce2", "dir"],
+        tail_trace = {"phases": ["fold+push", "-", "-", "poll+Ap", "allreduce1", "update", "allreduce2", "dir"],
                       "us_per_launch": [[float(tt_[b, k] / max(tt_[b, 15], 1) / mhz) for k in range(8)] for b in range(3)],
                       "launches": float(tt_[0, 15]), "sm_mhz": mhz, "rank": rank}
         if rank != 0:
             sys.stderr.write("rank %d tail_trace %s\n" % (rank, json.dumps(tail_trace)))
+    del Hp
 
     # ---- e2e: the SAME iterations W+1..W+K through the C ABI with HOST buffers ---------------------
     # A second handle on the same device matrix replays the solve; every step moves the iterate in
     # from host memory (H2D), runs one iteration with a residual check and reads the iterate and the
     # p/d/g record back (D2H), all inside the timed region.
     H2 = fos.Handle(local_rank)
-    H2.set_option("matvec_impl", args.matvec_impl)
+    apply_options(H2)
     if world > 1:
         cid2 = parallel.exchange_comm_id(rank, parallel.nccl_unique_id, dist)
         parallel.init_comm(H2, rank, world, cid2)
@@ -462,9 +484,12 @@ def main():
                "hbm_gbs": bytes_pass * H3.info("total_passes") / tte_s / 1e9,
                "note": "wall clock of fos_solve from z0 (tau = kappa = 1), max over ranks; includes getsol and the "
                        "final check"}
-        del H3, z0
+        del z0
 
-    # ---- N > 1: the sharded result against a single-GPU replay of the same iterations on rank 0 ----------
+    # ---- N > 1: the sharded path against one GPU holding the whole matrix (rank 0) ----------------------
+    #   free-running: iterations 1..W+K on N shards vs the same iterations on one GPU;
+    #   lock-step:    from the state the sharded time-to-eps solve ended in (tau > 0, residuals finite), ONE more
+    #                 iteration with a residual check on both -- iterate, p/d/g record and CG count side by side
     multi = None
     if world > 1 and not args.no_extras:
         import zlib
@@ -472,12 +497,15 @@ def main():
         crc = torch.tensor([float(zlib.crc32(z_sh.tobytes()))], dtype=torch.float64, device=dev)
         crcs = [torch.empty_like(crc) for _ in range(world)]
         dist.all_gather(crcs, crc)
-        Hc = None
-        # one more iteration with a residual check on every rank: the p/d/g record of the sharded path
-        _, _, rec_sh, _ = H.run(W + K + 1, 1, 1, 1e-5)
+        x3, xi3, s13 = H3.get_state("x"), H3.get_state("xinit"), H3.info("s1_calls")
+        i3 = int(done3) + 1
+        _, _, rec_sh, _ = H3.run(i3, 1, 1, 1e-5)
+        z3 = H3.get_iterate()
+        cg_sh = int(H3.info("cgiter"))
         if rank == 0:
             A_full = gen_rows_device(torch, dev, 0, m, n, args.seed)
             Hc = fos.Handle(local_rank)
+            apply_options(Hc)
             Hc.ck(Hc.L.fos_load_conic_dense(Hc.h, m, n, C.c_void_p(A_full.data_ptr()), n, 1, 0, m, _d(b), _d(c),
                                             len(t1), _i32p(t1), _i64p(l1), len(t2), _i32p(t2), _i64p(l2)))
             Hc.set_algorithm(fos.DR(0.5))
@@ -485,21 +513,28 @@ def main():
             Hc.ck(Hc.L.fos_begin_solve(Hc.h))
             Hc.run(1, W + K, 100, 1e-5)
             z_1 = Hc.get_iterate()
-            _, _, rec_1, _ = Hc.run(W + K + 1, 1, 1, 1e-5)
-            den = max(np.abs(z_1).max(), 1e-300)
+            cg_free_1 = int(Hc.info("total_cg"))
+            Hc.set_state("x", x3)
+            Hc.set_state("xinit", xi3)
+            Hc.set_info("s1_calls", s13)
+            _, _, rec_1, _ = Hc.run(i3, 1, 1, 1e-5)
+            zc = Hc.get_iterate()
+            rel = lambda u, v: float(np.abs(u - v).max() / max(np.abs(v).max(), 1e-300))
+            recd = lambda r: {"i": int(r[0, 0]), "p": float(r[0, 1]), "d": float(r[0, 2]), "g": float(r[0, 3]),
+                              "cgiter": int(r[0, 8]), "status": int(r[0, 9])}
             multi = {"ranks_bitwise_identical": bool(all(float(t.item()) == float(crc.item()) for t in crcs)),
                      "iterate_crc32": int(crc.item()),
-                     "parity_vs_n1": float(np.abs(z_sh - z_1).max() / den),
-                     "record_sharded": {"i": int(rec_sh[0, 0]), "p": float(rec_sh[0, 1]), "d": float(rec_sh[0, 2]),
-                                        "g": float(rec_sh[0, 3]), "cgiter": int(rec_sh[0, 8])},
-                     "record_n1": {"i": int(rec_1[0, 0]), "p": float(rec_1[0, 1]), "d": float(rec_1[0, 2]),
-                                   "g": float(rec_1[0, 3]), "cgiter": int(rec_1[0, 8])},
-                     "cg_iterations_sharded": int(H.info("total_cg")), "cg_iterations_n1": int(Hc.info("total_cg")),
-                     "note": f"free-running iterations 1..{W + K} on {world} row shards vs the same iterations on one "
-                             "GPU (rank 0 replay); the sums are associated differently, the truncated CG amplifies "
-                             "that (DESIGN.md parity budget)"}
+                     "free_running": {"iterations": f"1..{W + K}", "iterate_deviation_vs_n1": rel(z_sh, z_1),
+                                      "cg_iterations_sharded": int(cg0 + cg_iters), "cg_iterations_n1": cg_free_1},
+                     "lockstep": {"iteration": i3, "iterate_deviation_vs_n1": rel(z3, zc),
+                                  "record_sharded": recd(rec_sh), "record_n1": recd(rec_1),
+                                  "cg_iterations_sharded": cg_sh, "cg_iterations_n1": int(Hc.info("cgiter"))},
+                     "note": "row shards associate the A' sums differently from one GPU; free-running, the truncated CG "
+                             "amplifies that (DESIGN.md parity budget); in lock-step one iteration agrees to rounding"}
             del Hc, A_full
         barrier()
+    if tte is not None:
+        del H3
 
     if rank != 0:
         if world > 1:
@@ -524,7 +559,9 @@ def main():
                 "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_pass, "launches_timed": int(mv2_n),
                 "avg_launch_ms": (mv2_ms / mv2_n) if mv2_n else None,
-                "share_of_step": ((mv2_ms + mv1_ms) / ms_total) if ms_total > 0 else None,
+                "share_of_step": ((mv2_ms + mv1_ms) / prof_ms_total) if prof_ms_total > 0 else None,
+                "measured_in": "event-bracketed replay of the timed iterations (kernel-per-launch path): "
+                               f"{prof_ms_total / K:.3f} ms per step there",
                 "whole_iteration_gbs": bytes_pass * passes / (ms_total / 1e3) / 1e9,
                 "whole_iteration_frac": bytes_pass * passes / (ms_total / 1e3) / 1e9 / peak}
     parity = None
@@ -542,7 +579,8 @@ def main():
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "cg_tail_avg_launch_us": (1e3 * tail_ms / tail_n) if tail_n else None,
             "cg_iterations_per_step": cg_iters / K, "passes_over_A_per_step": passes / K,
-            "wall_ms_per_step": t_wall * 1e3 / K, "status_after_timed": int(st)}
+            "wall_ms_per_step": t_wall * 1e3 / K, "status_after_timed": int(st),
+            "iteration_path": "kernel per launch" if args.no_graphs else "CUDA graph per outer iteration (CG loop = WHILE node)"}
     line["time_to_eps"] = tte
     line["parity"] = parity
     if multi is not None:

@@ -867,6 +867,8 @@ __global__ void k_batch_reset(BatchCtl *ctl, int B, int what)
     if (what == 0 || what == 1) {
         c.status = FOS_STATUS_CONTINUE;
         c.checked = 0;
+        c.warn_maxit = 0;  // the warning of conjugategradients.jl:53 is per occurrence
+        c.last_i = 0;      // a fresh status object counts from i = 0
     }
     if (what == 0 || what == 2) {
         c.alpha12 = 2.0;  // gapa.jl:29

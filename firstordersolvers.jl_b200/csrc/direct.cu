@@ -132,6 +132,13 @@ void Handle::set_direct(bool on)
     require_loaded();
     FOS_REQUIRE(L.form == 0, "direct = true applies to the conic (HSDE) form; the Feasibility form takes its S1 from the user");
     FOS_REQUIRE(A.nranks == 1, "direct = true is not offered with row sharding");
+    if (direct) {
+        // s1_prox_direct borrows rhs and r as scratch; the CG path with "fuse_rhs" = 0 relies on rhs[LP..2LP) = b = 0
+        // (HSDE.jl:22) and never rewrites it
+        FOS_CUDA(cudaMemsetAsync(rhs.p, 0, (size_t)L.NP * 8, stream));
+        FOS_CUDA(cudaMemsetAsync(r.p, 0, (size_t)L.NP * 8, stream));
+        FOS_CUDA(cudaStreamSynchronize(stream));
+    }
     direct = false;
     Wop.reset();
     Winv.release();

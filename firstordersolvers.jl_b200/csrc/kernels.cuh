@@ -639,8 +639,10 @@ __device__ __forceinline__ double cone_project(uint8_t op, double x, const doubl
     switch (op) {
     case OP_ZERO: return 0.0;
     case OP_COPY: return x;
-    case OP_MAX0: return x > 0.0 ? x : 0.0;   // max(x,0); NaN -> 0 like Julia's max? (NaN stays NaN in Julia)
-    case OP_MIN0: return x < 0.0 ? x : 0.0;
+    // NaN goes through, as in the reference (IndNonnegative: `x < 0 ? 0 : x`; Julia's max(NaN, 0) is NaN for tau and
+    // kappa, cones.jl:138,141): after a CG breakdown on the indefinite KKT matrix the reference ends Indeterminate
+    case OP_MAX0: return x < 0.0 ? 0.0 : x;
+    case OP_MIN0: return x > 0.0 ? 0.0 : x;
     case OP_PRE: return proj[e];
     case OP_BOX: {  // IndBox: min(max(x, lo), hi)
         const double2 b = box[cone_of[e]];

@@ -789,6 +789,11 @@ void Handle::begin_solve()
 {
     status = FOS_STATUS_CONTINUE;
     checked = false;
+    // a fresh status object counts from i = 0 (a forced final check after max_iters = 0 records i = 0), and the
+    // "CG reached max iterations" warning is raised per occurrence (conjugategradients.jl:53), not once per model
+    cur_i = 0;
+    warn_maxit = false;
+    FOS_CUDA(cudaMemsetAsync(&d_ctrl.p->warn_maxit, 0, sizeof(int32_t), stream));
     if (L.form == 1) {
         std::vector<double> nanv((size_t)L.NP, std::nan(""));
         FOS_CUDA(cudaMemcpy(prev.p, nanv.data(), (size_t)L.NP * 8, cudaMemcpyHostToDevice));

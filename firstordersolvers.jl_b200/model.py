@@ -655,6 +655,7 @@ def solve_batch(alg: FOSAlgorithm, cs, As, bs, constr_cones, var_cones, device=0
     eps = float(opts.get("eps", 1e-5))
     checki = int(opts.get("checki", 100))
     debug = int(opts.get("debug", 1))
+    verbose = int(opts.get("verbose", 1))
     bs = np.ascontiguousarray(bs, dtype=np.float64)
     cs = np.ascontiguousarray(cs, dtype=np.float64)
     B, m = bs.shape
@@ -679,17 +680,20 @@ def solve_batch(alg: FOSAlgorithm, cs, As, bs, constr_cones, var_cones, device=0
         mod.K1, mod.K2 = tuple(constr_cones), tuple(var_cones)
         mod.b, mod.c = bs[j], cs[j]
         mod.last_iteration = int(done[j])
-        if debug > 0:
-            for r in recs[j]:
+        for r in recs[j]:
+            if debug > 0:   # savedata (HSDEStatus.jl:125-139); :t is the wall time of the WHOLE batch launch: the
+                # problems are solved concurrently, so there is no per-check clock to report
                 for key, v in (("p", r[1]), ("d", r[2]), ("g", r[3]), ("ctx", r[4]), ("bty", r[5]), ("κ", r[6]),
                                ("τ", r[7]), ("t", t)):
                     mod.history.push(key, int(r[0]), v)
+            if verbose > 0:  # HSDEStatus.jl:43-47: cgiter is gated on verbose, not on debug
                 mod.history.push("cgiter", int(r[0]), int(r[8]))
         g = guess[j]
         tau = g[l - 1]
         with np.errstate(all="ignore"):
             mod.primal_sol, mod.dual_sol, mod.slack = g[:n] / tau, g[n:n + m] / tau, g[l + n:l + n + m] / tau
-        mod.solve_stat = STATUS_SYMBOLS[int(st[j])]
+        stj = int(st[j])
+        mod.solve_stat = "Indeterminate" if STATUS_SYMBOLS[stj] == "Continue" else STATUS_SYMBOLS[stj]  # HSDE.jl:56-59
         mod.obj_val = float(np.dot(cs[j], mod.primal_sol))
         models.append(mod)
     return models

@@ -606,8 +606,9 @@ static int prox_cone(double *y, int type, const double *x, int64_t len)
     case CONE_EXPDUAL: return prox_exp(y, x, len, 1);
     case CONE_FREE: for (int64_t i = 0; i < len; i++) y[i] = x[i]; return 0;
     case CONE_ZERO: for (int64_t i = 0; i < len; i++) y[i] = 0.0; return 0;
-    case CONE_NONNEG: for (int64_t i = 0; i < len; i++) y[i] = x[i] > 0.0 ? x[i] : 0.0; return 0;
-    case CONE_NONPOS: for (int64_t i = 0; i < len; i++) y[i] = x[i] < 0.0 ? x[i] : 0.0; return 0;
+    /* NaN passes through (IndNonnegative: `x < 0 ? 0 : x`), as it does through Julia's max(x, 0) below */
+    case CONE_NONNEG: for (int64_t i = 0; i < len; i++) y[i] = x[i] < 0.0 ? 0.0 : x[i]; return 0;
+    case CONE_NONPOS: for (int64_t i = 0; i < len; i++) y[i] = x[i] > 0.0 ? 0.0 : x[i]; return 0;
     case CONE_SOC: prox_soc(y, x, len); return 0;
     case CONE_SDP: prox_sdp(y, x, len); return 0;
     default: return -1;
@@ -677,10 +678,10 @@ static int dualconeprod_prox(double *y, const coneprod_t *K1, const coneprod_t *
     int rc = 0;
     rc |= coneprod_prox(y, K2, x, 0);                          /* :136 */
     rc |= coneprod_prox(y + n, K1, x + n, 1);                  /* :137 */
-    y[nu - 1] = x[nu - 1] > 0.0 ? x[nu - 1] : 0.0;             /* :138 */
+    y[nu - 1] = x[nu - 1] < 0.0 ? 0.0 : x[nu - 1];             /* :138  max(tau, 0), NaN stays NaN */
     rc |= coneprod_prox(y + nu, K2, x + nu, 1);                /* :139 */
     rc |= coneprod_prox(y + nu + n, K1, x + nu + n, 0);        /* :140 */
-    y[2 * nu - 1] = x[2 * nu - 1] > 0.0 ? x[2 * nu - 1] : 0.0; /* :141 */
+    y[2 * nu - 1] = x[2 * nu - 1] < 0.0 ? 0.0 : x[2 * nu - 1]; /* :141 */
     return rc;
 }
 
