@@ -194,7 +194,7 @@ def parity_block(fos, device):
     fo.build(variant="hp")
     out = {"twin": "lasso_like(2000, 4000, seed=2): 1/10-scale twin of the workload, DR iterations 3..5 in lock-step from the C "
                    "oracle's state, S1 call counter advanced to 40 (CG tolerance 4e-5); exact = long-double reductions"}
-    for tag, scale in (("well_conditioned", 0.1), ("unscaled", 1.0)):
+    for tag, scale in (("well_conditioned", 0.02), ("unscaled", 1.0)):
         P = problems.lasso_like(2000, 4000, seed=2, scale=scale)
         O = fo.OracleConic(P.c, P.A, P.b, P.constr_cones, P.var_cones)
         X = fo.OracleConic(P.c, P.A, P.b, P.constr_cones, P.var_cones, variant="hp")

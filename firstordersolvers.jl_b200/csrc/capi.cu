@@ -160,7 +160,9 @@ int32_t fos_comm_init(fos_handle_t hh, int32_t rank, int32_t nranks, const uint8
     FOS_REQUIRE(!h.loaded, "fos_comm_init must precede loading");
     FOS_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "bad rank / nranks");
     FOS_REQUIRE(idb != nullptr, "null id");
-    if (nranks > 1) {
+    bool want_nccl = false;  // an all-zero id = "peer-memory exchange only": no NCCL communicator is created
+    for (int k = 0; k < FOS_COMM_ID_BYTES; k++) want_nccl = want_nccl || idb[k] != 0;
+    if (nranks > 1 && want_nccl) {
         NcclId id;
         memcpy(id.bytes, idb, FOS_COMM_ID_BYTES);
         void *comm = nullptr;

@@ -573,6 +573,9 @@ MVView MatOp::run_t(const double *const *X, const double *const *W, const int32_
         k1_finalize_local<NV><<<grid, VBLOCK, 0, st>>>(V, n, n_pad, m_local, row_begin, m_pad, xbuf.p, skip);
         if (stats) stats->launches++;
         const size_t count = (size_t)NV * (size_t)(n_pad + m_pad);
+        if (comm == nullptr)
+            throw Error(FOS_ERR_COMM, "no NCCL communicator on this handle (fos_comm_init was given an all-zero id): "
+                                      "enable the peer-memory exchange (fos_comm_p2p_export / _import) before running");
         int rc = nccl_api().AllReduce(xbuf.p, xbuf.p, count, /*ncclFloat64*/ 8, /*ncclSum*/ 0, comm, st);
         if (rc != 0) throw Error(FOS_ERR_COMM, std::string("ncclAllReduce failed: ") + nccl_api().GetErrorString(rc));
         V = view_full(NV, xbuf.p + (size_t)NV * n_pad, xbuf.p);

@@ -62,8 +62,11 @@ def nccl_unique_id() -> bytes:
     return bytes(arr)
 
 
-def init_comm(handle, rank: int, nranks: int, comm_id: bytes):
-    """fos_comm_init on a ``Handle`` (before loading the problem)."""
+def init_comm(handle, rank: int, nranks: int, comm_id: bytes = None):
+    """fos_comm_init on a ``Handle`` (before loading the problem).  ``comm_id=None`` passes the all-zero id: no NCCL
+    communicator, the peer-memory exchange (``enable_p2p_exchange``) must follow the load."""
+    if comm_id is None:
+        comm_id = bytes(_lib.FOS_COMM_ID_BYTES)
     arr = (C.c_uint8 * _lib.FOS_COMM_ID_BYTES).from_buffer_copy(comm_id)
     handle.ck(handle.L.fos_comm_init(handle.h, rank, nranks, arr))
 

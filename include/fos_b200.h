@@ -123,6 +123,8 @@ int32_t fos_set_option(fos_handle_t h, const char *key, double value);
 /* ====================================================================================== */
 #define FOS_COMM_ID_BYTES 128
 int32_t fos_comm_unique_id(uint8_t *id_out /* FOS_COMM_ID_BYTES */);
+/* An all-zero id creates no NCCL communicator: the handle then relies on the peer-memory exchange below
+ * (fos_comm_p2p_export / _import must follow the load); used where NCCL cannot run, e.g. several ranks on one GPU. */
 int32_t fos_comm_init(fos_handle_t h, int32_t rank, int32_t nranks, const uint8_t *id /* FOS_COMM_ID_BYTES */);
 /* Fused exchange over NVLink peer memory (optional, after fos_load_conic_dense on every rank): replaces
  * the fold kernel + ncclAllReduce of every pass over A by ONE kernel that publishes this rank's partial

@@ -42,20 +42,45 @@ def timed(torch, stream, fn):
 
 
 def run_c5(args):
+    """C5: `--nprob` independent NNLS 256 x 512 problems (conic form m = 769, n = 513), FISTA and Dykstra.  Under
+    torchrun the batch is split across the ranks with parallel.batch_shard (no collective on the data
+    path); problems are generated in chunks of 64 with chunk-indexed seeds, so the batch is the same for every
+    rank count.  Timing: barrier, CUDA events on every rank's library stream, max over ranks."""
+    import os
     import torch
     import fos_b200 as fos
-    dev = torch.device("cuda", 0)
-    B, rows, cols = args.nprob, 256, 512
+    from fos_b200 import parallel
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    Btot, rows, cols = args.nprob, 256, 512
+    p0, B = parallel.batch_shard(Btot, rank, world)
     m, n = rows + 1 + cols, cols + 1
-    g = torch.Generator(device=dev)
-    g.manual_seed(5)
-    D = torch.randn((B, rows, cols), dtype=torch.float64, device=dev, generator=g) / np.sqrt(cols)
-    d = torch.randn((B, rows), dtype=torch.float64, device=dev, generator=g)
+    CH = 64
+    D = torch.empty((B, rows, cols), dtype=torch.float64, device=dev)
+    d = torch.empty((B, rows), dtype=torch.float64, device=dev)
+    c0 = (p0 // CH) * CH
+    while c0 < p0 + B:
+        g = torch.Generator(device=dev)
+        g.manual_seed(5 * 1000003 + c0 // CH)
+        Dc = torch.randn((CH, rows, cols), dtype=torch.float64, device=dev, generator=g) / np.sqrt(cols)
+        dc = torch.randn((CH, rows), dtype=torch.float64, device=dev, generator=g)
+        lo, hi = max(c0, p0), min(c0 + CH, p0 + B)
+        D[lo - p0:hi - p0] = Dc[lo - c0:hi - c0]
+        d[lo - p0:hi - p0] = dc[lo - c0:hi - c0]
+        c0 += CH
     A = torch.zeros((B, m, n), dtype=torch.float64, device=dev)
     A[:, 0, 0] = -1.0
     A[:, 1:rows + 1, 1:] = -D
     idx = torch.arange(cols, device=dev)
     A[:, rows + 1 + idx, 1 + idx] = -1.0
+    del D
     b = np.zeros((B, m))
     b[:, 1:rows + 1] = -d.cpu().numpy()
     c = np.zeros((B, n))
@@ -63,7 +88,7 @@ def run_c5(args):
     cones1, cones2 = [("SOC", rows + 1), ("NonNeg", cols)], [("Free", n)]
     peak, peak_src = peak_hbm()
     for name, alg in (("FISTA", fos.FISTA()), ("Dykstra", fos.Dykstra())):
-        H = fos.Handle(0)
+        H = fos.Handle(local)
         H.set_option("batch_hybrid", 0 if args.dense_batch else 1)
         if args.batch_ctas:
             H.set_option("batch_ctas", args.batch_ctas)
@@ -73,21 +98,34 @@ def run_c5(args):
         H.ck(H.L.fos_begin_solve_batch(H.h))
         W, K = args.warmup, args.iters
         H.run_batch(1, W, 10 ** 9, 1e-5)
-        p0 = H.info_batch("total_passes").sum()
+        pp0 = H.info_batch("total_passes").sum()
         cg0 = H.info_batch("total_cg").sum()
+        if world > 1:
+            dist.barrier()
         ms, (done, st, recs) = timed(torch, stream, lambda: H.run_batch(W + 1, K, K, 1e-5))
-        passes = H.info_batch("total_passes").sum() - p0
+        passes = H.info_batch("total_passes").sum() - pp0
         cgs = H.info_batch("total_cg").sum() - cg0
-        bytes_pass = H.info("bytes_per_pass")   # dense rows as FP64 + sparse rows as CSR/CSC entries
-        gbs = passes * bytes_pass / (ms / 1e3) / 1e9
-        line = {"config": "C5", "batch_ctas": args.batch_ctas, "dense_equivalent_bytes_per_pass": 8.0 * m * n, "algorithm": name, "nprob": B, "m": m, "n": n, "iterations_timed": K,
-                "ms_total": ms, "problem_iterations_per_s": B * K / (ms / 1e3),
-                "iterations_per_s_per_problem_stream": K / (ms / 1e3),
-                "cg_iterations_per_step": cgs / (B * K), "passes_over_A_per_step": passes / (B * K),
-                "algorithmic_bytes_per_pass": bytes_pass, "achieved_gbs": gbs, "peak_gbs": peak, "frac": gbs / peak,
-                "peak_source": peak_src, "all_iterated": bool((done == K).all()),
-                "check_p_median": float(np.median([r[-1][1] for r in recs if len(r)])) if K else None}
-        if args.cpu:
+        ms_local = ms
+        tot = torch.tensor([float(passes), float(cgs), float((done == K).all()), float(np.sum(H.get_iterate_batch()))],
+                           dtype=torch.float64, device=dev)
+        if world > 1:
+            tt = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+            dist.all_reduce(tot)
+        passes_all, cgs_all, all_done, checksum = [float(x) for x in tot.tolist()]
+        bytes_pass = H.info("bytes_per_pass")   # dense rows as FP64 + sparse rows as CSR/CSC entries, per problem
+        gbs = passes_all * bytes_pass / (ms / 1e3) / 1e9
+        line = {"config": "C5", "n_gpus": world, "algorithm": name, "nprob": Btot, "nprob_per_gpu": B, "m": m, "n": n,
+                "batch_ctas": args.batch_ctas, "dense_equivalent_bytes_per_pass": 8.0 * m * n,
+                "iterations_timed": K, "ms_total": ms, "ms_rank0": ms_local,
+                "problem_iterations_per_s": Btot * K / (ms / 1e3),
+                "cg_iterations_per_step": cgs_all / (Btot * K), "passes_over_A_per_step": passes_all / (Btot * K),
+                "algorithmic_bytes_per_pass": bytes_pass, "aggregate_gbs": gbs, "per_gpu_gbs": gbs / world,
+                "peak_gbs_per_gpu": peak, "frac_per_gpu": gbs / world / peak, "peak_source": peak_src,
+                "all_iterated": bool(all_done == world), "iterate_checksum": checksum,
+                "check_p_median_rank0": float(np.median([r[-1][1] for r in recs if len(r)])) if K else None}
+        if args.cpu and rank == 0:
             from oracle import fos_oracle as fo
             import scipy.sparse as sp
             fo.build()
@@ -102,8 +140,11 @@ def run_c5(args):
             dt = time.perf_counter() - t0
             line["cpu_baseline"] = {"value": kk / dt, "unit": "problem-iterations/s", "cores": 1, "kind": "port",
                                     "sample": f"oracle (C, CSC) on problem 0, iterations {W + 1}..{W + kk}"}
-        print(json.dumps(line), flush=True)
+        if rank == 0:
+            print(json.dumps(line), flush=True)
         del H
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def run_c4(args):

@@ -1,5 +1,11 @@
-"""Run under torchrun (one rank per GPU): row-sharded A + NCCL all-reduce inside the library must
-reproduce the single-GPU iterates.  Exit code 0 = parity holds on every rank."""
+"""Run under torchrun (one rank per GPU): row-sharded A + the exchange inside the library (NCCL all-reduce, and the
+fused peer-memory kernels) must reproduce the single-GPU iterates.  Exit code 0 = parity holds on
+every rank.
+
+  --same-device   every rank uses cuda:0 (rendezvous over gloo, no NCCL communicator: NCCL refuses two ranks on one
+                  GPU): the peer-memory exchange between PROCESSES is exercised on a box with a single GPU -- the
+                  kernels of the two ranks are time-sliced, each exchange completes when the peer gets its slice.
+"""
 import ctypes as C
 import os
 import sys
@@ -33,10 +39,16 @@ def main():
     rank = int(os.environ["RANK"])
     world = int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
+    one_dev = "--same-device" in sys.argv
+    if one_dev:
+        local = 0
     torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if one_dev:
+        dist.init_process_group("gloo")
+    else:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ok = True
-    cases = [(m, n, scale, tol, alg, ex) for ex in ("nccl", "p2p")
+    cases = [(m, n, scale, tol, alg, ex) for ex in (("p2p",) if one_dev else ("nccl", "p2p"))
              for (m, n, scale, tol, alg) in ((1000, 2500, 0.1, 1e-10, "DR"), (2000, 1300, 1.0, 1e-4, "GAPA"),
                                              (333, 4100, 0.1, 1e-10, "FISTA"))]
     for (m, n, scale, tol, alg, ex) in cases:
@@ -44,11 +56,11 @@ def main():
         A = np.asarray(P.A)
         r0, cnt = parallel.row_shard(m, rank, world)
         Hs = fos.Handle(local)
-        cid = parallel.exchange_comm_id(rank, parallel.nccl_unique_id, dist)
+        cid = None if one_dev else parallel.exchange_comm_id(rank, parallel.nccl_unique_id, dist)
         parallel.init_comm(Hs, rank, world, cid)
         load_dense(Hs, P, A[r0:r0 + cnt], r0, cnt)
         if ex == "p2p":  # fused peer-memory exchange kernel instead of fold + ncclAllReduce
-            parallel.enable_p2p_exchange(Hs, rank, world, dist)
+            assert parallel.enable_p2p_exchange(Hs, rank, world, dist) or not one_dev, "CUDA IPC unavailable"
         H1 = fos.Handle(local)  # unsharded reference on the same device
         load_dense(H1, P, A, 0, m)
         for H in (Hs, H1):
@@ -82,7 +94,7 @@ def main():
         Hs.ck(Hs.L.fos_begin_solve(Hs.h))
         done, st, rec, _ = Hs.run(1, 60, 10, 1e-7)
         sig = torch.tensor([float(done), float(st), float(Hs.info("total_cg")), float(np.sum(Hs.get_iterate()))],
-                           dtype=torch.float64, device="cuda")
+                           dtype=torch.float64, device="cpu" if one_dev else "cuda")
         sigs = [torch.empty_like(sig) for _ in range(world)]
         dist.all_gather(sigs, sig)
         same = all(torch.equal(sigs[0], t) for t in sigs)
@@ -90,7 +102,7 @@ def main():
             ok = False
             print(f"rank {rank}: free-running state differs across ranks [{ex}] {sigs}", flush=True)
         del Hs, H1
-    flag = torch.tensor([0 if ok else 1], device="cuda")
+    flag = torch.tensor([0 if ok else 1], device="cpu" if one_dev else "cuda")
     dist.all_reduce(flag)
     dist.destroy_process_group()
     sys.exit(1 if flag.item() else 0)

@@ -133,7 +133,7 @@ def three_way(step_other, P, oracle, alg, n_iter):
     return np.array(e_c), np.array(e_o), f_c, f_o
 
 
-def assert_no_worse_than_reference_arithmetic(tag, e_c, e_o, f_c, f_o, min_iters=6, who="GPU"):
+def assert_no_worse_than_reference_arithmetic(tag, e_c, e_o, f_c, f_o, min_iters=6, who="GPU", premise=True):
     ratio = e_o / e_c
     gm = float(np.exp(np.mean(np.log(ratio))))
     print(f"{tag}: C-vs-exact median {np.median(e_c):.2e} max {e_c.max():.2e} flips {f_c} | "
@@ -145,6 +145,7 @@ def assert_no_worse_than_reference_arithmetic(tag, e_c, e_o, f_c, f_o, min_iters
     assert np.median(e_o) <= 2.0 * np.median(e_c)
     assert e_o.max() <= 50.0 * e_c.max()
     # and the premise of the test: the reference's arithmetic is itself NOT within 1e-10 of exact here
-    assert e_c.max() > 1e-10
+    if premise:
+        assert e_c.max() > 1e-10
 
 
