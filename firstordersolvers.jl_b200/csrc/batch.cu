@@ -28,7 +28,7 @@ namespace {
 struct BK {
     const BatchArgs *a;
     int ct, NT, warp, lane;
-    double *tiles, *s_ax, *s_atw, *s_x, *s_wv, *s_red;
+    double *tiles, *s_ax, *s_atw, *s_part, *s_wv, *s_red;
     SocScale *s_soc;
     uint64_t *full, *empty;
     uint32_t t;  // tiles consumed so far by this CTA
@@ -71,12 +71,14 @@ __device__ __forceinline__ void bt_reduce(BK &k, double (&q)[NQ])
 }
 
 // One pass over A: s_ax[v] = A * X_v, s_atw[v] = A' * W_v, v = 0, 1.
-// Two thread mappings read each tile from shared memory:
-//   * column owners (all consumer threads): thread ct owns column pairs ct + kk*NT and keeps the four
-//     column sums of A'W in registers for the whole pass -- no reduction at all;
-//   * row owners: warp r takes row r of the tile (BT_TR = 8 rows), lanes stride the columns, one
-//     warp_sum per right-hand side gives the finished row of A X.
-// No cross-warp reduction and no CTA barrier inside the tile loop: warps drift apart by up to S tiles.
+// Every tile element is read from shared memory ONCE (round 1 read it twice -- once by a column owner, once by a
+// row owner -- plus two X loads per element: the shared-memory pipe sat at 70 % of its peak and bounded the pass;
+// profiles/r1_ncu_other_kernels.md).  Thread ct owns the column pairs ct + kk*NT for the whole pass:
+//   * the X entries of its columns live in registers (no X staging in shared memory at all);
+//   * the four column sums of A'W per pair stay in registers for the whole pass -- no reduction;
+//   * its contribution to the 8 x 2 row sums of a tile is reduced over the warp with the transposed butterfly of
+//     the single-problem kernel (16 values -> 16 shuffles), then over the consumer warps through a double-buffered
+//     shared array: one consumer barrier per tile, fixed order -> deterministic.
 template <int KP>
 __device__ __forceinline__ void bt_pass(BK &k, const double *X0, const double *X1, const double *W0, const double *W1)
 {
@@ -88,11 +90,16 @@ __device__ __forceinline__ void bt_pass(BK &k, const double *X0, const double *X
     const int64_t n_pad = a.L.n_pad, m_pad = a.L.m_pad;
     const int mr = a.mr;
     const int CW = k.NT >> 5;
-    for (int64_t e = k.ct; e < n_pad; e += k.NT) {
-        k.s_x[e] = X0[e];
-        k.s_x[n_pad + e] = X1[e];
+    constexpr int V = 2 * BT_TR;  // row sums per tile
+    double2 xv[KP][2];
+#pragma unroll
+    for (int kk = 0; kk < KP; kk++) {
+        const int cp = k.ct + kk * k.NT;
+        const bool in = cp < npairs && 2 * (int64_t)cp < n_pad;
+        xv[kk][0] = in ? *reinterpret_cast<const double2 *>(X0 + 2 * cp) : make_double2(0.0, 0.0);
+        xv[kk][1] = in ? *reinterpret_cast<const double2 *>(X1 + 2 * cp) : make_double2(0.0, 0.0);
     }
-    for (int64_t e = k.ct; e < m_pad; e += k.NT) {  // W rides in shared memory too: 16 broadcast reads per tile
+    for (int64_t e = k.ct; e < m_pad; e += k.NT) {  // W rides in shared memory: 16 broadcast reads per tile
         k.s_wv[e] = W0[e];
         k.s_wv[mr + e] = W1[e];
     }
@@ -104,10 +111,12 @@ __device__ __forceinline__ void bt_pass(BK &k, const double *X0, const double *X
         mbar_wait(&k.full[k.stage], k.phase);
         const double *tp = k.tiles + (size_t)k.stage * tile_elems;
         const int row0 = tile * BT_TR;
+        double rs[V];
 #pragma unroll
         for (int r = 0; r < BT_TR; r++) {
             const int rr = __ldg(k.drow + row0 + r);  // original row of this tile row
             const double w0 = k.s_wv[rr], w1 = k.s_wv[mr + rr];
+            double s0 = 0.0, s1 = 0.0;
 #pragma unroll
             for (int kk = 0; kk < KP; kk++) {
                 const int cp = k.ct + kk * k.NT;
@@ -117,31 +126,27 @@ __device__ __forceinline__ void bt_pass(BK &k, const double *X0, const double *X
                     ca[kk][0].y = fma(e.y, w0, ca[kk][0].y);
                     ca[kk][1].x = fma(e.x, w1, ca[kk][1].x);
                     ca[kk][1].y = fma(e.y, w1, ca[kk][1].y);
+                    s0 = fma(e.x, xv[kk][0].x, s0);
+                    s0 = fma(e.y, xv[kk][0].y, s0);
+                    s1 = fma(e.x, xv[kk][1].x, s1);
+                    s1 = fma(e.y, xv[kk][1].y, s1);
                 }
             }
-        }
-        for (int r = k.warp; r < BT_TR; r += CW) {
-            const double *rowp = tp + (size_t)r * lda;
-            double a0x = 0.0, a0y = 0.0, a1x = 0.0, a1y = 0.0;
-#pragma unroll 3
-            for (int cp = k.lane; cp < npairs; cp += 32) {
-                const double2 e = *reinterpret_cast<const double2 *>(rowp + 2 * cp);
-                const double2 x0 = *reinterpret_cast<const double2 *>(k.s_x + 2 * cp);
-                const double2 x1 = *reinterpret_cast<const double2 *>(k.s_x + n_pad + 2 * cp);
-                a0x = fma(e.x, x0.x, a0x);
-                a0y = fma(e.y, x0.y, a0y);
-                a1x = fma(e.x, x1.x, a1x);
-                a1y = fma(e.y, x1.y, a1y);
-            }
-            const double r0 = warp_sum(a0x + a0y), r1 = warp_sum(a1x + a1y);
-            if (k.lane == 0) {
-                const int rr = __ldg(k.drow + row0 + r);
-                k.s_ax[rr] = r0;
-                k.s_ax[mr + rr] = r1;
-            }
+            rs[r] = s0;
+            rs[BT_TR + r] = s1;
         }
         __syncwarp();
-        if (k.lane == 0) mbar_arrive(&k.empty[k.stage]);
+        if (k.lane == 0) mbar_arrive(&k.empty[k.stage]);  // the tile is in registers: hand the stage back early
+        warp_transpose_reduce<V>(rs, k.lane);
+        double *part = k.s_part + (tile & 1) * (16 * V);
+        if ((k.lane & 1) == 0) part[k.warp * V + (k.lane >> 1)] = rs[0];
+        cbar(k.NT);
+        if (k.ct < V) {
+            double sum = 0.0;
+            for (int w = 0; w < CW; w++) sum += part[w * V + k.ct];
+            const int v = k.ct / BT_TR, r = k.ct - v * BT_TR;
+            k.s_ax[v * mr + __ldg(k.drow + row0 + r)] = sum;
+        }
         k.t++;
         if (++k.stage == S) {
             k.stage = 0;
@@ -162,8 +167,8 @@ __device__ __forceinline__ void bt_pass(BK &k, const double *X0, const double *X
         for (int p = __ldg(k.srow_ptr + sr); p < __ldg(k.srow_ptr + sr + 1); p++) {
             const int j = __ldg(k.scol + p);
             const double v = __ldg(k.sval + p);
-            a0 = fma(v, k.s_x[j], a0);
-            a1 = fma(v, k.s_x[n_pad + j], a1);
+            a0 = fma(v, X0[j], a0);
+            a1 = fma(v, X1[j], a1);
         }
         const int row = __ldg(k.srow_id + sr);
         k.s_ax[row] = a0;
@@ -597,9 +602,9 @@ __global__ void __launch_bounds__(MAXT, MINB) k_batch_solve(const BatchArgs a)
     double *tiles = reinterpret_cast<double *>(bt_smem);
     double *s_ax = tiles + (size_t)a.S * tile_elems;
     double *s_atw = s_ax + 2 * a.mr;
-    double *s_x = s_atw + 2 * a.L.n_pad;
-    double *s_wv = s_x + 2 * a.L.n_pad;
-    double *s_red = s_wv + 2 * a.mr;
+    double *s_wv = s_atw + 2 * a.L.n_pad;
+    double *s_part = s_wv + 2 * a.mr;           // [2 tile parities][16 warps][2 * BT_TR] row-sum partials
+    double *s_red = s_part + 2 * 16 * 2 * BT_TR;
     SocScale *s_soc = reinterpret_cast<SocScale *>(s_red + 8 * 16);
     uint64_t *full = reinterpret_cast<uint64_t *>(s_soc + BT_MAX_SOC);
     uint64_t *empty = full + BT_MAX_STAGES;
@@ -618,7 +623,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_batch_solve(const BatchArgs a)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    for (int64_t e = threadIdx.x; e < 4 * ((int64_t)a.mr + a.L.n_pad); e += blockDim.x) s_ax[e] = 0.0;  // ax, atw, x, wv
+    for (int64_t e = threadIdx.x; e < 4 * (int64_t)a.mr + 2 * a.L.n_pad; e += blockDim.x) s_ax[e] = 0.0;  // ax, atw, wv
     __syncthreads();
 
     if (warp == CW) {
@@ -662,7 +667,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_batch_solve(const BatchArgs a)
     k.tiles = tiles;
     k.s_ax = s_ax;
     k.s_atw = s_atw;
-    k.s_x = s_x;
+    k.s_part = s_part;
     k.s_wv = s_wv;
     k.s_red = s_red;
     k.s_soc = s_soc;
@@ -900,8 +905,8 @@ BatchGeom batch_geometry(int64_t m, int64_t n)
     if ((int64_t)g.KP * 32 * BT_MAX_CW < npairs) throw Error(FOS_ERR_UNSUPPORTED, "batch mode: n too large");
     g.CW = std::max(4, (npairs + g.KP * 32 - 1) / (g.KP * 32));
     const size_t tile_bytes = (size_t)BT_TR * g.lda * 8;
-    const size_t fixed = (size_t)(4 * (m_pad + 16) + 4 * n_pad + 8 * 16) * 8 + BT_MAX_SOC * sizeof(SocScale) +
-                         2 * BT_MAX_STAGES * 8 + 64;
+    const size_t fixed = (size_t)(4 * (m_pad + 16) + 2 * n_pad + 2 * 16 * 2 * BT_TR + 8 * 16) * 8 +
+                         BT_MAX_SOC * sizeof(SocScale) + 2 * BT_MAX_STAGES * 8 + 64;
     // two CTAs (= two problems) per SM when they fit: one CTA's vector phases overlap the other's pass
     g.ctas_per_sm = 1;
     g.S = BT_MAX_STAGES;
