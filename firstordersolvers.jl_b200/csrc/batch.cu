@@ -77,7 +77,7 @@ __device__ __forceinline__ void bt_reduce(BK &k, double (&q)[NQ])
 //   * the X entries of its columns live in registers (no X staging in shared memory at all);
 //   * the four column sums of A'W per pair stay in registers for the whole pass -- no reduction;
 //   * its contribution to the 8 x 2 row sums of a tile is reduced over the warp with the transposed butterfly of
-//     the single-problem kernel (16 values -> 16 shuffles), then over the consumer warps through a double-buffered
+//     the single-problem kernel (2*BT_TR values), then over the consumer warps through a double-buffered
 //     shared array: one consumer barrier per tile, fixed order -> deterministic.
 template <int KP>
 __device__ __forceinline__ void bt_pass(BK &k, const double *X0, const double *X1, const double *W0, const double *W1)
@@ -139,7 +139,8 @@ __device__ __forceinline__ void bt_pass(BK &k, const double *X0, const double *X
         if (k.lane == 0) mbar_arrive(&k.empty[k.stage]);  // the tile is in registers: hand the stage back early
         warp_transpose_reduce<V>(rs, k.lane);
         double *part = k.s_part + (tile & 1) * (16 * V);
-        if ((k.lane & 1) == 0) part[k.warp * V + (k.lane >> 1)] = rs[0];
+        constexpr int LPV = 32 / V;  // lanes that end up holding the same value
+        if ((k.lane & (LPV - 1)) == 0) part[k.warp * V + (k.lane / LPV)] = rs[0];
         cbar(k.NT);
         if (k.ct < V) {
             double sum = 0.0;

@@ -186,7 +186,7 @@ struct K1Args {
 template <int V>
 __device__ __forceinline__ void warp_transpose_reduce(double (&vals)[V], int lane)
 {
-    static_assert(V == 16 || V == 32, "V must be 16 or 32");
+    static_assert(V == 8 || V == 16 || V == 32, "V must be 8, 16 or 32");
     int s = 16;
 #pragma unroll
     for (int cnt = V / 2; cnt >= 1; cnt >>= 1, s >>= 1) {
