@@ -12,8 +12,8 @@
 
 namespace fos {
 
-constexpr int BT_TR = 4;            // rows per A tile (NV * TR = 8 row sums per tile): 17 KB tiles at config 5, four
-                                    // ring stages per CTA instead of two 34 KB ones -> three tiles in flight while one is read
+constexpr int BT_TR = 8;            // rows per A tile (NV * TR = 16 row sums per tile).  4-row tiles (four 17 KB stages at
+                                    // config 5) were measured 12 % SLOWER: the per-tile barrier + reduce dominates (profiles/r2_c5_notes.md)
 constexpr int BT_MAX_STAGES = 4;
 constexpr int BT_MAX_CW = 15;       // consumer warps
 constexpr int BT_MAX_KP = 4;        // column pairs per consumer thread

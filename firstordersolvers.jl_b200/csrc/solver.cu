@@ -221,7 +221,22 @@ void ConeSet::build(int64_t NP_, const std::vector<ConeSeg> &segs)
         chunk_sum.alloc((size_t)nchunks);
     }
     counter.alloc(1);
-    if (!psd.empty()) d_psd.upload(psd);
+    if (!psd.empty()) {
+        // tiny cones first: they take the one-warp-per-cone kernel (psd.cu), the others one CTA per cone
+        std::stable_partition(psd.begin(), psd.end(), [](const PsdCone &c) { return c.d <= PSD_WARP_MAX_D; });
+        psd_nsmall = 0;
+        psd_small_max_d = 0;
+        psd_max_d = 0;
+        for (const PsdCone &c : psd) {
+            if (c.d <= PSD_WARP_MAX_D) {
+                psd_nsmall++;
+                psd_small_max_d = std::max<int>(psd_small_max_d, c.d);
+            } else {
+                psd_max_d = std::max<int>(psd_max_d, c.d);
+            }
+        }
+        d_psd.upload(psd);
+    }
     if (!psd_large.empty()) d_psd_large.upload(psd_large);
 }
 

@@ -201,7 +201,8 @@ struct ConeSet {
     DevBuf<uint8_t> psd_ctl;
     DevBuf<double> psd_vstore;   // eigenvector bases of the previous projection (warm start of K5L)
     bool psd_warm = false, psd_warm_enabled = true;
-    int psd_max_d = 0;
+    int psd_max_d = 0;                      // largest cone of the one-CTA-per-cone kernel
+    int psd_nsmall = 0, psd_small_max_d = 0;  // psd[0 .. psd_nsmall): d <= PSD_WARP_MAX_D, one warp per cone
     bool fusable = true;  // every cone projects entry by entry from (x_e, per-cone scalars): RelaxArgs may feed it
     void build(int64_t NP_, const std::vector<ConeSeg> &segs);
 };
@@ -374,6 +375,7 @@ struct Handle {
     } while (0)
 
 constexpr int PSD_SMEM_MAX_D = 112;  // largest cone whose S and V fit one SM's shared memory
+constexpr int PSD_WARP_MAX_D = 32;   // up to here a cone is projected by ONE WARP (eight cones per CTA, no block barriers)
 void psd_project(Handle *h, ConeSet &K, const double *in, double *projbuf);        // K5, psd.cu
 void psd_project_large(Handle *h, ConeSet &K, const double *in, double *projbuf);  // K5, psd_large.cu
 int psd_large_last_sweeps(Handle *h, ConeSet &K);

@@ -157,8 +157,8 @@ def test_batch_mode_geometry(fos):
         assert L.fos_batch_plan(m, n, out) == 0, (m, n)
         lda, ntiles, S, CW, KP, cps, smem, a_stride = list(out)
         assert lda % 16 == 0 and lda >= n and lda - n < 16
-        assert ntiles * 4 >= m > (ntiles - 1) * 4          # tiles of BT_TR = 4 rows
-        assert a_stride == ntiles * 4 * lda
+        assert ntiles * 8 >= m > (ntiles - 1) * 8          # tiles of BT_TR = 8 rows
+        assert a_stride == ntiles * 8 * lda
         assert 2 <= S <= 4 and 4 <= CW <= 15 and 1 <= KP <= 4
         assert KP * 32 * CW >= lda // 2                      # every column pair is owned by a consumer thread
         assert (KP - 1) * 32 * 15 < lda // 2                 # ... with the smallest KP that can cover the row
@@ -168,7 +168,7 @@ def test_batch_mode_geometry(fos):
             assert 2 * (smem + 1024) <= 227 * 1024 and (CW + 1) * 32 <= 320 and KP == 1
     assert list(out[:6]) != []                               # last call succeeded
     L.fos_batch_plan(769, 513, out)
-    assert list(out)[:6] == [528, 193, 4, 9, 1, 2]           # config 5: four 17 KB stages, nine consumer warps, two problems per SM
+    assert list(out)[:6] == [528, 97, 2, 9, 1, 2]            # config 5: nine consumer warps, two problems per SM
     assert L.fos_batch_plan(100, 1281, out) == -3            # FOS_ERR_UNSUPPORTED: n > 1280
     assert L.fos_batch_plan(7000, 700, out) == -3            # the A X / W staging of m = 7000 rows does not fit an SM
     assert L.fos_batch_plan(0, 5, out) != 0
