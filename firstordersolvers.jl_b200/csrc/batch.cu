@@ -99,9 +99,15 @@ __device__ __forceinline__ void bt_pass(BK &k, const double *X0, const double *X
         xv[kk][0] = in ? *reinterpret_cast<const double2 *>(X0 + 2 * cp) : make_double2(0.0, 0.0);
         xv[kk][1] = in ? *reinterpret_cast<const double2 *>(X1 + 2 * cp) : make_double2(0.0, 0.0);
     }
-    for (int64_t e = k.ct; e < m_pad; e += k.NT) {  // W rides in shared memory: 16 broadcast reads per tile
-        k.s_wv[e] = W0[e];
-        k.s_wv[mr + e] = W1[e];
+    // W rides in shared memory IN TILE-ROW ORDER (gathered through drow once per pass): the inner loop then reads it
+    // at compile-time offsets instead of chasing drow -> address per row (a dependent global load per row, 8.5 % of
+    // the kernel's stall samples: profiles/r2_c5_notes.md); padding rows of the last tile read 0
+    const int nrows_t = a.ntiles * BT_TR;
+    for (int t = k.ct; t < nrows_t; t += k.NT) {
+        const int rr = __ldg(k.drow + t);
+        const bool real = rr < m_pad;
+        k.s_wv[t] = real ? W0[rr] : 0.0;
+        k.s_wv[mr + t] = real ? W1[rr] : 0.0;
     }
     double2 ca[KP][2];
 #pragma unroll
@@ -114,8 +120,7 @@ __device__ __forceinline__ void bt_pass(BK &k, const double *X0, const double *X
         double rs[V];
 #pragma unroll
         for (int r = 0; r < BT_TR; r++) {
-            const int rr = __ldg(k.drow + row0 + r);  // original row of this tile row
-            const double w0 = k.s_wv[rr], w1 = k.s_wv[mr + rr];
+            const double w0 = k.s_wv[row0 + r], w1 = k.s_wv[mr + row0 + r];
             double s0 = 0.0, s1 = 0.0;
 #pragma unroll
             for (int kk = 0; kk < KP; kk++) {
@@ -182,8 +187,8 @@ __device__ __forceinline__ void bt_pass(BK &k, const double *X0, const double *X
         for (int p = __ldg(k.ccol_ptr + sc); p < __ldg(k.ccol_ptr + sc + 1); p++) {
             const int i = __ldg(k.crow + p);
             const double v = __ldg(k.cval + p);
-            a0 = fma(v, k.s_wv[i], a0);
-            a1 = fma(v, k.s_wv[mr + i], a1);
+            a0 = fma(v, W0[i], a0);  // W by original row: straight from the (L1-resident) vector
+            a1 = fma(v, W1[i], a1);
         }
         const int col = __ldg(k.ccol_id + sc);
         k.s_atw[col] += a0;
