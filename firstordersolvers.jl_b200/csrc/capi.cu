@@ -118,7 +118,8 @@ int32_t fos_set_option(fos_handle_t hh, const char *key, double value)
         h.batch_hybrid = value != 0;
     } else if (k == "hybrid_rows") {
         FOS_REQUIRE(!h.loaded, "hybrid_rows must be set before loading the problem");
-        h.hybrid_rows = value != 0;
+        FOS_REQUIRE(value == 0 || value == 1 || value == 2, "hybrid_rows must be 0 (off), 1 (whenever it saves bytes) or 2 (auto)");
+        h.hybrid_rows = (int)value;
     } else if (k == "batch_ctas") {
         h.batch_ctas = (int)value;
         if (h.batch) h.batch->grid_ctas = (int)value;
@@ -226,7 +227,7 @@ static void load_matrix_csc(Handle &h, int64_t m, int64_t n, const int64_t *colp
                 D[(size_t)i * (size_t)n + (size_t)j] += nzval[k];
             }
         if (h.hybrid_rows)
-            h.A.init_hybrid(m, n, D.data(), n, FOS_MEM_HOST, h.grid_ctas, h.stream);
+            h.A.init_hybrid(m, n, D.data(), n, FOS_MEM_HOST, h.grid_ctas, h.stream, h.hybrid_rows == 2);
         else
             h.A.init_dense(m, n, D.data(), n, FOS_MEM_HOST, 0, m, h.grid_ctas, h.stream);
     } else {
@@ -264,7 +265,7 @@ int32_t fos_load_conic_dense(fos_handle_t hh, int64_t m, int64_t n, const double
     if (a_location == FOS_MEM_DEVICE) FOS_CUDA(cudaDeviceSynchronize());
     h.A.impl = h.matvec_impl;
     if (h.hybrid_rows && h.nranks == 1 && row_begin == 0 && row_count == m)
-        h.A.init_hybrid(m, n, A, lda, a_location, h.grid_ctas, h.stream);
+        h.A.init_hybrid(m, n, A, lda, a_location, h.grid_ctas, h.stream, h.hybrid_rows == 2);
     else
         h.A.init_dense(m, n, A, lda, a_location, row_begin, row_count, h.grid_ctas, h.stream);
     h.load_conic(m, n, b, c, ncones1, cone_type1, cone_len1, ncones2, cone_type2, cone_len2);

@@ -245,7 +245,7 @@ HybridPlan hybrid_row_plan(const int32_t *row_nnz, int64_t m, int64_t n)
 }
 
 void MatOp::init_hybrid(int64_t m_, int64_t n_, const double *Asrc, int64_t lda_src, int location, int grid_ctas,
-                        cudaStream_t st)
+                        cudaStream_t st, bool auto_only)
 {
     FOS_REQUIRE(nranks == 1, "hybrid row storage is not offered with row sharding");
     init_dense(m_, n_, Asrc, lda_src, location, 0, m_, grid_ctas, st);  // A / lda: the whole matrix on the device
@@ -260,6 +260,10 @@ void MatOp::init_hybrid(int64_t m_, int64_t n_, const double *Asrc, int64_t lda_
     FOS_CUDA(cudaMemcpy(rn.data(), d_nnz.p, rn.size() * 4, cudaMemcpyDeviceToHost));
     HybridPlan hp = hybrid_row_plan(rn.data(), m, n);
     if (!hp.use) return;  // nothing to gain: the matrix stays dense (kind 1)
+    if (auto_only) {
+        const double saved = 8.0 * (double)m * (double)n - (8.0 * (double)hp.md * (double)n + 24.0 * (double)hp.sparse_nnz);
+        if (saved < 64.0 * 1024.0 * 1024.0) return;  // three more launches per pass would cost more than the bytes saved
+    }
     const int64_t r0 = hp.r0, r1 = hp.r0 + hp.md, md = hp.md, nz = hp.sparse_nnz;
     std::vector<int32_t> row_id, row_ptr(1, 0);
     {

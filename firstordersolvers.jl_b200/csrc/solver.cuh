@@ -149,8 +149,10 @@ struct MatOp {
     // device; the contiguous range that holds every row with more than n/8 non-zeros stays dense (K1 streams only
     // that block), the other non-empty rows are kept as CSR + CSC.  Falls back to plain dense storage (kind 1) when
     // that would not save at least 2 % of the bytes of a pass.  Single rank only.
+    // auto_only: keep the dense layout unless the bytes saved per pass are worth the three extra launches per pass
+    // (>= 64 MB, i.e. >= ~10 us of HBM time: config 3 saves 3.2 GB, a 24000 x 4000 problem would lose)
     void init_hybrid(int64_t m_, int64_t n_, const double *Asrc, int64_t lda_src, int location, int grid_ctas,
-                     cudaStream_t st);
+                     cudaStream_t st, bool auto_only = false);
     int64_t hyb_sparse_rows = 0;  // rows kept as CSR / CSC (kind 3)
     double bytes_per_pass() const;
     // Runs one pass; X[v] have n_pad entries, W[v] have m_pad entries (global rows).
@@ -253,7 +255,7 @@ struct Handle {
     int num_sms = 148;
     std::string err;
     // options
-    int matvec_impl = 0, grid_ctas = 0, cg_batch = 0, fuse_rhs = 1, batch_ctas = 0, fuse_tail = 1, batch_hybrid = 1, tail_blocks = 0, tail_flag_mode = 0, hybrid_rows = 0;
+    int matvec_impl = 0, grid_ctas = 0, cg_batch = 0, fuse_rhs = 1, batch_ctas = 0, fuse_tail = 1, batch_hybrid = 1, tail_blocks = 0, tail_flag_mode = 0, hybrid_rows = 2;
     // problem
     bool loaded = false;
     Lay L{};

@@ -107,9 +107,11 @@ const char *fos_last_error(fos_handle_t h);
  *                  of ~10); 0 = always start from the identity.  Set after loading.
  *   "exchange_impl" multi-GPU: 1 = fused peer-memory exchange (after fos_comm_p2p_import), 0 = NCCL
  *   "profile_matvec" 1 = CUDA events around every mat-vec launch (read back with fos_get_info)
- *   "hybrid_rows"  1 = single-problem dense loads classify the rows on the device and keep only the contiguous block
- *                  that holds every row with more than n/8 non-zeros as dense tiles; the other non-empty rows are
- *                  stored as CSR + CSC (default 0 this round: opt-in; set before loading; single rank only)
+ *   "hybrid_rows"  single-problem dense loads classify the rows on the device and keep only the contiguous block that
+ *                  holds every row with more than n/8 non-zeros as dense tiles; the other non-empty rows (the -I blocks
+ *                  of SOC / NonNeg constraints on the variables) are stored as CSR + CSC.  2 (default) = only when that
+ *                  saves at least 64 MB per pass (config 3: 19.2 -> 16.0 GB, +17 % iterations/s); 1 = whenever it saves
+ *                  2 % of the bytes; 0 = never.  Set before loading; single rank only.
  *   "batch_hybrid" 1 (default) = batch mode keeps rows with <= n/8 non-zeros out of the dense tiles (CSR + CSC) and
  *                  skips empty rows; 0 = every row is streamed as dense FP64.  Set before loading the batch.
  *   "batch_ctas"   persistent CTAs of the batch kernel (default = #SMs)

@@ -240,8 +240,11 @@ def run_c3(args):
     c[0] = 1.0
     cones1, cones2 = [("SOC", md + 1), ("SOC", nx + 1)], [("Free", n)]
     H = fos.Handle(local)
-    if getattr(args, "hybrid", False) and world == 1:
-        H.set_option("hybrid_rows", 1)   # dense block of the D rows through K1, the -I rows as CSR + CSC
+    if world == 1:   # dense block of the D rows through K1, the -I rows as CSR + CSC (default: automatic)
+        if getattr(args, "hybrid", False):
+            H.set_option("hybrid_rows", 1)
+        elif getattr(args, "no_hybrid", False):
+            H.set_option("hybrid_rows", 0)
     if world > 1:
         cid = parallel.exchange_comm_id(rank, parallel.nccl_unique_id, dist)
         parallel.init_comm(H, rank, world, cid)
@@ -296,7 +299,8 @@ def main():
     ap.add_argument("--batch-ctas", type=int, default=0, help="c5: persistent CTAs of the batch kernel (0 = default)")
     ap.add_argument("--dense-batch", action="store_true", help="c5: stream every row as dense FP64 (batch_hybrid = 0)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"])
-    ap.add_argument("--hybrid", action="store_true", help="c3, one GPU: hybrid row storage (option hybrid_rows = 1)")
+    ap.add_argument("--hybrid", action="store_true", help="c3, one GPU: force the hybrid row storage (hybrid_rows = 1)")
+    ap.add_argument("--no-hybrid", action="store_true", help="c3, one GPU: all rows as dense tiles (hybrid_rows = 0)")
     args = ap.parse_args()
     {"c3": run_c3, "c4": run_c4, "c5": run_c5}[args.config](args)
 
