@@ -81,6 +81,8 @@ struct Ctrl {
     int64_t s1_calls_dev;   // S1.i (affinepluslinear.jl:66): indexes the tolerance table, advanced by k_iter_begin
     int64_t cur_i;          // iteration index (solverwrapper.jl:24), advanced by k_iter_begin
     int64_t total_cg_dev;   // CG iterations executed since the run started
+    double fista_t;         // FISTA's t (fista.jl:14) while the graph path runs; the host copy is synchronised around it
+    double fista_coef;      // (t_old - 1) / t of the current iteration (fista.jl:45-46), set by k_iter_begin
     uint32_t p2p_error;  // host copy only: peer-exchange timeout flag fetched by sync_ctrl
     uint32_t pad_;
 };

@@ -350,9 +350,11 @@ static __global__ void k_cg_begin(Ctrl *ctrl, double tol, int max_iters)
 //                                                            max(0.2^sqrt(i), l*eps) so that both paths compare ||r||
 //                                                            with the same bits)
 //   i += 1 ; done = 0 ; iter = 0
+//   FISTA: told = t ; t = (1 + sqrt(1 + 4 told^2)) / 2 ; coef = (told - 1) / t   (fista.jl:44-46; every operation
+//   rounded separately, like the host's -- the legacy path computes the same bits in Handle::step)
 static __global__ void __launch_bounds__(VBLOCK)
 k_iter_begin(Lay L, const double *__restrict__ x0, const double *__restrict__ xin, double *__restrict__ dvec,
-             Ctrl *ctrl, const double *__restrict__ tol_table, int tbl_n, int max_iters)
+             Ctrl *ctrl, const double *__restrict__ tol_table, int tbl_n, int max_iters, int fista)
 {
     for (int64_t e = (int64_t)blockIdx.x * VBLOCK + threadIdx.x; e < L.NP; e += (int64_t)gridDim.x * VBLOCK)
         dvec[e] = e < L.LP ? x0[e] : sub_(x0[e], xin[e]);
@@ -364,6 +366,12 @@ k_iter_begin(Lay L, const double *__restrict__ x0, const double *__restrict__ xi
         ctrl->max_iters = max_iters;
         ctrl->done = 0;
         ctrl->iter = 0;
+        if (fista) {
+            const double told = ctrl->fista_t;
+            const double t = __ddiv_rn(__dadd_rn(1.0, __dsqrt_rn(__dadd_rn(1.0, __dmul_rn(__dmul_rn(4.0, told), told)))), 2.0);
+            ctrl->fista_t = t;
+            ctrl->fista_coef = __ddiv_rn(__dsub_rn(told, 1.0), t);
+        }
     }
 }
 
@@ -711,6 +719,7 @@ struct EpiArgs {
     double *aux2;      // FISTA: y (out)    ; Dykstra: y (in)
     double ls_alpha;   // EPI_LS / EPI_LSW: the step length tested
     int use_a12;       // EPI_GAPP_PROJ / EPI_LSW: take alpha2 from ctrl->alpha12 (GAPA under LineSearchWrapper)
+    int coef_from_ctrl;  // EPI_FISTA on the graph path: coef = ctrl->fista_coef (set by k_iter_begin)
 };
 
 // proj = P_S2(in);  then the algorithm-specific epilogue:
@@ -733,6 +742,7 @@ k4_cone_apply(int64_t NP, const double *__restrict__ in, double *__restrict__ pr
         rb_ = 1.0 - ra;
     }
     double a2 = E.a2, om_a2 = E.om_a2;
+    const double fcoef = (EPI == EPI_FISTA && E.coef_from_ctrl) ? ctrl->fista_coef : E.coef;
     if (EPI == EPI_GAPA || ((EPI == EPI_GAPP_PROJ || EPI == EPI_LSW) && E.use_a12)) {
         a2 = ctrl->alpha12;
         om_a2 = 1.0 - a2;
@@ -762,7 +772,7 @@ k4_cone_apply(int64_t NP, const double *__restrict__ in, double *__restrict__ pr
             const double xo = E.x[e];
             E.aux1[e] = xo;
             E.x[e] = pj;
-            E.aux2[e] = add_(pj, mul_(E.coef, sub_(pj, xo)));
+            E.aux2[e] = add_(pj, mul_(fcoef, sub_(pj, xo)));
         } else if (EPI == EPI_DYKSTRA) {
             E.x[e] = pj;
             E.aux1[e] = sub_(t1, pj);

@@ -831,6 +831,7 @@ int64_t Handle::run(int64_t i_start, int64_t n_iters, int64_t checki, double eps
     h_ctrl->s1_calls_dev = s1_calls;
     h_ctrl->cur_i = i_start - 1;
     h_ctrl->total_cg_dev = 0;
+    h_ctrl->fista_t = fista_t;
     FOS_CUDA(cudaMemcpyAsync(d_ctrl.p, h_ctrl, sizeof(Ctrl), cudaMemcpyHostToDevice, stream));
     int64_t done = 0;
     if (!trace && graph_ok()) {
@@ -878,7 +879,8 @@ void Handle::finish(double *guess, double *record, int64_t *n_rec)
 // =======================================================================================
 bool Handle::graph_ok() const
 {
-    return use_graphs && loaded && L.form == 0 && (alg == FOS_ALG_GAP || alg == FOS_ALG_GAPA) && lsinterval == 0 &&
+    return use_graphs && loaded && L.form == 0 &&
+           (alg == FOS_ALG_GAP || alg == FOS_ALG_GAPA || alg == FOS_ALG_FISTA || alg == FOS_ALG_DYKSTRA) && lsinterval == 0 &&
            !direct && fuse_rhs && fuse_tail && A.kind == 1 && A.impl == 0 && cones.fusable && !A.profile &&
            (A.nranks == 1 || A.p2p_on) && L.NP > 0;
 }
@@ -915,16 +917,23 @@ void Handle::build_iter_graph(bool with_check)
     try {
         FOS_CUDA(cudaStreamBeginCapture(main_stream, cudaStreamCaptureModeThreadLocal));
         const int64_t l0 = stats.launches;
+        // ---- the point S1 projects: x (GAP family, gap.jl:45), y (FISTA, fista.jl:35), x + p (Dykstra, dykstra.jl:29) ----
+        const double *xin = x.p;
+        if (alg == FOS_ALG_FISTA) xin = fy.p;
+        if (alg == FOS_ALG_DYKSTRA) {
+            FOS_LAUNCH(this, k_add_scaled, vgrid(L.NP), VBLOCK, 0, L.NP, w1.p, x.p, 1.0, dp.p, d_ctrl.p, 0);
+            xin = w1.p;
+        }
         // ---- AffinePlusLinear.prox!, first part: right-hand side folded into the initial residual ----
-        FOS_LAUNCH(this, k_iter_begin, vgrid(L.NP), VBLOCK, 0, L, sol.p, x.p, Ap.p, d_ctrl.p, tol_table.p, TOL_TABLE_N,
-                   1000);
+        FOS_LAUNCH(this, k_iter_begin, vgrid(L.NP), VBLOCK, 0, L, sol.p, xin, Ap.p, d_ctrl.p, tol_table.p, TOL_TABLE_N,
+                   1000, alg == FOS_ALG_FISTA ? 1 : 0);
         MVView V = kkt_pass(Ap.p, nullptr, /*defer_exchange=*/p2p);
         if (p2p) {
             const int grid = (int)std::min<int64_t>((L.LP + VBLOCK - 1) / VBLOCK, 2 * (int64_t)num_sms);
-            FOS_LAUNCH(this, k2_resid_hsde_p2p, grid, VBLOCK, 0, L, V, A.p2p, Ap.p, d_c.p, d_b.p, x.p, r.p, p.p,
+            FOS_LAUNCH(this, k2_resid_hsde_p2p, grid, VBLOCK, 0, L, V, A.p2p, Ap.p, d_c.p, d_b.p, xin, r.p, p.p,
                        d_ctrl.p, rb);
         } else {
-            FOS_LAUNCH(this, k2_kkt_hsde<K2_RESID>, vgrid(L.LP), VBLOCK, 0, L, V, Ap.p, d_c.p, d_b.p, nullptr, x.p, r.p,
+            FOS_LAUNCH(this, k2_kkt_hsde<K2_RESID>, vgrid(L.LP), VBLOCK, 0, L, V, Ap.p, d_c.p, d_b.p, nullptr, xin, r.p,
                        p.p, d_ctrl.p, rb, 0);
         }
         // ---- conjugategradient!'s loop (conjugategradients.jl:37-52) as a WHILE node; always >= 1 trip ----
@@ -959,7 +968,7 @@ void Handle::build_iter_graph(bool with_check)
         const int64_t body_launches = stats.launches - lb;
         FOS_CUDA(cudaStreamEndCapture(stream2, nullptr));
         FOS_CUDA(cudaStreamUpdateCaptureDependencies(main_stream, &wnode, 1, cudaStreamSetCaptureDependencies));
-        // ---- S1 relaxation + S2 = DualConeProduct + S2 relaxation + averaging, one kernel (two with SOC cones) ----
+        // ---- S1 relaxation + S2 = DualConeProduct + the algorithm's epilogue: one kernel (two with SOC cones) ----
         EpiArgs E{};
         E.tmp2 = tmp2.p;
         E.x = x.p;
@@ -970,21 +979,42 @@ void Handle::build_iter_graph(bool with_check)
         E.om_a = 1.0 - alpha;
         RelaxArgs R{};
         R.X = sol.p;
-        R.Y = x.p;
-        R.a = alpha1;
-        R.b = 1.0 - alpha1;
-        R.use_a12 = ada ? 1 : 0;
         R.tmp1 = tmp1.p;
         ConeSet &K = cones;
-        if (K.nsoc > 0)
-            FOS_LAUNCH(this, k4_soc_norms<true>, K.nchunks, VBLOCK, 0, nullptr, K.soc.p, K.nsoc, K.chunk_cone.p,
-                       K.chunk_sum.p, K.soc_scale.p, K.counter.p, R, d_ctrl.p);
-        if (ada)
-            FOS_LAUNCH(this, (k4_cone_apply<EPI_GAPA, true>), vgrid(K.NP), VBLOCK, 0, K.NP, nullptr, proj.p, K.ops.p,
-                       K.cone_of.p, K.soc_scale.p, K.soc.p, K.box.p, E, d_ctrl.p, rb, R);
-        else
-            FOS_LAUNCH(this, (k4_cone_apply<EPI_GAP, true>), vgrid(K.NP), VBLOCK, 0, K.NP, nullptr, proj.p, K.ops.p,
-                       K.cone_of.p, K.soc_scale.p, K.soc.p, K.box.p, E, d_ctrl.p, rb, R);
+        const int gK = vgrid(K.NP);
+        if (alg == FOS_ALG_DYKSTRA) {
+            // p = (x + p) - y ; y + q -> P2 ; x = P2(y + q) ; q = (y + q) - x   (dykstra.jl:31-35), y = sol
+            FOS_LAUNCH(this, k_dykstra_mid, gK, VBLOCK, 0, L.NP, w1.p, sol.p, dp.p, dq.p, w2.p);
+            E.aux1 = dq.p;
+            if (K.nsoc > 0)
+                FOS_LAUNCH(this, k4_soc_norms<false>, K.nchunks, VBLOCK, 0, w2.p, K.soc.p, K.nsoc, K.chunk_cone.p,
+                           K.chunk_sum.p, K.soc_scale.p, K.counter.p, R, d_ctrl.p);
+            FOS_LAUNCH(this, (k4_cone_apply<EPI_DYKSTRA, false>), gK, VBLOCK, 0, K.NP, w2.p, proj.p, K.ops.p, K.cone_of.p,
+                       K.soc_scale.p, K.soc.p, K.box.p, E, d_ctrl.p, rb, R);
+        } else {
+            const bool fis = alg == FOS_ALG_FISTA;
+            R.Y = fis ? fy.p : x.p;                 // fista.jl:37 relaxes against y with alpha; gap.jl:48 against x with alpha1
+            R.a = fis ? alpha : alpha1;
+            R.b = 1.0 - R.a;
+            R.use_a12 = ada ? 1 : 0;
+            if (fis) {
+                E.aux1 = fxold.p;
+                E.aux2 = fy.p;
+                E.coef_from_ctrl = 1;
+            }
+            if (K.nsoc > 0)
+                FOS_LAUNCH(this, k4_soc_norms<true>, K.nchunks, VBLOCK, 0, nullptr, K.soc.p, K.nsoc, K.chunk_cone.p,
+                           K.chunk_sum.p, K.soc_scale.p, K.counter.p, R, d_ctrl.p);
+            if (fis)
+                FOS_LAUNCH(this, (k4_cone_apply<EPI_FISTA, true>), gK, VBLOCK, 0, K.NP, nullptr, proj.p, K.ops.p,
+                           K.cone_of.p, K.soc_scale.p, K.soc.p, K.box.p, E, d_ctrl.p, rb, R);
+            else if (ada)
+                FOS_LAUNCH(this, (k4_cone_apply<EPI_GAPA, true>), gK, VBLOCK, 0, K.NP, nullptr, proj.p, K.ops.p,
+                           K.cone_of.p, K.soc_scale.p, K.soc.p, K.box.p, E, d_ctrl.p, rb, R);
+            else
+                FOS_LAUNCH(this, (k4_cone_apply<EPI_GAP, true>), gK, VBLOCK, 0, K.NP, nullptr, proj.p, K.ops.p,
+                           K.cone_of.p, K.soc_scale.p, K.soc.p, K.box.p, E, d_ctrl.p, rb, R);
+        }
         // ---- checkstatus on the unrelaxed projection (gap.jl:56; HSDEStatus.jl:27-71) ----
         if (with_check) {
             const double *X1[1] = {proj.p};
@@ -1034,12 +1064,19 @@ int64_t Handle::run_graph(int64_t i_start, int64_t n_iters)
                           since_checks * graphs[1].fixed_launches + 2 * delta;
         cgiter = h_ctrl->iter;
         if (h_ctrl->warn_maxit) warn_maxit = true;
+        if (alg == FOS_ALG_FISTA) fista_t = h_ctrl->fista_t;  // the device advanced t (k_iter_begin)
         since_iters = 0;
         since_checks = 0;
     };
     for (int64_t i = i_start; i < i_start + n_iters; i++) {
-        if (firstrun) {  // affinepluslinear.jl:101-104
-            FOS_CUDA(cudaMemcpyAsync(sol.p, x.p, (size_t)L.NP * 8, cudaMemcpyDeviceToDevice, stream));
+        if (alg == FOS_ALG_FISTA && i == 1)  // fista.jl:31-33
+            FOS_CUDA(cudaMemcpyAsync(fy.p, x.p, (size_t)L.NP * 8, cudaMemcpyDeviceToDevice, stream));
+        if (firstrun) {  // affinepluslinear.jl:101-104: the first point S1 ever projects is its own warm start
+            const double *first = alg == FOS_ALG_FISTA ? fy.p : x.p;  // Dykstra: x + p with p = 0 (bitwise x) on a first run
+            if (alg == FOS_ALG_DYKSTRA)
+                FOS_LAUNCH(this, k_add_scaled, vgrid(L.NP), VBLOCK, 0, L.NP, sol.p, x.p, 1.0, dp.p, d_ctrl.p, 0);
+            else
+                FOS_CUDA(cudaMemcpyAsync(sol.p, first, (size_t)L.NP * 8, cudaMemcpyDeviceToDevice, stream));
             firstrun = false;
         }
         const bool chk = (i % cur_checki) == 0;
