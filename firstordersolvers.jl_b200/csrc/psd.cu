@@ -168,13 +168,25 @@ k5_psd_jacobi(const PsdCone *__restrict__ cones, const double *__restrict__ in, 
 
 // ---------------------------------------------------------------------------------------
 // Tiny cones (d <= PSD_WARP_MAX_D = 32; the 2x2 / 3x3 blocks of LMI models, hundreds of them): ONE WARP per cone,
-// PSD_WPB cones per CTA.  Same two-sided Jacobi, same rotation formulas, same round-robin order as the kernel above
-// (element for element: results are bitwise equal), but S and V of a cone sit in the warp's slice of shared memory
-// and the three phases of a step are separated by __syncwarp only -- no CTA barrier, no idle 480 threads.
+// PSD_WPB cones per CTA.  Same two-sided Jacobi and round-robin order as the kernel above, but S and V of a cone sit
+// in the warp's slice of shared memory, the three phases of a step are separated by __syncwarp only (no CTA barrier,
+// no idle 480 threads), a lane owns a whole row (column) in the update phases, the pair schedule is tabulated once
+// (no integer division in the sweeps) and the rotation needs one sqrt, one divide and one rsqrt.
 // 1024 cones of order 16: 0.68 ms with one 512-thread CTA per cone (round 1) against 0.46 ms for cuSOLVER's batched
-// syevj; see profiles/r2_psd_probe.md for this kernel.
+// syevj; this kernel: profiles/r2_psd_probe.jsonl.
 // ---------------------------------------------------------------------------------------
 constexpr int PSD_WPB = 8;
+
+// shared memory of one warp: S and V with an ODD leading dimension (row stride d or d+1: the column phase reads
+// S[lane][p] -- an even stride would put all lanes on one bank), the (c, s) pairs of a step and the round-robin
+// schedule (p, q) of every (step, pair), built once so that the sweeps contain no integer division
+__host__ __device__ inline int psd_warp_ld(int d) { return d | 1; }
+__host__ __device__ inline size_t psd_warp_doubles(int dmax)
+{
+    const int D = (dmax + 1) & ~1, ld = psd_warp_ld(dmax);
+    const size_t tab_bytes = (size_t)(D - 1) * (D / 2) * 2;
+    return (size_t)2 * dmax * ld + (size_t)D + (tab_bytes + 7) / 8;
+}
 
 __global__ void __launch_bounds__(PSD_WPB * 32)
 k5_psd_jacobi_warp(const PsdCone *__restrict__ cones, int ncones, const double *__restrict__ in,
@@ -187,83 +199,98 @@ k5_psd_jacobi_warp(const PsdCone *__restrict__ cones, int ncones, const double *
     const PsdCone C = cones[ci];
     const int d = C.d;
     const int D = (d + 1) & ~1;
-    const int Dmax = (dmax + 1) & ~1;
-    double *S = psd_smem + (size_t)warp * (2 * dmax * dmax + Dmax);
-    double *V = S + (size_t)dmax * dmax;
-    double *cs = V + (size_t)dmax * dmax;
+    const int ld = psd_warp_ld(d);
+    double *S = psd_smem + (size_t)warp * psd_warp_doubles(dmax);
+    double *V = S + (size_t)dmax * psd_warp_ld(dmax);
+    double *cs = V + (size_t)dmax * psd_warp_ld(dmax);
+    unsigned char *tab = reinterpret_cast<unsigned char *>(cs + ((dmax + 1) & ~1));
     const double sq2 = 1.4142135623730951;
     const double sgn = C.dual ? -1.0 : 1.0;
+    const int npairs = D / 2;
+    for (int idx = lane; idx < (D - 1) * npairs; idx += 32) {
+        int p, q;
+        rr_pair(idx / npairs, idx % npairs, D, p, q);
+        tab[2 * idx] = (unsigned char)p;
+        tab[2 * idx + 1] = (unsigned char)q;
+    }
     double acc = 0.0;
     for (int idx = lane; idx < d * d; idx += 32) {
-        const int i = idx / d, j = idx % d;
+        const int i = idx / d, j = idx - i * d;
         const int lo = i > j ? i : j, hi = i > j ? j : i;
         const int64_t k = (int64_t)hi * d - (int64_t)hi * (hi - 1) / 2 + (lo - hi);
         double v = sgn * in[C.off + k];
         if (i == j) v *= sq2;
-        S[idx] = v;
-        V[idx] = (i == j) ? 1.0 : 0.0;
+        S[i * ld + j] = v;
+        V[i * ld + j] = (i == j) ? 1.0 : 0.0;
         acc = fma(v, v, acc);
     }
     const double thr = 1e-17 * sqrt(warp_sum(acc));
     __syncwarp();
-    const int npairs = D / 2;
     for (int sweep = 0; sweep < PSD_MAX_SWEEPS; sweep++) {
         bool rotated = false;
         for (int step = 0; step < D - 1; step++) {
+            const unsigned char *tp = tab + 2 * step * npairs;
+            // phase 1: one lane per pair.  t = tan of the rotation angle from the stable two-term form
+            // t = 2 a_pq / (delta + sign(delta) sqrt(delta^2 + 4 a_pq^2)): one sqrt, one divide, one rsqrt
             bool mine = false;
-            for (int k = lane; k < npairs; k += 32) {
-                int p, q;
-                rr_pair(step, k, D, p, q);
-                double c = 1.0, s = 0.0;
+            if (lane < npairs) {
+                const int p = tp[2 * lane], q = tp[2 * lane + 1];
+                double c = 1.0, sn = 0.0;
                 if (q < d) {
-                    const double apq = S[p * d + q];
-                    const double app = S[p * d + p], aqq = S[q * d + q];
+                    const double apq = S[p * ld + q];
                     if (fabs(apq) > thr) {
-                        const double theta = (aqq - app) / (2.0 * apq);
-                        const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-                        c = 1.0 / sqrt(t * t + 1.0);
-                        s = t * c;
+                        const double delta = S[q * ld + q] - S[p * ld + p];
+                        const double rt = sqrt(fma(delta, delta, 4.0 * apq * apq));
+                        const double t = (2.0 * apq) / (delta >= 0.0 ? delta + rt : delta - rt);
+                        c = rsqrt(fma(t, t, 1.0));
+                        sn = t * c;
                         mine = true;
                     }
                 }
-                cs[2 * k] = c;
-                cs[2 * k + 1] = s;
+                cs[2 * lane] = c;
+                cs[2 * lane + 1] = sn;
             }
             rotated = rotated || __any_sync(0xffffffffu, mine);
             __syncwarp();
-            for (int idx = lane; idx < npairs * d; idx += 32) {  // columns: S <- S J, V <- V J
-                const int k = idx / d, row = idx - k * d;
-                const double c = cs[2 * k], s = cs[2 * k + 1];
-                if (s == 0.0) continue;
-                int p, q;
-                rr_pair(step, k, D, p, q);
-                const int ip = row * d + p, iq = row * d + q;
-                const double sp = S[ip], sq = S[iq];
-                S[ip] = c * sp - s * sq;
-                S[iq] = s * sp + c * sq;
-                const double vp = V[ip], vq = V[iq];
-                V[ip] = c * vp - s * vq;
-                V[iq] = s * vp + c * vq;
+            // phase 2: lane = row.  S <- S J, V <- V J  (the pairs of a step are disjoint: independent updates)
+            if (lane < d) {
+                double *Sr = S + lane * ld, *Vr = V + lane * ld;
+#pragma unroll 4
+                for (int k = 0; k < npairs; k++) {
+                    const double c = cs[2 * k], sn = cs[2 * k + 1];
+                    if (sn == 0.0) continue;
+                    const int p = tp[2 * k], q = tp[2 * k + 1];
+                    const double sp = Sr[p], sq = Sr[q];
+                    Sr[p] = c * sp - sn * sq;
+                    Sr[q] = sn * sp + c * sq;
+                    const double vp = Vr[p], vq = Vr[q];
+                    Vr[p] = c * vp - sn * vq;
+                    Vr[q] = sn * vp + c * vq;
+                }
             }
             __syncwarp();
-            for (int idx = lane; idx < npairs * d; idx += 32) {  // rows: S <- J' S
-                const int k = idx / d, col = idx - k * d;
-                const double c = cs[2 * k], s = cs[2 * k + 1];
-                if (s == 0.0) continue;
-                int p, q;
-                rr_pair(step, k, D, p, q);
-                const int ip = p * d + col, iq = q * d + col;
-                const double sp = S[ip], sq = S[iq];
-                S[ip] = (col == q) ? 0.0 : c * sp - s * sq;
-                S[iq] = (col == p) ? 0.0 : s * sp + c * sq;
+            // phase 3: lane = column.  S <- J' S, the annihilated entries set to exactly 0
+            if (lane < d) {
+#pragma unroll 4
+                for (int k = 0; k < npairs; k++) {
+                    const double c = cs[2 * k], sn = cs[2 * k + 1];
+                    if (sn == 0.0) continue;
+                    const int p = tp[2 * k], q = tp[2 * k + 1];
+                    const double sp = S[p * ld + lane], sq = S[q * ld + lane];
+                    S[p * ld + lane] = (lane == q) ? 0.0 : c * sp - sn * sq;
+                    S[q * ld + lane] = (lane == p) ? 0.0 : sn * sp + c * sq;
+                }
             }
             __syncwarp();
         }
         if (!rotated) break;
     }
-    for (int idx = lane; idx < d * d; idx += 32) {
-        const double lam = S[(idx % d) * d + (idx % d)];
-        V[idx] = lam > 0.0 ? V[idx] * sqrt(lam) : 0.0;
+    // W = V sqrt(max(lambda, 0)) column-wise, then P = W W'
+    if (lane < d) {
+        for (int e = 0; e < d; e++) {
+            const double lam = S[e * ld + e];
+            V[lane * ld + e] = lam > 0.0 ? V[lane * ld + e] * sqrt(lam) : 0.0;
+        }
     }
     __syncwarp();
     const int plen = d * (d + 1) / 2;
@@ -273,7 +300,7 @@ k5_psd_jacobi_warp(const PsdCone *__restrict__ cones, int ncones, const double *
         while ((j + 1) * d - (j + 1) * j / 2 <= k) j++;
         const int i = j + (k - (j * d - j * (j - 1) / 2));
         double a2 = 0.0;
-        const double *wi = V + i * d, *wj = V + j * d;
+        const double *wi = V + i * ld, *wj = V + j * ld;
         for (int e = 0; e < d; e++) a2 = fma(wi[e], wj[e], a2);
         if (i == j) a2 /= sq2;
         const double x = in[C.off + k];
@@ -288,8 +315,7 @@ void psd_project(Handle *h, ConeSet &K, const double *in, double *projbuf)
     const int ns = K.psd_nsmall;
     if (ns > 0) {
         const int dm = K.psd_small_max_d;
-        const size_t per_warp = ((size_t)2 * dm * dm + (size_t)((dm + 1) & ~1)) * sizeof(double);
-        const size_t need_w = per_warp * PSD_WPB;
+        const size_t need_w = psd_warp_doubles(dm) * sizeof(double) * PSD_WPB;
         FOS_CUDA(cudaFuncSetAttribute(k5_psd_jacobi_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_w));
         FOS_LAUNCH(h, k5_psd_jacobi_warp, (ns + PSD_WPB - 1) / PSD_WPB, PSD_WPB * 32, need_w, K.d_psd.p, ns, in, projbuf, dm);
     }
