@@ -226,6 +226,11 @@ k5_psd_jacobi_warp(const PsdCone *__restrict__ cones, int ncones, const double *
     }
     const double thr = 1e-17 * sqrt(warp_sum(acc));
     __syncwarp();
+    // update phases: lane -> (row, pair group).  With d <= 16 a row is shared by 32 / P lanes (P = d rounded up to a
+    // power of two), each taking every G-th pair of the step: the pairs are disjoint, so the groups touch different columns
+    int P = 1;
+    while (P < d) P <<= 1;
+    const int G = 32 / P, row = lane & (P - 1), grp = lane / P;
     for (int sweep = 0; sweep < PSD_MAX_SWEEPS; sweep++) {
         bool rotated = false;
         for (int step = 0; step < D - 1; step++) {
@@ -252,11 +257,11 @@ k5_psd_jacobi_warp(const PsdCone *__restrict__ cones, int ncones, const double *
             }
             rotated = rotated || __any_sync(0xffffffffu, mine);
             __syncwarp();
-            // phase 2: lane = row.  S <- S J, V <- V J  (the pairs of a step are disjoint: independent updates)
-            if (lane < d) {
-                double *Sr = S + lane * ld, *Vr = V + lane * ld;
+            // phase 2: (row, group) lanes.  S <- S J, V <- V J  (the pairs of a step are disjoint: independent updates)
+            if (row < d) {
+                double *Sr = S + row * ld, *Vr = V + row * ld;
 #pragma unroll 4
-                for (int k = 0; k < npairs; k++) {
+                for (int k = grp; k < npairs; k += G) {
                     const double c = cs[2 * k], sn = cs[2 * k + 1];
                     if (sn == 0.0) continue;
                     const int p = tp[2 * k], q = tp[2 * k + 1];
@@ -269,16 +274,16 @@ k5_psd_jacobi_warp(const PsdCone *__restrict__ cones, int ncones, const double *
                 }
             }
             __syncwarp();
-            // phase 3: lane = column.  S <- J' S, the annihilated entries set to exactly 0
-            if (lane < d) {
+            // phase 3: (column, group) lanes.  S <- J' S, the annihilated entries set to exactly 0
+            if (row < d) {
 #pragma unroll 4
-                for (int k = 0; k < npairs; k++) {
+                for (int k = grp; k < npairs; k += G) {
                     const double c = cs[2 * k], sn = cs[2 * k + 1];
                     if (sn == 0.0) continue;
                     const int p = tp[2 * k], q = tp[2 * k + 1];
-                    const double sp = S[p * ld + lane], sq = S[q * ld + lane];
-                    S[p * ld + lane] = (lane == q) ? 0.0 : c * sp - sn * sq;
-                    S[q * ld + lane] = (lane == p) ? 0.0 : sn * sp + c * sq;
+                    const double sp = S[p * ld + row], sq = S[q * ld + row];
+                    S[p * ld + row] = (row == q) ? 0.0 : c * sp - sn * sq;
+                    S[q * ld + row] = (row == p) ? 0.0 : sn * sp + c * sq;
                 }
             }
             __syncwarp();

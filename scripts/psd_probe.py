@@ -46,7 +46,7 @@ def lib_bar(Ms, reps):
 def main():
     H = fos.Handle(0)
     rng = np.random.default_rng(0)
-    cases = [(512, 2), (512, 1), (256, 2), (128, 8), (1024, 1), (64, 64), (16, 1024)]
+    cases = [(512, 2), (512, 1), (256, 2), (128, 8), (1024, 1), (64, 64), (32, 256), (16, 1024), (8, 2048), (3, 4096)]
     for d, nc in cases:
         Ms = np.zeros((nc, d, d))
         X = np.zeros((nc, d * (d + 1) // 2))
