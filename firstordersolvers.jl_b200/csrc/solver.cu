@@ -6,6 +6,8 @@
 
 namespace fos {
 
+int g_psd_warp_max_d = 16;
+
 // =======================================================================================
 // handle lifecycle
 // =======================================================================================
@@ -223,12 +225,12 @@ void ConeSet::build(int64_t NP_, const std::vector<ConeSeg> &segs)
     counter.alloc(1);
     if (!psd.empty()) {
         // tiny cones first: they take the one-warp-per-cone kernel (psd.cu), the others one CTA per cone
-        std::stable_partition(psd.begin(), psd.end(), [](const PsdCone &c) { return c.d <= PSD_WARP_MAX_D; });
+        std::stable_partition(psd.begin(), psd.end(), [](const PsdCone &c) { return c.d <= g_psd_warp_max_d; });
         psd_nsmall = 0;
         psd_small_max_d = 0;
         psd_max_d = 0;
         for (const PsdCone &c : psd) {
-            if (c.d <= PSD_WARP_MAX_D) {
+            if (c.d <= g_psd_warp_max_d) {
                 psd_nsmall++;
                 psd_small_max_d = std::max<int>(psd_small_max_d, c.d);
             } else {
@@ -834,8 +836,10 @@ int64_t Handle::run(int64_t i_start, int64_t n_iters, int64_t checki, double eps
     h_ctrl->fista_t = fista_t;
     FOS_CUDA(cudaMemcpyAsync(d_ctrl.p, h_ctrl, sizeof(Ctrl), cudaMemcpyHostToDevice, stream));
     int64_t done = 0;
+    bool synced = false;
     if (!trace && graph_ok()) {
         done = run_graph(i_start, n_iters);
+        synced = true;  // run_graph ends with a synchronisation that fetched the control block
     } else {
         for (int64_t i = i_start; i < i_start + n_iters; i++) {
             cur_i = i;  // solverwrapper.jl:24
@@ -845,7 +849,7 @@ int64_t Handle::run(int64_t i_start, int64_t n_iters, int64_t checki, double eps
             if (status != FOS_STATUS_CONTINUE) break;  // :26-28
         }
     }
-    sync_ctrl();
+    if (!synced) sync_ctrl();
     const int64_t nrec = h_ctrl->nrec;
     if (n_rec) *n_rec = nrec;
     const int64_t ncopy = std::min<int64_t>(std::min<int64_t>(nrec, rec_cap_host), rec_cap);

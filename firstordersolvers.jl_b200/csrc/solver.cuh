@@ -377,7 +377,8 @@ struct Handle {
     } while (0)
 
 constexpr int PSD_SMEM_MAX_D = 112;  // largest cone whose S and V fit one SM's shared memory
-constexpr int PSD_WARP_MAX_D = 32;   // up to here a cone is projected by ONE WARP (eight cones per CTA, no block barriers)
+constexpr int PSD_WARP_MAX_D = 32;   // the one-warp-per-cone kernel supports cones up to this order ...
+extern int g_psd_warp_max_d;         // ... and takes those up to this one (default 16; option "psd_warp_max_d", process-wide)
 void psd_project(Handle *h, ConeSet &K, const double *in, double *projbuf);        // K5, psd.cu
 void psd_project_large(Handle *h, ConeSet &K, const double *in, double *projbuf);  // K5, psd_large.cu
 int psd_large_last_sweeps(Handle *h, ConeSet &K);
