@@ -124,7 +124,7 @@ int32_t fos_set_option(fos_handle_t hh, const char *key, double value)
         h.batch_ctas = (int)value;
         if (h.batch) h.batch->grid_ctas = (int)value;
     } else if (k == "psd_warp_max_d") {
-        FOS_REQUIRE(value >= 0 && value <= PSD_WARP_MAX_D, "psd_warp_max_d must be 0 .. 32");
+        FOS_REQUIRE(value >= 0 && value <= PSD_WARP_MAX_D, "psd_warp_max_d must be 0 .. 16");
         g_psd_warp_max_d = (int)value;  // applies to problems loaded afterwards
     } else if (k == "tail_trace") {
         if (value != 0) {

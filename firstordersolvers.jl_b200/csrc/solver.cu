@@ -6,7 +6,7 @@
 
 namespace fos {
 
-int g_psd_warp_max_d = 16;
+int g_psd_warp_max_d = 16;  // at most 16: the 128-thread kernel takes over from there (psd.cu)
 
 // =======================================================================================
 // handle lifecycle
@@ -224,19 +224,22 @@ void ConeSet::build(int64_t NP_, const std::vector<ConeSeg> &segs)
     }
     counter.alloc(1);
     if (!psd.empty()) {
-        // tiny cones first: they take the one-warp-per-cone kernel (psd.cu), the others one CTA per cone
-        std::stable_partition(psd.begin(), psd.end(), [](const PsdCone &c) { return c.d <= g_psd_warp_max_d; });
-        psd_nsmall = 0;
-        psd_small_max_d = 0;
-        psd_max_d = 0;
+        // sorted by order: the projection kernel gives a cone 32, 128 or 512 threads depending on d (psd.cu)
+        std::stable_sort(psd.begin(), psd.end(), [](const PsdCone &a, const PsdCone &b) { return a.d < b.d; });
+        psd_n16 = psd_n48 = 0;
+        psd_dmax16 = psd_dmax48 = psd_max_d = 0;
         for (const PsdCone &c : psd) {
             if (c.d <= g_psd_warp_max_d) {
-                psd_nsmall++;
-                psd_small_max_d = std::max<int>(psd_small_max_d, c.d);
+                psd_n16++;
+                psd_dmax16 = std::max<int>(psd_dmax16, c.d);
+            } else if (c.d <= 48) {
+                psd_dmax48 = std::max<int>(psd_dmax48, c.d);
             } else {
                 psd_max_d = std::max<int>(psd_max_d, c.d);
             }
+            if (c.d <= 48) psd_n48++;
         }
+        if (psd_n48 < psd_n16) psd_n48 = psd_n16;
         d_psd.upload(psd);
     }
     if (!psd_large.empty()) d_psd_large.upload(psd_large);

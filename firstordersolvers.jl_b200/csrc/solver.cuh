@@ -203,8 +203,8 @@ struct ConeSet {
     DevBuf<uint8_t> psd_ctl;
     DevBuf<double> psd_vstore;   // eigenvector bases of the previous projection (warm start of K5L)
     bool psd_warm = false, psd_warm_enabled = true;
-    int psd_max_d = 0;                      // largest cone of the one-CTA-per-cone kernel
-    int psd_nsmall = 0, psd_small_max_d = 0;  // psd[0 .. psd_nsmall): d <= PSD_WARP_MAX_D, one warp per cone
+    // psd is sorted by order: [0, psd_n16) one warp per cone, [psd_n16, psd_n48) 128 threads, the rest 512 (psd.cu)
+    int psd_max_d = 0, psd_n16 = 0, psd_n48 = 0, psd_dmax16 = 0, psd_dmax48 = 0;
     bool fusable = true;  // every cone projects entry by entry from (x_e, per-cone scalars): RelaxArgs may feed it
     void build(int64_t NP_, const std::vector<ConeSeg> &segs);
 };
@@ -377,8 +377,8 @@ struct Handle {
     } while (0)
 
 constexpr int PSD_SMEM_MAX_D = 112;  // largest cone whose S and V fit one SM's shared memory
-constexpr int PSD_WARP_MAX_D = 32;   // the one-warp-per-cone kernel supports cones up to this order ...
-extern int g_psd_warp_max_d;         // ... and takes those up to this one (default 16; option "psd_warp_max_d", process-wide)
+constexpr int PSD_WARP_MAX_D = 16;   // up to this order a cone is projected by ONE WARP (eight cones per CTA) ...
+extern int g_psd_warp_max_d;         // ... unless the option "psd_warp_max_d" lowers it (process-wide; 0 = never)
 void psd_project(Handle *h, ConeSet &K, const double *in, double *projbuf);        // K5, psd.cu
 void psd_project_large(Handle *h, ConeSet &K, const double *in, double *projbuf);  // K5, psd_large.cu
 int psd_large_last_sweeps(Handle *h, ConeSet &K);

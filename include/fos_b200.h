@@ -115,9 +115,9 @@ const char *fos_last_error(fos_handle_t h);
  *   "batch_hybrid" 1 (default) = batch mode keeps rows with <= n/8 non-zeros out of the dense tiles (CSR + CSC) and
  *                  skips empty rows; 0 = every row is streamed as dense FP64.  Set before loading the batch.
  *   "batch_ctas"   persistent CTAs of the batch kernel (default = #SMs)
- *   "psd_warp_max_d" PSD cones up to this order (default 16, at most 32) are projected by one warp each, eight cones per
- *                  CTA; larger ones by one CTA each (up to 112) or by the cooperative kernel.  Process-wide; applies to
- *                  problems loaded afterwards.
+ *   "psd_warp_max_d" PSD cones up to this order (default and at most 16) are projected by one warp each, eight cones per
+ *                  CTA; up to 48 by 128 threads, up to 112 by one 512-thread CTA, larger ones by the cooperative kernel.
+ *                  Process-wide; applies to problems loaded afterwards.
  *   "tail_trace"   1 = the fused CG tail records the SM cycles of each of its phases (fos_get_tail_trace)
  *   "use_graphs"   reserved                                                                */
 int32_t fos_set_option(fos_handle_t h, const char *key, double value);

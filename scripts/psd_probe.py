@@ -47,9 +47,7 @@ def main():
     H = fos.Handle(0)
     rng = np.random.default_rng(0)
     cases = [(512, 2), (512, 1), (256, 2), (128, 8), (1024, 1), (64, 64), (32, 256), (24, 512), (16, 1024), (8, 2048), (3, 4096)]
-    if "--warp32" in sys.argv:   # which kernel should take 17 <= d <= 32?
-        H.set_option("psd_warp_max_d", 32)
-        cases = [(32, 256), (24, 512), (20, 512)]
+    cases += [(48, 128), (96, 32)]
     for d, nc in cases:
         Ms = np.zeros((nc, d, d))
         X = np.zeros((nc, d * (d + 1) // 2))

@@ -325,7 +325,7 @@ def test_psd_literal_known_answer(fos):
     np.testing.assert_allclose(Pd, P_PSD_YS, rtol=1e-10, atol=1e-14)
 
 
-@pytest.mark.parametrize("d", [1, 2, 3, 5, 16, 33, 64, 100, 112, 113, 130, 200, 256, 300, 512])
+@pytest.mark.parametrize("d", [1, 2, 3, 5, 8, 15, 16, 17, 24, 33, 47, 48, 49, 64, 100, 112, 113, 130, 200, 256, 300, 512])
 @pytest.mark.parametrize("dual", [False, True])
 def test_psd_projection_vs_lapack(fos, d, dual):
     from oracle import np_oracle as npo
@@ -343,6 +343,31 @@ def test_psd_projection_vs_lapack(fos, d, dual):
         S = (G * lam) @ G.T
         got = problems.smat(H.prox_cone("SDP", problems.svec(S)))
         np.testing.assert_allclose(got, (G * np.maximum(lam, 0)) @ G.T, atol=1e-12)
+
+
+def test_psd_mixed_orders_in_one_cone_set(fos):
+    """One model whose constraint cones are SDP blocks of orders 3, 20, 7, 60, 16, 48, 112, 2 (in this order): the
+    projection sorts them by order and hands them to the 32-, 128- and 512-thread kernels; every block must come back
+    in its own place, primal and dual image alike (DualConeProduct, cones.jl:122-142)."""
+    import scipy.sparse as sp
+    from oracle import np_oracle as npo
+    from helpers import load_conic
+    from fos_b200.problems import ConicProblem
+    ds = [3, 20, 7, 60, 16, 48, 112, 2]
+    lens = [d * (d + 1) // 2 for d in ds]
+    n = sum(lens)
+    P = ConicProblem(np.zeros(n), -sp.identity(n, format="csc"), np.zeros(n), [("SDP", ln) for ln in lens], [("Free", n)])
+    H = load_conic(fos, P, storage="sparse")
+    rng = np.random.default_rng(5)
+    z = rng.standard_normal(2 * (2 * n + 1))
+    y = H.cone_prox(z)
+    l = 2 * n + 1
+    off = 0
+    for ln in lens:
+        a, b = n + off, l + n + off                       # y block (dual cone K1*), s block (K1)
+        assert rel_err(y[a:a + ln], npo.prox_cone_dual("SDP", z[a:a + ln])) < 1e-12
+        assert rel_err(y[b:b + ln], npo.prox_cone("SDP", z[b:b + ln])) < 1e-12
+        off += ln
 
 
 @pytest.mark.parametrize("d,nc", [(512, 2), (129, 5), (640, 1), (1024, 1)])
