@@ -247,6 +247,7 @@ def main():
     ap.add_argument("--tte-max-iters", type=int, default=2000, help="iteration cap of the time-to-eps solve")
     ap.add_argument("--tail-blocks", type=int, default=0, help="blocks of the fused CG-tail kernel (0 = one per SM)")
     ap.add_argument("--no-graphs", action="store_true", help="kernel-per-launch path with host synchronisation per CG batch")
+    ap.add_argument("--k1-balance", type=int, default=-1, help="0 = even split of the tiles over the SMs, 1 = sized to the SMs' measured speed (default)")
     ap.add_argument("--tail-trace", action="store_true", help="phase timing of the fused CG tail (extra key tail_trace_us)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: fused peer-memory exchange kernel (default) or fold + ncclAllReduce")
@@ -318,6 +319,8 @@ def main():
             Hx.set_option("tail_blocks", args.tail_blocks)
         if args.no_graphs:
             Hx.set_option("use_graphs", 0)
+        if args.k1_balance >= 0:
+            Hx.set_option("k1_balance", args.k1_balance)
 
     H = fos.Handle(local_rank)
     apply_options(H)
@@ -562,6 +565,8 @@ def main():
                 "share_of_step": ((mv2_ms + mv1_ms) / prof_ms_total) if prof_ms_total > 0 else None,
                 "measured_in": "event-bracketed replay of the timed iterations (kernel-per-launch path): "
                                f"{prof_ms_total / K:.3f} ms per step there",
+                "sm_balanced": bool(H.info("k1_balanced")),
+                "sm_time_spread_before_after": [H.info("k1_spread_before"), H.info("k1_spread_after")],
                 "whole_iteration_gbs": bytes_pass * passes / (ms_total / 1e3) / 1e9,
                 "whole_iteration_frac": bytes_pass * passes / (ms_total / 1e3) / 1e9 / peak}
     parity = None

@@ -123,6 +123,10 @@ int32_t fos_set_option(fos_handle_t hh, const char *key, double value)
     } else if (k == "batch_ctas") {
         h.batch_ctas = (int)value;
         if (h.batch) h.batch->grid_ctas = (int)value;
+    } else if (k == "k1_balance") {
+        FOS_REQUIRE(!h.loaded, "k1_balance must be set before loading the problem");
+        FOS_REQUIRE(value == 0 || value == 1 || value == 2, "k1_balance must be 0 (even split), 1 (auto) or 2 (always)");
+        h.A.k1_balance = (int)value;
     } else if (k == "psd_warp_max_d") {
         FOS_REQUIRE(value >= 0 && value <= PSD_WARP_MAX_D, "psd_warp_max_d must be 0 .. 16");
         g_psd_warp_max_d = (int)value;  // applies to problems loaded afterwards
@@ -470,6 +474,9 @@ int32_t fos_get_info(fos_handle_t hh, int32_t which, double *out)
     case 18: *out = (double)h.A.kind; break;
     case 19: *out = h.A.kind == 3 ? (double)h.A.m_local : 0.0; break;
     case 20: *out = h.A.kind == 3 ? (double)h.A.hyb_sparse_rows : 0.0; break;
+    case 21: *out = h.A.by_smid ? 1.0 : 0.0; break;
+    case 22: *out = h.A.calib_spread[0]; break;
+    case 23: *out = h.A.calib_spread[1]; break;
     default: throw Error(FOS_ERR_INVALID, "unknown info selector");
     }
     FOS_API_END(hh)

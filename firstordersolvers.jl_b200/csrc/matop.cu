@@ -2,6 +2,9 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <map>
+#include <mutex>
+#include <tuple>
 
 #include "solver.cuh"
 
@@ -79,12 +82,11 @@ void MatOp::init_dense(int64_t m_, int64_t n_, const double *Asrc, int64_t lda_s
     }
     make_tmap(&tmap, A, std::max<int64_t>(m_local, 1), n, lda);
     int G = grid_ctas > 0 ? grid_ctas : num_sms;
+    by_smid = false;
+    sm_weight.clear();
     plan = k1_make_plan(std::max<int64_t>(m_local, 1), n, G);
-    d_unit_begin.upload(plan.cta_unit_begin);
-    d_slot_base.upload(plan.band_slot_base);
-    d_first_cta.upload(plan.band_first_cta);
+    upload_plan();
     rowpart.alloc((size_t)plan.NB * 2 * m_pad_local);
-    colpart.alloc((size_t)std::max(plan.nslots, 1) * 2 * K1_BW);
     // plain path / exchange buffers
     full_ax.alloc((size_t)2 * m_pad);
     full_atw.alloc((size_t)2 * n_pad);
@@ -96,6 +98,117 @@ void MatOp::init_dense(int64_t m_, int64_t n_, const double *Asrc, int64_t lda_s
     FOS_CUDA(cudaFuncSetAttribute(k1_dual_matvec_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)k1_smem_bytes(2)));
     if (nranks > 1) xbuf.alloc((size_t)2 * (n_pad + m_pad));
+    if (k1_balance && impl == 0 && grid_ctas <= 0) calibrate(st);
+}
+
+void MatOp::upload_plan()
+{
+    d_unit_begin.upload(plan.cta_unit_begin);
+    d_slot_base.upload(plan.band_slot_base);
+    d_first_cta.upload(plan.band_first_cta);
+    colpart.alloc((size_t)std::max(plan.nslots, 1) * 2 * K1_BW);
+    d_claim.alloc((size_t)plan.G + 8);
+    d_cta_cycles.alloc((size_t)plan.G);
+    d_cta_smid.alloc((size_t)plan.G);
+}
+
+// ---------------------------------------------------------------------------------------
+// SM-speed calibration.  A persistent CTA per SM and an even split of the tiles leave 7-8 % on the table: ncu shows
+// the SMs finishing between 0.85 and 0.99 of the kernel's duration (profiles/r2_k1_balance.md) -- the SMs do not
+// stream at the same rate (GPCs with fewer SMs give each of them a larger share of the GPC's path to L2).  The work
+// ranges are therefore bound to SMs (K1Args::by_smid) and sized to their measured speed: a few timed passes over the
+// real matrix at load, weights w_s ~ tiles_s / cycles_s, re-plan, repeat.  The weights are cached per (device, shard
+// shape) for the life of the process, so every handle of that shape gets the same plan -- the summation order, and with
+// it every bit of the results, is the same for all of them.
+// ---------------------------------------------------------------------------------------
+namespace {
+std::mutex g_calib_mutex;
+std::map<std::tuple<int, int64_t, int64_t, int>, std::vector<double>> g_calib_cache;
+}  // namespace
+
+void MatOp::calibrate(cudaStream_t st)
+{
+    const int G = plan.G;
+    const int64_t units = (int64_t)plan.NB * plan.RT;
+    if ((kind != 1 && kind != 3) || G != num_sms || units < (k1_balance >= 2 ? 1 : 4) * (int64_t)G) return;  // too little work per SM
+    int dev = 0;
+    FOS_CUDA(cudaGetDevice(&dev));
+    const auto key = std::make_tuple(dev, m_local, n, G);
+    {
+        std::lock_guard<std::mutex> lk(g_calib_mutex);
+        auto it = g_calib_cache.find(key);
+        if (it != g_calib_cache.end()) {
+            sm_weight = it->second;
+            if (!sm_weight.empty()) {
+                plan = k1_make_plan(m_local, n, G, sm_weight.data());
+                upload_plan();
+                by_smid = true;
+            }
+            return;
+        }
+    }
+    // zero vectors: the timing does not depend on the values
+    DevBuf<double> zx, zw;
+    zx.alloc((size_t)n_pad);
+    // run() expects W indexed by GLOBAL row: the hybrid layout (kind 3) reads all of it, a shard only its own rows
+    zw.alloc((size_t)(kind == 3 ? m_pad : m_pad_local) + K1_TR);
+    const double *wbase = kind == 3 ? zw.p : zw.p - row_begin;
+    const double *X[2] = {zx.p, zx.p}, *W[2] = {wbase, wbase};
+    std::vector<double> w((size_t)G, 1.0);
+    std::vector<unsigned long long> cyc((size_t)G);
+    std::vector<int32_t> smid((size_t)G);
+    bool ok = true;
+    const bool keep_profile = profile;
+    profile = false;
+    Stats *keep_stats = stats;
+    stats = nullptr;
+    for (int round = 0; round < 4 && ok; round++) {
+        by_smid = true;
+        double tsum[2] = {0.0, 0.0};
+        std::vector<double> t((size_t)G, 0.0);
+        for (int rep = 0; rep < 3; rep++) {  // first repetition warms up
+            run(2, X, W, nullptr, st);
+            FOS_CUDA(cudaStreamSynchronize(st));
+            FOS_CUDA(cudaMemcpy(cyc.data(), d_cta_cycles.p, (size_t)G * 8, cudaMemcpyDeviceToHost));
+            FOS_CUDA(cudaMemcpy(smid.data(), d_cta_smid.p, (size_t)G * 4, cudaMemcpyDeviceToHost));
+            for (int g = 0; g < G; g++)
+                if (smid[(size_t)g] != g) ok = false;  // SM ids are not 0..G-1 one to one: keep the even split
+            if (rep > 0)
+                for (int g = 0; g < G; g++) t[(size_t)g] += (double)cyc[(size_t)g];
+        }
+        if (!ok) break;
+        double tmean = 0.0, tmin = 1e300, tmax = 0.0;
+        for (int g = 0; g < G; g++) {
+            tmean += t[(size_t)g] / G;
+            tmin = std::min(tmin, t[(size_t)g]);
+            tmax = std::max(tmax, t[(size_t)g]);
+        }
+        (void)tsum;
+        const double spread = (tmax - tmin) / tmean;
+        if (round == 0) calib_spread[0] = spread;
+        calib_spread[1] = spread;
+        if (round == 3) break;
+        // work_g ~ w_g and time_g = work_g / speed_g: move w_g towards equal times, damped
+        double wmean = 0.0;
+        for (int g = 0; g < G; g++) {
+            w[(size_t)g] *= std::pow(tmean / t[(size_t)g], 0.7);
+            wmean += w[(size_t)g] / G;
+        }
+        for (int g = 0; g < G; g++) w[(size_t)g] = std::min(1.3, std::max(0.7, w[(size_t)g] / wmean));
+        plan = k1_make_plan(m_local, n, G, w.data());
+        upload_plan();
+    }
+    profile = keep_profile;
+    stats = keep_stats;
+    if (!ok) {
+        by_smid = false;
+        w.clear();
+        plan = k1_make_plan(m_local, n, G);
+        upload_plan();
+    }
+    sm_weight = w;
+    std::lock_guard<std::mutex> lk(g_calib_mutex);
+    g_calib_cache[key] = w;
 }
 
 void MatOp::init_sparse(int64_t m_, int64_t n_, const int64_t *colptr, const int64_t *rowval, const double *nzval,
@@ -320,14 +433,14 @@ void MatOp::init_hybrid(int64_t m_, int64_t n_, const double *Asrc, int64_t lda_
     A = A + (size_t)r0 * lda;  // A_own (if any) keeps the ownership of the whole allocation
     make_tmap(&tmap, A, md, n, lda);
     const int G = grid_ctas > 0 ? grid_ctas : num_sms;
+    by_smid = false;   // the block K1 streams has changed: even split (the weights were measured on the whole matrix)
+    sm_weight.clear();
     plan = k1_make_plan(md, n, G);
-    d_unit_begin.upload(plan.cta_unit_begin);
-    d_slot_base.upload(plan.band_slot_base);
-    d_first_cta.upload(plan.band_first_cta);
+    upload_plan();
     rowpart.alloc((size_t)plan.NB * 2 * m_pad_local);
-    colpart.alloc((size_t)std::max(plan.nslots, 1) * 2 * K1_BW);
     xbuf.alloc((size_t)2 * (n_pad + m_pad));
     kind = 3;
+    if (k1_balance && grid_ctas <= 0) calibrate(st);
 }
 
 MatOp::~MatOp()
@@ -508,6 +621,12 @@ MVView MatOp::run_t(const double *const *X, const double *const *W, const int32_
         a.RT = plan.RT;
         a.NB = plan.NB;
         a.kc_last = plan.kc_last;
+        a.by_smid = by_smid ? 1 : 0;
+        a.claim = d_claim.p;
+        a.claim_epoch = d_claim.p + plan.G;
+        a.exit_ticket = d_claim.p + plan.G + 1;
+        a.cta_cycles = d_cta_cycles.p;
+        a.cta_smid = d_cta_smid.p;
         k1_dual_matvec_tma<NV><<<plan.G, K1_THREADS, k1_smem_bytes(NV), st>>>(tmap, a);
         if (stats) stats->launches++;
         V.rowpart = rowpart.p;

@@ -23,6 +23,8 @@
 //     per entry in fixed order -> bitwise reproducible, no atomics.
 //   * extra HBM traffic over the algorithmic 8*m*n bytes: 8*NV*(m*NB + n*slots/NB...) ~ 0.2 %.
 #pragma once
+#include <cmath>
+
 #include "common.cuh"
 
 namespace fos {
@@ -49,7 +51,9 @@ struct K1Plan {
     std::vector<int32_t> band_first_cta;  // [NB]
 };
 
-inline K1Plan k1_make_plan(int64_t m_local, int64_t n, int G_req)
+// `weight` (optional, G_req entries, mean 1): relative speed of the SM that runs work range g (MatOp::calibrate):
+// range g receives a share of the tiles proportional to its weight instead of 1/G.
+inline K1Plan k1_make_plan(int64_t m_local, int64_t n, int G_req, const double *weight = nullptr)
 {
     K1Plan P;
     P.RT = (int32_t)((m_local + K1_TR - 1) / K1_TR);
@@ -72,8 +76,15 @@ inline K1Plan k1_make_plan(int64_t m_local, int64_t n, int G_req)
     // every CTA gets a non-empty, contiguous range (G <= units): the slot of a CTA inside a band is
     // its distance from the band's first CTA, which needs the owners of a band to be consecutive.
     int64_t u = 0;
+    double wsum = 0.0, wacc = 0.0;
+    if (weight && G == G_req)
+        for (int g = 0; g < G; g++) wsum += weight[g];
     for (int g = 0; g < G; g++) {
         int64_t target = (Wt * g + G - 1) / G;  // ceil
+        if (wsum > 0.0) {
+            target = (int64_t)std::ceil((double)Wt * (wacc / wsum) - 1e-9);
+            wacc += weight[g];
+        }
         while (u < units - (G - g) && pre(u) < target) u++;
         if (g > 0 && u <= P.cta_unit_begin[g - 1]) u = P.cta_unit_begin[g - 1] + 1;
         P.cta_unit_begin[g] = (int32_t)u;
@@ -174,6 +185,17 @@ struct K1Args {
     const int32_t *band_slot_base;
     const int32_t *band_first_cta;
     const int32_t *skip_flag;  // device int: nonzero -> return immediately (CG batch predication)
+    // Work ranges bound to SMs (MatOp::calibrate): with by_smid the CTA running on SM s takes range s (one CTA per SM:
+    // the kernel needs the whole shared memory), so that a range can be sized to the measured speed of its SM.
+    // claim[r] == epoch + 1 marks range r as taken in this launch (a CTA whose SM's range is taken -- which only happens
+    // when the grid is not fully co-resident -- probes for the next free one: every range runs exactly once whatever
+    // the placement, and its content never depends on who runs it).
+    int32_t by_smid;
+    unsigned int *claim;        // [G]
+    unsigned int *claim_epoch;  // launches completed so far; advanced by the last CTA to finish
+    unsigned int *exit_ticket;
+    unsigned long long *cta_cycles;  // optional [G]: SM cycles from kernel start to the end of range g's work
+    int32_t *cta_smid;               // optional [G]: the SM that ran range g
     int64_t n_pad;
     int64_t m_pad_local;
     int32_t RT, NB, kc_last;
@@ -218,10 +240,23 @@ k1_dual_matvec_tma(const __grid_constant__ CUtensorMap tmap, const K1Args<NV> ar
     uint64_t *empty = full + S;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int g = blockIdx.x;
-    const int u_begin = args.cta_unit_begin[g], u_end = args.cta_unit_begin[g + 1];
-
+    __shared__ int s_rank;
+    const long long t_start = clock64();
+    unsigned int epoch = 0;
     if (threadIdx.x == 0) {
+        int r = blockIdx.x;
+        if (args.by_smid) {
+            unsigned int smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            epoch = *args.claim_epoch;
+            r = smid < gridDim.x ? (int)smid : (int)blockIdx.x;
+            for (unsigned int k = 0; k < gridDim.x; k++) {
+                if (atomicExch(&args.claim[r], epoch + 1u) != epoch + 1u) break;  // range r was free: it is ours
+                r = r + 1 == (int)gridDim.x ? 0 : r + 1;
+            }
+            if (args.cta_smid) args.cta_smid[r] = (int32_t)smid;
+        }
+        s_rank = r;
         for (int s = 0; s < S; s++) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], K1_CONSUMER_WARPS);
@@ -230,7 +265,24 @@ k1_dual_matvec_tma(const __grid_constant__ CUtensorMap tmap, const K1Args<NV> ar
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
-    if (u_begin >= u_end) return;
+    const int g = s_rank;
+    const int u_begin = args.cta_unit_begin[g], u_end = args.cta_unit_begin[g + 1];
+    // the CTA's last act (thread 0): record its time, and -- as the last CTA of the launch -- open the next epoch
+    auto finish_cta = [&]() {
+        if (args.cta_cycles) args.cta_cycles[g] = (unsigned long long)(clock64() - t_start);
+        if (args.by_smid) {
+            __threadfence();
+            if (atomicAdd(args.exit_ticket, 1u) == gridDim.x - 1) {
+                *args.exit_ticket = 0u;
+                *args.claim_epoch = epoch + 1u;
+                __threadfence();
+            }
+        }
+    };
+    if (u_begin >= u_end) {
+        if (threadIdx.x == 0) finish_cta();
+        return;
+    }
 
     if (warp == K1_CONSUMER_WARPS) {
         // ================= producer warp: one elected lane drives TMA =================
@@ -341,6 +393,8 @@ k1_dual_matvec_tma(const __grid_constant__ CUtensorMap tmap, const K1Args<NV> ar
         }
     }
     if (cur_band >= 0) flush_cols(cur_band);
+    consumer_bar_sync();                 // every consumer warp has finished its part of the range
+    if (threadIdx.x == 0) finish_cta();  // (thread 0 is a consumer: the producer warp is the last one)
 }
 
 // ---------------------------------------------------------------------------------------

@@ -102,6 +102,16 @@ struct MatOp {
     K1Plan plan;
     DevBuf<int32_t> d_unit_begin, d_slot_base, d_first_cta;
     DevBuf<double> rowpart, colpart;
+    // SM-bound work ranges sized to the measured speed of every SM (calibrate(), option "k1_balance")
+    bool by_smid = false;
+    int k1_balance = 1;
+    DevBuf<unsigned int> d_claim;            // [G] claims + [G] epoch / exit ticket
+    DevBuf<unsigned long long> d_cta_cycles; // [G]
+    DevBuf<int32_t> d_cta_smid;              // [G]
+    std::vector<double> sm_weight;           // relative speed of SM g (mean 1); empty = uniform
+    double calib_spread[2] = {0.0, 0.0};     // (max - min) / mean of the per-SM times before / after balancing
+    void upload_plan();
+    void calibrate(cudaStream_t st);
     // plain path + sparse path: complete results
     DevBuf<double> full_ax, full_atw, scratch;
     DevBuf<int32_t> d_one_band;  // {0, 1}

@@ -170,7 +170,8 @@ class _Handle:
     _INFO = {"s1_calls": 0, "cgiter": 1, "alpha12": 2, "fista_t": 3, "cg_warned": 4, "total_cg": 5,
              "total_passes": 6, "launches": 7, "alphabest": 8, "mv2_ms": 9, "mv2_n": 10, "mv1_ms": 11, "mv1_n": 12,
              "mv_skipped": 13, "bytes_per_pass": 14, "num_sms": 15, "tail_ms": 16, "tail_n": 17,
-             "storage_kind": 18, "hybrid_dense_rows": 19, "hybrid_sparse_rows": 20}
+             "storage_kind": 18, "hybrid_dense_rows": 19, "hybrid_sparse_rows": 20, "k1_balanced": 21,
+             "k1_spread_before": 22, "k1_spread_after": 23}
 
     def get_state(self, which):
         z = np.empty(self.n())

@@ -115,6 +115,11 @@ const char *fos_last_error(fos_handle_t h);
  *   "batch_hybrid" 1 (default) = batch mode keeps rows with <= n/8 non-zeros out of the dense tiles (CSR + CSC) and
  *                  skips empty rows; 0 = every row is streamed as dense FP64.  Set before loading the batch.
  *   "batch_ctas"   persistent CTAs of the batch kernel (default = #SMs)
+ *   "k1_balance"   the fused mat-vec runs one persistent CTA per SM; the SMs do not stream at the same rate, so an even split
+ *                  of the tiles leaves the faster ones idle for 7-8 % of a pass.  1 (default) = at load, time a few passes
+ *                  per SM and size every SM's work range to its speed (when there are at least 4 row groups per SM;
+ *                  cached per device and shard shape for the life of the process, so equal problems get equal plans and
+ *                  bit-identical results); 2 = always; 0 = even split.  Set before loading.
  *   "psd_warp_max_d" PSD cones up to this order (default and at most 16) are projected by one warp each, eight cones per
  *                  CTA; up to 48 by 128 threads, up to 112 by one 512-thread CTA, larger ones by the cooperative kernel.
  *                  Process-wide; applies to problems loaded afterwards.
@@ -215,7 +220,8 @@ int32_t fos_set_state(fos_handle_t h, int32_t which, const double *buf, int64_t 
  * same for 1-RHS launches, 13 predicated no-op launches; 14 algorithmic bytes of one pass over A,
  * 15 number of SMs, 16 / 17 summed milliseconds / count of executed fused CG-tail launches,
  * 18 storage of A (1 dense, 2 sparse, 3 hybrid), 19 / 20 rows of the dense block / rows kept sparse
- * under hybrid row storage (0 otherwise). */
+ * under hybrid row storage (0 otherwise), 21 = 1 when the work ranges of the fused mat-vec are sized to the SMs'
+ * measured speed ("k1_balance"), 22 / 23 (max - min) / mean of the per-SM times of a pass before / after balancing. */
 int32_t fos_get_info(fos_handle_t h, int32_t which, double *out);
 /* Restores a scalar: which = 0 (S1.i), 2 (alpha12) or 3 (FISTA t). */
 int32_t fos_set_info(fos_handle_t h, int32_t which, double value);

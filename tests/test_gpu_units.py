@@ -429,3 +429,27 @@ def test_errors_are_loud(fos):
     P.constr_cones = [("SOC", 5)]            # does not cover 1:m
     with pytest.raises((fos.FosError, AssertionError)):
         load_conic(fos, P)
+
+
+def test_sm_balanced_work_ranges(fos, oracle):
+    """"k1_balance": the work ranges of the fused mat-vec are bound to SMs and sized to their measured speed.  Whatever
+    the split, every row group is processed exactly once: the products agree with the oracle and with the even split;
+    two handles of the same shape share the calibration (bit-identical results), repeated calls are bitwise equal."""
+    from fos_b200 import problems
+    P = _rand_conic(problems, 2512, 4100, seed=13)
+    O = oracle.OracleConic(P.c, P.A, P.b, P.constr_cones, P.var_cones)
+    He = load_conic(fos, P, storage="dense_direct", k1_balance=0)
+    Hb = load_conic(fos, P, storage="dense_direct", k1_balance=2)
+    Hb2 = load_conic(fos, P, storage="dense_direct", k1_balance=2)
+    assert He.info("k1_balanced") == 0
+    if Hb.info("k1_balanced") != 1:
+        pytest.skip("SM ids are not 0..G-1 on this device: the library kept the even split")
+    rng = np.random.default_rng(3)
+    for _ in range(3):
+        v = rng.standard_normal(2 * (P.m + P.n + 1))
+        yb = Hb.kkt_mul(v)
+        assert rel_err(yb, O.kkt_mul(v)) < OP_TOL
+        assert rel_err(yb, He.kkt_mul(v)) < OP_TOL
+        assert np.array_equal(yb, Hb.kkt_mul(v))
+        assert np.array_equal(yb, Hb2.kkt_mul(v))
+    print(f"per-SM time spread (max - min) / mean: {Hb.info('k1_spread_before'):.3f} -> {Hb.info('k1_spread_after'):.3f}")
