@@ -104,7 +104,7 @@ struct MatOp {
     DevBuf<double> rowpart, colpart;
     // SM-bound work ranges sized to the measured speed of every SM (calibrate(), option "k1_balance")
     bool by_smid = false;
-    int k1_balance = 1;
+    int k1_balance = 0;  // measured: no gain (the pass is bound by HBM, not by the slowest SM) -> opt-in
     DevBuf<unsigned int> d_claim;            // [G] claims + [G] epoch / exit ticket
     DevBuf<unsigned long long> d_cta_cycles; // [G]
     DevBuf<int32_t> d_cta_smid;              // [G]

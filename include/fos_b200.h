@@ -115,11 +115,13 @@ const char *fos_last_error(fos_handle_t h);
  *   "batch_hybrid" 1 (default) = batch mode keeps rows with <= n/8 non-zeros out of the dense tiles (CSR + CSC) and
  *                  skips empty rows; 0 = every row is streamed as dense FP64.  Set before loading the batch.
  *   "batch_ctas"   persistent CTAs of the batch kernel (default = #SMs)
- *   "k1_balance"   the fused mat-vec runs one persistent CTA per SM; the SMs do not stream at the same rate, so an even split
- *                  of the tiles leaves the faster ones idle for 7-8 % of a pass.  1 (default) = at load, time a few passes
- *                  per SM and size every SM's work range to its speed (when there are at least 4 row groups per SM;
- *                  cached per device and shard shape for the life of the process, so equal problems get equal plans and
- *                  bit-identical results); 2 = always; 0 = even split.  Set before loading.
+ *   "k1_balance"   the fused mat-vec runs one persistent CTA per SM and ncu shows the SMs finishing between 0.85 and 0.99 of
+ *                  a pass.  1 / 2 = at load, time a few passes per SM, bind the work ranges to SMs and size them to the
+ *                  measured speeds (1: only with >= 4 row groups per SM; cached per device and shard shape for the life of
+ *                  the process, so equal problems get equal plans and bit-identical results).  Measured on B200
+ *                  (profiles/r2_k1_balance.md): the spread of the per-SM times shrinks but the pass does not get faster --
+ *                  an SM that finishes early hands its share of the HBM bandwidth to the others; the pass is bound by
+ *                  HBM, not by the slowest SM.  Default 0 (even split).  Set before loading.
  *   "psd_warp_max_d" PSD cones up to this order (default and at most 16) are projected by one warp each, eight cones per
  *                  CTA; up to 48 by 128 threads, up to 112 by one 512-thread CTA, larger ones by the cooperative kernel.
  *                  Process-wide; applies to problems loaded afterwards.
