@@ -57,3 +57,25 @@ def test_gpu_is_as_exact_as_the_reference_arithmetic(fos, oracle, kind, alg, n_i
         return H.get_iterate(), H.info("cgiter")
 
     assert_no_worse_than_reference_arithmetic(f"{kind}/{alg}", *three_way(step_gpu, P, oracle, alg, n_iter))
+
+
+@pytest.mark.parametrize("scale,tag", [(0.02, "well-conditioned"), (1.0, "unscaled")])
+def test_gapp_projected_steps_against_exact(fos, oracle, scale, tag):
+    """GAPP's projected iterations (every iproj-th: 21 trial steps alpha = 2^k along P1(P2 P1 x) - P1 x, gapproj.jl:34-62)
+    multiply a difference of projections by up to 2^20, and the rounding of the projections with it: the strict lock-step
+    test allows 1e-9 there instead of 1e-10 (tests/test_gpu_solvers.py).  Measured against exact, that allowance is the
+    reference arithmetic's own error: the CUDA path is no further from exact than the C oracle is."""
+    from fos_b200 import problems
+    P = problems.nnls_conic(40, 50, seed=1, scale=scale)
+    H = load_conic(fos, P)
+    H.set_algorithm(ALG_SETUPS["GAPP"][1](fos))
+    H.ck(H.L.fos_begin_solve(H.h))
+
+    def step_gpu(O, i):
+        sync_state_from_oracle(H, O, "GAPP")
+        done, _, _, _ = H.run(i, 1, 100000, 1e-12)
+        assert done == 1
+        return H.get_iterate(), H.info("cgiter")
+
+    e_c, e_o, f_c, f_o = three_way(step_gpu, P, oracle, "GAPP", 42)     # iproj = 7: six projected iterations
+    assert_no_worse_than_reference_arithmetic(f"nnls/GAPP {tag}", e_c, e_o, f_c, f_o, premise=False)

@@ -79,9 +79,9 @@ def test_lockstep_strict_1e10(fos, oracle, kind, alg):
         assert H.info("s1_calls") == O.s1_calls
         e = rel_err(H.get_iterate(), O.get_state("x"))
         worst = max(worst, e)
-        # GAPP's projected step multiplies a difference of projections by alpha_best = 2^k (up to 2^20,
-        # gapproj.jl:46-58), which scales the rounding of the cone projections with it
-        tol = STEP_TOL * (10 if alg == "GAPP" else 1)
+        # (GAPP's projected step multiplies a difference of projections by alpha_best = 2^k, gapproj.jl:46-58, and the
+        # rounding of the cone projections with it: measured worst 6.8e-13 on the B200, still inside the bar)
+        tol = STEP_TOL
         assert e < tol, f"iteration {i}: iterate differs by {e:.3e}"
         if alg not in ("FISTA", "Dykstra"):  # relaxed S1 output (gap.jl:48); other algorithms reuse the buffer
             assert rel_err(H.get_state("tmp1"), O.get_state("tmp1")) < tol
@@ -254,7 +254,7 @@ def test_direct_lockstep_and_solve(fos, oracle, kind, alg):
         sync_state_from_oracle(H, O, name)
         ro = O.run(i, 1, checki=5, eps=1e-12)
         done, st, rec, _ = H.run(i, 1, 5, 1e-12)
-        tol = STEP_TOL * (100 if name == "GAPP" else 1)   # alpha_best = 2^k scales the rounding (see above)
+        tol = STEP_TOL   # (alpha_best = 2^k scales the rounding of GAPP's projected steps: measured 3.5e-15)
         assert rel_err(H.get_iterate(), O.get_state("x")) < tol, i
         if i % 5 == 0:
             assert rec[0, 8] == 0
@@ -310,6 +310,7 @@ def test_linesearch_wrapper_lockstep(fos, oracle, kind, inner):
         # then runs long and amplifies rounding (parity budget)
         tol = 1e-7 if i > 1 and ((i - 1) % 4 == 0 or i % 4 == 0) else 10 * STEP_TOL   # x0 + alpha_best*res scales rounding too
         e = rel_err(H.get_iterate(), O.get_state("x"))
+        print(f"linesearch {kind}/{inner} i={i}: deviation {e:.2e} (allowed {tol:.0e})")
         assert e < tol, (i, e)
         if i % 4 == 0:
             assert H.info("alphabest") == pytest.approx(lib_alpha(O), rel=0, abs=0)
