@@ -159,6 +159,7 @@ __device__ __forceinline__ void rotate_pair(double *__restrict__ cp, double *__r
         *reinterpret_cast<double2 *>(cp + 64 * k + 2 * lane) = pn;
         *reinterpret_cast<double2 *>(cq + 64 * k + 2 * lane) = qn;
     }
+    __syncwarp();  // every lane has read *n2p / *n2q before lane 0 replaces them
     if (lane == 0) {
         *n2p = fma(-t, ga, al);
         *n2q = fma(t, ga, be);
@@ -201,6 +202,7 @@ __device__ __forceinline__ void rotate_pair_reg(double2 (&P)[DK], double &al, do
         P[k] = pn;
         *reinterpret_cast<double2 *>(cq + 64 * k + 2 * lane) = qn;
     }
+    __syncwarp();  // every lane has read *n2q before lane 0 replaces it
     if (lane == 0) *n2q = fma(t, ga, be);
     al = fma(-t, ga, al);
 }

@@ -15,10 +15,21 @@ def rel_err(a, b):
     return float(np.abs(a - b).max(initial=0.0) / den)
 
 
+def _tool_overrides(options):
+    """FOS_TEST_USE_GRAPHS=0 runs every test on the kernel-per-launch path unless the test chooses itself:
+    compute-sanitizer's synccheck / racecheck cannot follow a conditional WHILE node (scripts/gpu_sanitize_r2.sh,
+    profiles/r2_sanitizer.md), so those tools check the same kernels launched one by one."""
+    import os
+    v = os.environ.get("FOS_TEST_USE_GRAPHS")
+    if v is not None and "use_graphs" not in options:
+        options["use_graphs"] = int(v)
+
+
 def load_conic(fos, P, storage="auto", **options):
     """ConicProblem -> fos Handle with the problem loaded (C ABI: fos_load_conic_csc/dense)."""
     from fos_b200 import model as M
     H = fos.Handle(0)
+    _tool_overrides(options)
     for k, v in options.items():
         H.set_option(k, v)
     t1, l1 = M._cone_arrays(P.constr_cones, P.m, "constraint")
@@ -43,6 +54,7 @@ def load_conic(fos, P, storage="auto", **options):
 def load_affine(fos, A, b, q, beta, cones, decreasing=False, storage="auto", **options):
     from fos_b200 import model as M
     H = fos.Handle(0)
+    _tool_overrides(options)
     for k, v in options.items():
         H.set_option(k, v)
     Am, colptr, rowval, nzval = M._csc_arrays(A)
