@@ -21,13 +21,17 @@
 // after falling by >= 100x in one sweep (quadratic phase: the next sweep would find ~1e-15).
 // Deterministic: fixed pair order, fixed reduction trees, no floating-point atomics.
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 
 #include "solver.cuh"
 
 namespace fos {
 
 constexpr int PL_MAX_SWEEPS = 48;
-constexpr int PL_MAX_BLOCKS = 128;  // d_pad / BS for d <= 1024
+constexpr unsigned int PL_SPIN_LIMIT = 1u << 22;  // polls of one thread for one block (seconds) before the kernel gives up
+constexpr int PL_NBUF = 8;         // G buffers: version v of a block lives in buffer v % PL_NBUF ...
+constexpr int PL_SYNC_STEPS = 8;   // ... and the CTAs of a cone meet every PL_SYNC_STEPS steps (see "block exchange" below)
 constexpr int PL_TILE = 64;
 constexpr int PL_JC = 32;  // columns of W per shared-memory chunk of the final product
 
@@ -38,8 +42,6 @@ struct PsdLargeCtl {  // one per cone, zeroed before every launch
     unsigned int flag;  // last completed barrier target, on its own cache line (the waiters poll this one)
     unsigned int pad1_[31];
     unsigned long long maxcos[PL_MAX_SWEEPS];  // bit pattern of the largest |cos| seen in sweep k
-    unsigned int ready[PL_MAX_BLOCKS];  // version of every column block in global memory: 1 after the initial
-                                        // fill, +1 per Jacobi step (each block is rotated once per step)
 };
 
 struct PsdLargeArgs {
@@ -47,7 +49,7 @@ struct PsdLargeArgs {
     const double *in;
     double *proj;
     double *work;
-    int64_t work_stride;  // doubles per cone: G [d_pad][dS] | M [d_pad][dS] | lam [d_pad]
+    int64_t work_stride;  // doubles per cone: PL_NBUF x G [d_pad][dS] | M [d_pad][dS] | lam [d_pad]
     PsdLargeCtl *ctl;
     double *vstore;       // per cone: the orthonormal eigenvector basis V of the previous projection [d_pad][dS]
     int64_t vstore_stride;
@@ -114,97 +116,134 @@ template <int DK>
 struct PLCfg {
     static constexpr int BS = 8;                 // columns per block == warps per CTA
     static constexpr int THREADS = 32 * BS;
-    static constexpr int DS = 64 * DK;           // padded column length
+    static constexpr int ROWS = 64 * DK;         // rows that take part in the arithmetic (d <= ROWS, the rest zero)
+    static constexpr int DS = ROWS + 4;          // column stride: +4 doubles keeps the MMA fragment loads of the Gram
+                                                 // step (8 columns x 4 rows per warp) free of bank conflicts
     static constexpr size_t COLS_BYTES = (size_t)2 * BS * DS * sizeof(double);
     static constexpr size_t PROD_BYTES = (size_t)2 * 32 * 64 * sizeof(double);  // Wi / Wk chunks of the final product
     static constexpr size_t SMEM = COLS_BYTES > PROD_BYTES ? COLS_BYTES : PROD_BYTES;
 };
 
-// one warp: orthogonalise columns P and Q (shared memory, DS doubles each).  n2p / n2q hold the squared
-// column norms: computed when the block is loaded, updated here with the rotation identities
-// alpha' = alpha - t*gamma, beta' = beta + t*gamma (at most 2*BS-1 updates before the next reload).
-// lmax2 tracks the largest cos^2 seen.
-template <int DK>
-__device__ __forceinline__ void rotate_pair(double *__restrict__ cp, double *__restrict__ cq, double *n2p, double *n2q,
-                                            int lane, double tiny2, double &lmax2)
+// D(8x8) += A(8x4) B(4x8) on the FP64 tensor cores.  Fragments: a = A[lane/4][lane%4], b = B[lane%4][lane/4],
+// c = {D[lane/4][2*(lane%4)], D[lane/4][2*(lane%4)+1]}.
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b)
 {
-    double2 P[DK], Q[DK];
-    double g0 = 0.0, g1 = 0.0;
-#pragma unroll
-    for (int k = 0; k < DK; k++) {
-        P[k] = *reinterpret_cast<const double2 *>(cp + 64 * k + 2 * lane);
-        Q[k] = *reinterpret_cast<const double2 *>(cq + 64 * k + 2 * lane);
-        g0 = fma(P[k].x, Q[k].x, g0);
-        g1 = fma(P[k].y, Q[k].y, g1);
-    }
-    const double ga = warp_sum(g0 + g1);
-    const double al = *n2p, be = *n2q;
-    const double ab = al * be;
-    if (!(ab > tiny2)) return;  // a zero (padding) column
-    const double g2 = ga * ga;
-    lmax2 = fmax(lmax2, g2 / ab);
-    if (!(g2 > 1e-30 * ab)) return;  // |cos| <= 1e-15
-    const double delta = be - al;
-    const double hyp = sqrt(fma(delta, delta, 4.0 * g2));
-    const double t = (delta >= 0.0 ? 2.0 : -2.0) * ga / (fabs(delta) + hyp);
-    const double c = rsqrt(fma(t, t, 1.0));
-    const double s = c * t;
-#pragma unroll
-    for (int k = 0; k < DK; k++) {
-        double2 pn, qn;
-        pn.x = fma(-s, Q[k].x, c * P[k].x);
-        pn.y = fma(-s, Q[k].y, c * P[k].y);
-        qn.x = fma(s, P[k].x, c * Q[k].x);
-        qn.y = fma(s, P[k].y, c * Q[k].y);
-        *reinterpret_cast<double2 *>(cp + 64 * k + 2 * lane) = pn;
-        *reinterpret_cast<double2 *>(cq + 64 * k + 2 * lane) = qn;
-    }
-    __syncwarp();  // every lane has read *n2p / *n2q before lane 0 replaces them
-    if (lane == 0) {
-        *n2p = fma(-t, ga, al);
-        *n2q = fma(t, ga, be);
-    }
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+        : "+d"(c[0]), "+d"(c[1])
+        : "d"(a), "d"(b));
 }
 
-// Same rotation with column P held in REGISTERS by its warp for all BS rounds of a step (shared memory
-// bandwidth, not FP64, bounds the sweep: this halves the LDS/STS traffic).  al = ||P||^2 travels with it.
-template <int DK>
-__device__ __forceinline__ void rotate_pair_reg(double2 (&P)[DK], double &al, double *__restrict__ cq, double *n2q,
-                                                int lane, double tiny2, double &lmax2)
+// 1/sqrt(w) to full precision for a normal positive w, without the branches of rsqrt(): hardware seed (about 20
+// bits) and two Newton steps.  w = 0 gives NaN (the callers select it away).
+__device__ __forceinline__ double rsqrt_nr(double w)
 {
-    double2 Q[DK];
-    double g0 = 0.0, g1 = 0.0;
-#pragma unroll
-    for (int k = 0; k < DK; k++) {
-        Q[k] = *reinterpret_cast<const double2 *>(cq + 64 * k + 2 * lane);
-        g0 = fma(P[k].x, Q[k].x, g0);
-        g1 = fma(P[k].y, Q[k].y, g1);
-    }
-    const double ga = warp_sum(g0 + g1);
-    const double be = *n2q;
-    const double ab = al * be;
-    if (!(ab > tiny2)) return;
-    const double g2 = ga * ga;
-    lmax2 = fmax(lmax2, g2 / ab);
-    if (!(g2 > 1e-30 * ab)) return;
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(w));
+    double e = fma(-(w * y), y, 1.0);
+    y = fma(0.5 * y, e, y);
+    e = fma(-(w * y), y, 1.0);
+    return fma(0.5 * y, e, y);
+}
+
+// The Jacobi rotation that orthogonalises columns p < q, from their Gram entries al = S[p][p], be = S[q][q],
+// g = S[p][q]:  p' = c p - s q,  q' = s p + c q  with tan(2 theta) = 2 g / (be - al), |theta| <= pi/4.
+// Returns, for index i of the pair (partner ip), the coefficients of  x_i' = c x_i + e x_ip  and cos^2 between the
+// two columns (20 bits are plenty for the convergence test).  Two rsqrt, no division, no branch:
+// r1 = 1/sqrt(delta^2 + 4 g^2),  c^2 = (1 + |delta| r1)/2,  s = sign(delta) g r1 / c.
+template <int LD>
+__device__ __forceinline__ void jacobi_cs(const double (*S)[LD], int i, int ip, double tiny2, double &c, double &e,
+                                          double &cos2)
+{
+    const int p = i < ip ? i : ip, q = i < ip ? ip : i;
+    const double al = S[p][p], be = S[q][q], g = S[p][q];
+    const double ab = al * be, g2 = g * g;
+    double rab;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rab) : "d"(ab));
+    const bool live = ab > tiny2;                // not a zero (padding) column
+    const bool rot = live && g2 > 1e-30 * ab;    // |cos| > 1e-15
     const double delta = be - al;
-    const double hyp = sqrt(fma(delta, delta, 4.0 * g2));
-    const double t = (delta >= 0.0 ? 2.0 : -2.0) * ga / (fabs(delta) + hyp);
-    const double c = rsqrt(fma(t, t, 1.0));
-    const double s = c * t;
+    const double r1 = rsqrt_nr(fma(delta, delta, 4.0 * g2));
+    const double cc = fma(0.5 * fabs(delta), r1, 0.5);
+    const double r2 = rsqrt_nr(cc);
+    const double sn = (delta >= 0.0 ? g : -g) * (r1 * r2);
+    c = rot ? cc * r2 : 1.0;
+    e = rot ? (i < ip ? -sn : sn) : 0.0;
+    cos2 = live ? g2 * rab : 0.0;
+}
+
+// ---- block exchange between the CTAs of a cone: self-validating words, no flags and no fences -------------------
+// Version v of a column block (v = number of steps it has been through) lives in G buffer v % PL_NBUF, and every
+// double of it carries bit (v / PL_NBUF) & 1 in its last mantissa bit (a perturbation of one ulp, the size of the
+// rounding of the rotation itself).  A reader polls the data, not a flag, and the writer's stores need no fence.
+// What can a location hold when its reader polls for version v?  Older versions of the same block, v - PL_NBUF,
+// v - 2 PL_NBUF, ...  The first carries the other bit; the second carries the SAME bit, so it must be impossible:
+// the CTAs of a cone meet at a barrier every PL_SYNC_STEPS steps, every version up to the last barrier's step is
+// written, and the reader is at most PL_SYNC_STEPS - 1 steps past it: the stalest content is younger than
+// v - PL_SYNC_STEPS - PL_NBUF + 1 > v - 2 PL_NBUF.  (Without the barrier the lag is only bounded by the number of
+// CTAs: a CTA may run one step ahead of its neighbour, two ahead of the next, ...; measured: with 64 CTAs and two
+// buffers, stale blocks WERE accepted.)  Overwriting is safe for any PL_NBUF >= 2: version v + PL_NBUF is written by
+// the CTA that read v + PL_NBUF - 1, which exists only after v was read.
+static_assert(PL_SYNC_STEPS <= PL_NBUF, "the stalest possible content must carry the other version bit");
+__device__ __forceinline__ unsigned long long version_bit(unsigned int ver) { return (ver / PL_NBUF) & 1u; }
+__device__ __forceinline__ double tag_word(double v, unsigned long long bit)
+{
+    return __longlong_as_double((long long)(((unsigned long long)__double_as_longlong(v) & ~1ull) | bit));
+}
+__device__ __forceinline__ double2 ld_relaxed_v2(const double *p)
+{
+    double2 v;
+    asm volatile("ld.relaxed.gpu.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_v2(double *p, double x, double y)
+{
+    asm volatile("st.relaxed.gpu.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(x), "d"(y) : "memory");
+}
+__device__ __forceinline__ bool tag_ok(double2 v, unsigned long long bit)
+{
+    return (((unsigned long long)__double_as_longlong(v.x) & 1ull) == bit) &&
+           (((unsigned long long)__double_as_longlong(v.y) & 1ull) == bit);
+}
+// rows 0..ROWS-1 of the BS columns of one block, version `ver`, into shared memory (the 4 padding rows stay zero)
+template <int DK, int BS, int T>
+__device__ __forceinline__ void load_block_tagged(double *sdst, const double *gsrc, unsigned int ver)
+{
+    constexpr int ROWS = 64 * DK, DS = ROWS + 4, H = ROWS / 2, NU = BS * H / T;
+    static_assert(BS * H % T == 0, "whole number of 16-byte units per thread");
+    const unsigned long long bit = version_bit(ver);
+    int off[NU];
 #pragma unroll
-    for (int k = 0; k < DK; k++) {
-        double2 pn, qn;
-        pn.x = fma(-s, Q[k].x, c * P[k].x);
-        pn.y = fma(-s, Q[k].y, c * P[k].y);
-        qn.x = fma(s, P[k].x, c * Q[k].x);
-        qn.y = fma(s, P[k].y, c * Q[k].y);
-        P[k] = pn;
-        *reinterpret_cast<double2 *>(cq + 64 * k + 2 * lane) = qn;
+    for (int k = 0; k < NU; k++) {
+        const int u = threadIdx.x + T * k, col = u / H;
+        off[k] = col * DS + 2 * (u - col * H);
     }
-    __syncwarp();  // every lane has read *n2q before lane 0 replaces it
-    if (lane == 0) *n2q = fma(t, ga, be);
-    al = fma(-t, ga, al);
+    double2 v[NU];
+    unsigned int spins = 0;  // a block that never arrives is a bug: stop the kernel instead of hanging the GPU
+    // the block's writer stores in this order too: when the last unit is there, the others mostly are
+    do {
+        v[NU - 1] = ld_relaxed_v2(gsrc + off[NU - 1]);
+        if (++spins > PL_SPIN_LIMIT) {
+            printf("k5_psd_hestenes: block (%d,%d) thread %d waited for version %u, last unit %016llx %016llx\n",
+                   (int)blockIdx.x, (int)NU - 1, (int)threadIdx.x, ver, (unsigned long long)__double_as_longlong(v[NU - 1].x),
+                   (unsigned long long)__double_as_longlong(v[NU - 1].y));
+            __trap();
+        }
+    } while (!tag_ok(v[NU - 1], bit));
+#pragma unroll
+    for (int k = 0; k < NU - 1; k++) v[k] = ld_relaxed_v2(gsrc + off[k]);
+#pragma unroll
+    for (int k = 0; k < NU; k++) {
+        while (!tag_ok(v[k], bit)) {
+            v[k] = ld_relaxed_v2(gsrc + off[k]);
+            if (++spins > PL_SPIN_LIMIT) {
+                printf("k5_psd_hestenes: block (%d,%d) thread %d waited for version %u, unit %016llx %016llx\n",
+                       (int)blockIdx.x, k, (int)threadIdx.x, ver, (unsigned long long)__double_as_longlong(v[k].x),
+                       (unsigned long long)__double_as_longlong(v[k].y));
+                __trap();
+            }
+        }
+        *reinterpret_cast<double2 *>(sdst + off[k]) = v[k];
+    }
 }
 
 // acc[j] = sum_k M[i][k] * vc[j][k] for the BS columns vc (shared memory) and row i; M symmetric, column k
@@ -231,13 +270,17 @@ template <int DK>
 __global__ void __launch_bounds__(PLCfg<DK>::THREADS, 1) k5_psd_hestenes(const PsdLargeArgs a)
 {
     using Cfg = PLCfg<DK>;
-    constexpr int BS = Cfg::BS, T = Cfg::THREADS, DS = Cfg::DS;
+    constexpr int BS = Cfg::BS, T = Cfg::THREADS, DS = Cfg::DS, ROWS = Cfg::ROWS, NC = 2 * BS, NW = T / 32;
+    static_assert(T == NC * NC && BS == 8, "one thread per entry of the NC x NC Gram block; 8x8 MMA tiles");
     extern __shared__ __align__(128) unsigned char pl_smem[];
     double *cols = reinterpret_cast<double *>(pl_smem);  // [2*BS][DS]
     __shared__ __align__(8) uint64_t s_mbar;
     __shared__ double s_w[T / 32][2 * BS > 4 ? 2 * BS : 4];
     __shared__ double s_lam[2 * BS];
-    __shared__ double s_n2[2 * BS];
+    __shared__ __align__(16) double s_part[NW][3][64];  // per-warp partial Gram tiles: (a,a), (b,a), (b,b)
+    __shared__ double s_S[2][NC][NC + 1];               // Gram block of the step's 2*BS columns, double-buffered
+    __shared__ __align__(16) double s_J[2][NC][NC];     // accumulated rotations
+    __shared__ signed char s_partner[2 * BS - 1][NC];   // rounds 0..BS-2: pairs inside each block; BS-1..2BS-2: cross pairs
     __shared__ int s_plist[1024 + 64];
     __shared__ int s_npos;
 
@@ -246,8 +289,9 @@ __global__ void __launch_bounds__(PLCfg<DK>::THREADS, 1) k5_psd_hestenes(const P
     const int d = C.d;
     const int NBk = 2 * a.CT;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double *G = a.work + (size_t)cone * a.work_stride;
-    double *M0 = G + (size_t)a.d_pad * DS;
+    double *G = a.work + (size_t)cone * a.work_stride;  // PL_NBUF G buffers, M, lambda
+    const size_t gbuf = (size_t)a.d_pad * DS;
+    double *M0 = G + PL_NBUF * gbuf;
     double *lam_g = M0 + (size_t)a.d_pad * DS;
     PsdLargeCtl *ctl = a.ctl + cone;
     unsigned int epoch = 0;
@@ -261,6 +305,24 @@ __global__ void __launch_bounds__(PLCfg<DK>::THREADS, 1) k5_psd_hestenes(const P
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     uint32_t mphase = 0;
+    for (int idx = threadIdx.x; idx < (2 * BS - 1) * NC; idx += T) {
+        const int r = idx / NC, i = idx - r * NC;
+        int partner = i;
+        if (r < BS - 1) {
+            const int blk = i / BS, li = i - blk * BS;
+            for (int k = 0; k < BS / 2; k++) {
+                int p, q;
+                rr_pair_l(r, k, BS, p, q);
+                if (p == li) partner = blk * BS + q;
+                if (q == li) partner = blk * BS + p;
+            }
+        } else {
+            const int rc = r - (BS - 1);
+            partner = i < BS ? BS + ((i + rc) & (BS - 1)) : ((i - BS - rc) & (BS - 1));
+        }
+        s_partner[r][i] = (signed char)partner;
+    }
+    for (int idx = threadIdx.x; idx < 2 * BS * DS; idx += T) cols[idx] = 0.0;  // the block loads skip the padding rows
 
     // ---- phase 0: ||M||_F (every CTA of the group computes the identical value) ----
     double fro2;
@@ -298,7 +360,7 @@ __global__ void __launch_bounds__(PLCfg<DK>::THREADS, 1) k5_psd_hestenes(const P
                 if (i == j) v *= sq2;
             }
             M0[(size_t)j * DS + i] = v;
-            G[(size_t)j * DS + i] = (i == j && i < d) ? v + sigma : v;
+            G[(size_t)j * DS + i] = tag_word((i == j && i < d) ? v + sigma : v, 0ull);  // version 0
         }
     }
     group_barrier(ctl, epoch, a.CT);
@@ -313,7 +375,8 @@ __global__ void __launch_bounds__(PLCfg<DK>::THREADS, 1) k5_psd_hestenes(const P
         if (threadIdx.x == 0) {
             asm volatile("fence.proxy.async;" ::: "memory");
             mbar_expect_tx(&s_mbar, 2 * BLK_BYTES0);
-            bulk_load_1d(cols, v0, 2 * BLK_BYTES0, &s_mbar);
+            bulk_load_1d(cols, v0, BLK_BYTES0, &s_mbar);  // one copy per block: a block is < 128 KB for every d <= 1024
+            bulk_load_1d(cols + BS * DS, v0 + (size_t)BS * DS, BLK_BYTES0, &s_mbar);
         }
         mbar_wait(&s_mbar, mphase);
         mphase ^= 1;
@@ -324,97 +387,134 @@ __global__ void __launch_bounds__(PLCfg<DK>::THREADS, 1) k5_psd_hestenes(const P
                 if (i < d) sym_times_cols<BS, DS>(M0, d, vc, i, acc);
 #pragma unroll
                 for (int j = 0; j < BS; j++)
-                    g0w[(size_t)(half * BS + j) * DS + i] = i < d ? fma(sigma, vc[(size_t)j * DS + i], acc[j]) : 0.0;
+                    g0w[(size_t)(half * BS + j) * DS + i] =
+                        tag_word(i < d ? fma(sigma, vc[(size_t)j * DS + i], acc[j]) : 0.0, 0ull);
             }
         }
         group_barrier(ctl, epoch, a.CT);
     }
 
     // ---- phase 2: block Jacobi sweeps ----
-    // Between steps a CTA only depends on the two CTAs that rotated its next blocks: every block carries a
-    // version counter in global memory (ready[]), bumped by its owner after the store and awaited by the next
-    // owner before the load.  Only the current owner reads or writes a block, so there is no WAR hazard and no
-    // group-wide barrier inside a sweep (one per sweep remains, for the convergence test).
+    // Between steps a CTA only depends on the two CTAs that rotated its next blocks, and it recognises their
+    // output by the version bit of the data itself (load_block_tagged): no flags and no fences; a group-wide barrier
+    // every PL_SYNC_STEPS steps bounds the lag between CTAs, and one per sweep serves the convergence test.
     constexpr uint32_t BLK_BYTES = (uint32_t)(BS * DS * sizeof(double));
     double prev_max = 1.0;
     int sweeps_done = 0;
-    unsigned int gstep = 0;  // global step counter: blocks must have version gstep + 1
+    unsigned int gstep = 0;  // steps done so far = version of every block
     for (int sweep = 0; sweep < PL_MAX_SWEEPS; sweep++) {
         double lmax = 0.0;
         for (int step = 0; step < NBk - 1; step++, gstep++) {
             int ba, bb;
             rr_pair_l(step, cta, NBk, ba, bb);
-            double *ga_ = G + (size_t)ba * BS * DS, *gb_ = G + (size_t)bb * BS * DS;
-            if (threadIdx.x == 0) {
-                if (gstep > 0) {
-                    const unsigned int want = gstep + 1u;
-                    unsigned int va, vb;
-                    do {
-                        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(va) : "l"(&ctl->ready[ba]) : "memory");
-                        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(vb) : "l"(&ctl->ready[bb]) : "memory");
-                    } while (va < want || vb < want);
-                    __threadfence();
-                }
-                asm volatile("fence.proxy.async;" ::: "memory");
-                mbar_expect_tx(&s_mbar, 2 * BLK_BYTES);
-                bulk_load_1d(cols, ga_, BLK_BYTES, &s_mbar);
-                bulk_load_1d(cols + BS * DS, gb_, BLK_BYTES, &s_mbar);
-            }
-            mbar_wait(&s_mbar, mphase);
-            mphase ^= 1;
-            for (int cidx = warp; cidx < 2 * BS; cidx += T / 32) {
-                const double *cp = cols + (size_t)cidx * DS;
-                double n0 = 0.0, n1 = 0.0;
-#pragma unroll
-                for (int k = 0; k < DK; k++) {
-                    const double2 v = *reinterpret_cast<const double2 *>(cp + 64 * k + 2 * lane);
-                    n0 = fma(v.x, v.x, n0);
-                    n1 = fma(v.y, v.y, n1);
-                }
-                n0 = warp_sum(n0 + n1);
-                if (lane == 0) s_n2[cidx] = n0;
-            }
-            __syncthreads();
-            if (step == 0) {
-                // pairs inside each of the two blocks, once per sweep
-                for (int st = 0; st < BS - 1; st++) {
-                    const int blk = warp / (BS / 2), k = warp - blk * (BS / 2);
-                    int p, q;
-                    rr_pair_l(st, k, BS, p, q);
-                    rotate_pair<DK>(cols + (size_t)(blk * BS + p) * DS, cols + (size_t)(blk * BS + q) * DS,
-                                    s_n2 + blk * BS + p, s_n2 + blk * BS + q, lane, tiny2, lmax);
-                    __syncthreads();
-                }
-            }
             {
-                // cross pairs: warp w keeps column w of the first block in registers through the BS rounds
-                double2 P[DK];
-                double *cp = cols + (size_t)warp * DS;
-#pragma unroll
-                for (int k = 0; k < DK; k++) P[k] = *reinterpret_cast<const double2 *>(cp + 64 * k + 2 * lane);
-                double al = s_n2[warp];
-                for (int r = 0; r < BS; r++) {
-                    const int q = BS + ((warp + r) & (BS - 1));
-                    rotate_pair_reg<DK>(P, al, cols + (size_t)q * DS, s_n2 + q, lane, tiny2, lmax);
-                    __syncthreads();
-                }
-#pragma unroll
-                for (int k = 0; k < DK; k++) *reinterpret_cast<double2 *>(cp + 64 * k + 2 * lane) = P[k];
+                const double *src = G + (gstep % PL_NBUF) * gbuf;
+                load_block_tagged<DK, BS, T>(cols, src + (size_t)ba * BS * DS, gstep);
+                load_block_tagged<DK, BS, T>(cols + BS * DS, src + (size_t)bb * BS * DS, gstep);
             }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncthreads();
-            if (threadIdx.x == 0) {
-                bulk_store_1d(ga_, cols, BLK_BYTES);
-                bulk_store_1d(gb_, cols + BS * DS, BLK_BYTES);
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-                asm volatile("fence.proxy.async;" ::: "memory");
-                __threadfence();
-                asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&ctl->ready[ba]), "r"(gstep + 2u) : "memory");
-                asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&ctl->ready[bb]), "r"(gstep + 2u) : "memory");
+            {
+
+            // S = X'X for the step's 2*BS columns on the FP64 tensor cores: warp w takes rows 8w..8w+7 of every
+            // 64 (two k-steps, two accumulator sets); the partial tiles are summed across warps in a fixed order.
+            {
+                const int g = lane >> 2, k4 = lane & 3;
+                const double *x0 = cols + (size_t)g * DS + k4;
+                const double *x1 = cols + (size_t)(BS + g) * DS + k4;
+                double c00[2] = {0.0, 0.0}, c10[2] = {0.0, 0.0}, c11[2] = {0.0, 0.0};
+                double e00[2] = {0.0, 0.0}, e10[2] = {0.0, 0.0}, e11[2] = {0.0, 0.0};
+#pragma unroll 2
+                for (int i0 = 8 * warp; i0 < ROWS; i0 += 8 * NW) {
+                    const double a0 = x0[i0], a1 = x1[i0], b0 = x0[i0 + 4], b1 = x1[i0 + 4];
+                    dmma884(c00, a0, a0);
+                    dmma884(c10, a1, a0);
+                    dmma884(c11, a1, a1);
+                    dmma884(e00, b0, b0);
+                    dmma884(e10, b1, b0);
+                    dmma884(e11, b1, b1);
+                }
+                double2 *pp = reinterpret_cast<double2 *>(&s_part[warp][0][g * 8 + 2 * k4]);
+                pp[0] = make_double2(c00[0] + e00[0], c00[1] + e00[1]);
+                pp[32] = make_double2(c10[0] + e10[0], c10[1] + e10[1]);
+                pp[64] = make_double2(c11[0] + e11[0], c11[1] + e11[1]);
+            }
+            __syncthreads();
+            const int ei_ = threadIdx.x >> 4, ej_ = threadIdx.x & (NC - 1);  // this thread's entry of S and J
+            {
+                int tile, idx;
+                if (ei_ < BS) {
+                    tile = ej_ < BS ? 0 : 1;
+                    idx = ej_ < BS ? ei_ * 8 + ej_ : (ej_ - BS) * 8 + ei_;
+                } else {
+                    tile = ej_ < BS ? 1 : 2;
+                    idx = ej_ < BS ? (ei_ - BS) * 8 + ej_ : (ei_ - BS) * 8 + (ej_ - BS);
+                }
+                double sv = 0.0;
+#pragma unroll
+                for (int w = 0; w < NW; w++) sv += s_part[w][tile][idx];
+                s_S[0][ei_][ej_] = sv;
+                s_J[0][ei_][ej_] = ei_ == ej_ ? 1.0 : 0.0;
+            }
+            __syncthreads();
+            // The rotations of the step on the Gram block: S <- R'SR, J <- JR per round of NC/2 disjoint pairs (in exact
+            // arithmetic what rotating the columns pair by pair does).  Every thread derives the rotations of its
+            // row pair and of its column pair itself, so a round costs one barrier.
+            int cur = 0;
+            for (int r = (step == 0 ? 0 : BS - 1); r < 2 * BS - 1; r++) {
+                const int ip = s_partner[r][ei_], jp = s_partner[r][ej_];
+                double ci, ei, cj, ej, cos2i, cos2j;
+                jacobi_cs<NC + 1>(s_S[cur], ei_, ip, tiny2, ci, ei, cos2i);
+                jacobi_cs<NC + 1>(s_S[cur], ej_, jp, tiny2, cj, ej, cos2j);
+                if (ej_ == ip && ei_ < ip) lmax = fmax(lmax, cos2i);
+                const double sij = s_S[cur][ei_][ej_], sijp = s_S[cur][ei_][jp];
+                const double sipj = s_S[cur][ip][ej_], sipjp = s_S[cur][ip][jp];
+                s_S[cur ^ 1][ei_][ej_] = ci * fma(ej, sijp, cj * sij) + ei * fma(ej, sipjp, cj * sipj);
+                s_J[cur ^ 1][ei_][ej_] = fma(ej, s_J[cur][ei_][jp], cj * s_J[cur][ei_][ej_]);
+                cur ^= 1;
+                __syncthreads();
+            }
+            // X <- X J, rows 2u and 2u+1 per thread and trip (the J entries are read once for both), straight into the
+            // next version's location with the version bit set: fire and forget
+            {
+                const double2 *J2 = reinterpret_cast<const double2 *>(&s_J[cur][0][0]);
+                double *dst = G + ((gstep + 1u) % PL_NBUF) * gbuf;
+                double *da = dst + (size_t)ba * BS * DS, *db = dst + (size_t)bb * BS * DS;
+                const unsigned long long bit = version_bit(gstep + 1u);
+#pragma unroll 1
+                for (int u = threadIdx.x; u < ROWS / 2; u += T) {
+                    asm volatile("" ::: "memory");  // keep the 128 J loads inside the trip (hoisted, they spill)
+                    double xa[NC], xb[NC], ya[NC], yb[NC];
+#pragma unroll
+                    for (int k = 0; k < NC; k++) {
+                        const double2 x2 = *reinterpret_cast<const double2 *>(cols + (size_t)k * DS + 2 * u);
+                        xa[k] = x2.x;
+                        xb[k] = x2.y;
+                        ya[k] = 0.0;
+                        yb[k] = 0.0;
+                    }
+#pragma unroll
+                    for (int k = 0; k < NC; k++) {
+#pragma unroll
+                        for (int j2 = 0; j2 < NC / 2; j2++) {
+                            const double2 jj = J2[k * (NC / 2) + j2];
+                            ya[2 * j2] = fma(xa[k], jj.x, ya[2 * j2]);
+                            ya[2 * j2 + 1] = fma(xa[k], jj.y, ya[2 * j2 + 1]);
+                            yb[2 * j2] = fma(xb[k], jj.x, yb[2 * j2]);
+                            yb[2 * j2 + 1] = fma(xb[k], jj.y, yb[2 * j2 + 1]);
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < BS; k++) {
+                        st_relaxed_v2(da + (size_t)k * DS + 2 * u, tag_word(ya[k], bit), tag_word(yb[k], bit));
+                        st_relaxed_v2(db + (size_t)k * DS + 2 * u, tag_word(ya[BS + k], bit), tag_word(yb[BS + k], bit));
+                    }
+                }
+            }
             }
             if (step == NBk - 2) {
                 // publish this CTA's largest |cos| of the sweep (non-negative doubles order like integers)
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) lmax = fmax(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
                 if (lane == 0) s_w[warp][0] = lmax;
                 __syncthreads();
                 if (threadIdx.x == 0) {
@@ -424,8 +524,10 @@ __global__ void __launch_bounds__(PLCfg<DK>::THREADS, 1) k5_psd_hestenes(const P
                     atomicMax(&ctl->maxcos[sweep], (unsigned long long)__double_as_longlong(mx));
                 }
                 group_barrier(ctl, epoch, a.CT);  // once per sweep: everybody's maxcos is in
+            } else if ((step % PL_SYNC_STEPS) == PL_SYNC_STEPS - 1) {
+                group_barrier(ctl, epoch, a.CT);  // bounds how far one CTA can run ahead of another (block exchange)
             } else {
-                __syncthreads();  // thread 0 has finished the store before the buffer is reused
+                __syncthreads();  // everybody has read the columns before the next step's loads replace them
             }
         }
         sweeps_done = sweep + 1;
@@ -438,14 +540,12 @@ __global__ void __launch_bounds__(PLCfg<DK>::THREADS, 1) k5_psd_hestenes(const P
     // ---- phase 3: own columns -> v_j, lambda_j = v_j' M v_j, w_j = sqrt(lambda_j+) v_j ----
     {
         double *g0 = G + (size_t)(2 * cta) * BS * DS;
-        if (threadIdx.x == 0) {
-            asm volatile("fence.proxy.async;" ::: "memory");
-            mbar_expect_tx(&s_mbar, 2 * BLK_BYTES);
-            bulk_load_1d(cols, g0, BLK_BYTES, &s_mbar);
-            bulk_load_1d(cols + BS * DS, g0 + BS * DS, BLK_BYTES, &s_mbar);
+        {   // the final version of this CTA's own two blocks (validated like every other block load)
+            const double *src = G + (gstep % PL_NBUF) * gbuf + (size_t)(2 * cta) * BS * DS;
+            load_block_tagged<DK, BS, T>(cols, src, gstep);
+            load_block_tagged<DK, BS, T>(cols + BS * DS, src + (size_t)BS * DS, gstep);
         }
-        mbar_wait(&s_mbar, mphase);
-        mphase ^= 1;
+        __syncthreads();
         for (int cidx = warp; cidx < 2 * BS; cidx += T / 32) {
             double *cp = cols + (size_t)cidx * DS;
             double nn = 0.0;
@@ -458,7 +558,8 @@ __global__ void __launch_bounds__(PLCfg<DK>::THREADS, 1) k5_psd_hestenes(const P
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
         if (threadIdx.x == 0) {
-            bulk_store_1d(Vst + (size_t)(2 * cta) * BS * DS, cols, 2 * BLK_BYTES);
+            bulk_store_1d(Vst + (size_t)(2 * cta) * BS * DS, cols, BLK_BYTES);
+            bulk_store_1d(Vst + (size_t)(2 * cta + 1) * BS * DS, cols + BS * DS, BLK_BYTES);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the source may be modified again
         }
@@ -497,7 +598,8 @@ __global__ void __launch_bounds__(PLCfg<DK>::THREADS, 1) k5_psd_hestenes(const P
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
         if (threadIdx.x == 0) {
-            bulk_store_1d(g0, cols, 2 * BLK_BYTES);
+            bulk_store_1d(g0, cols, BLK_BYTES);
+            bulk_store_1d(g0 + (size_t)BS * DS, cols + BS * DS, BLK_BYTES);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
             asm volatile("fence.proxy.async;" ::: "memory");
@@ -620,11 +722,12 @@ void psd_project_large(Handle *h, ConeSet &K, const double *in, double *projbuf)
     if (DK == 0)
         throw Error(FOS_ERR_UNSUPPORTED, "SDP cone of order " + std::to_string(dmax) + " exceeds the supported 1024");
     const int bs = 8;
-    const int dS = 64 * DK;
+    const int dS = 64 * DK + 4;  // PLCfg<DK>::DS
     PsdLargeArgs a;
+
     a.d_pad = (int)ru(dmax, 2 * bs);
     a.CT = a.d_pad / (2 * bs);
-    a.work_stride = ru((int64_t)2 * a.d_pad * dS + a.d_pad, 16);
+    a.work_stride = ru((int64_t)(PL_NBUF + 1) * a.d_pad * dS + a.d_pad, 16);  // G (PL_NBUF version buffers), M, lambda
     const int per_launch = std::max(1, h->num_sms / a.CT);
     const int chunk = std::min(per_launch, nc);
     if (K.psd_work.n < (size_t)a.work_stride * chunk) K.psd_work.alloc((size_t)a.work_stride * chunk);
@@ -647,6 +750,9 @@ void psd_project_large(Handle *h, ConeSet &K, const double *in, double *projbuf)
         a.vstore = K.psd_vstore.p + (size_t)c0 * a.vstore_stride;
         a.warm = (K.psd_warm && K.psd_warm_enabled) ? 1 : 0;
         FOS_CUDA(cudaMemsetAsync(K.psd_ctl.p, 0, (size_t)n * sizeof(PsdLargeCtl), h->stream));
+        // G buffers 1..PL_NBUF-1 must not hold anything a reader could take for their first version (bit 0): all ones
+        FOS_CUDA(cudaMemset2DAsync(K.psd_work.p + (size_t)a.d_pad * dS, (size_t)a.work_stride * sizeof(double), 0xFF,
+                                   (size_t)(PL_NBUF - 1) * a.d_pad * dS * sizeof(double), (size_t)n, h->stream));
         switch (DK) {
         case 2: launch_large<2>(h, a, n); break;
         case 4: launch_large<4>(h, a, n); break;

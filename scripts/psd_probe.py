@@ -48,6 +48,8 @@ def main():
     rng = np.random.default_rng(0)
     cases = [(512, 2), (512, 1), (256, 2), (128, 8), (1024, 1), (64, 64), (32, 256), (24, 512), (16, 1024), (8, 2048), (3, 4096)]
     cases += [(48, 128), (96, 32)]
+    if "--large" in sys.argv:
+        cases = [(512, 2), (512, 1), (256, 2), (256, 1), (128, 8), (1024, 1), (768, 1), (384, 1)]
     for d, nc in cases:
         Ms = np.zeros((nc, d, d))
         X = np.zeros((nc, d * (d + 1) // 2))
