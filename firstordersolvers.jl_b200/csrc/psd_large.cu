@@ -54,6 +54,7 @@ struct PsdLargeArgs {
     double *vstore;       // per cone: the orthonormal eigenvector basis V of the previous projection [d_pad][dS]
     int64_t vstore_stride;
     int warm;             // 1: start from G = (M + sigma I) V_prev instead of G = M + sigma I
+    unsigned long long *prof;  // diagnostics (FOS_PSD_PROF=1): SM clock cycles per part of the step, summed over CTAs
     int CT;     // CTAs per cone; the tournament has 2*CT blocks
     int d_pad;  // padded number of columns = 2*CT*bs
 };
@@ -204,9 +205,10 @@ __device__ __forceinline__ bool tag_ok(double2 v, unsigned long long bit)
     return (((unsigned long long)__double_as_longlong(v.x) & 1ull) == bit) &&
            (((unsigned long long)__double_as_longlong(v.y) & 1ull) == bit);
 }
-// rows 0..ROWS-1 of the BS columns of one block, version `ver`, into shared memory (the 4 padding rows stay zero)
-template <int DK, int BS, int T>
-__device__ __forceinline__ void load_block_tagged(double *sdst, const double *gsrc, unsigned int ver)
+// rows 0..ROWS-1 of the BS columns of NB blocks (1 or 2), version `ver`, into shared memory (the 4 padding rows of a
+// column stay zero).  Units that still carry the old bit are read again until they do not.
+template <int DK, int BS, int T, int NB>
+__device__ __forceinline__ void load_blocks_tagged(double *sdst, const double *gsrc0, const double *gsrc1, unsigned int ver)
 {
     constexpr int ROWS = 64 * DK, DS = ROWS + 4, H = ROWS / 2, NU = BS * H / T;
     static_assert(BS * H % T == 0, "whole number of 16-byte units per thread");
@@ -217,33 +219,43 @@ __device__ __forceinline__ void load_block_tagged(double *sdst, const double *gs
         const int u = threadIdx.x + T * k, col = u / H;
         off[k] = col * DS + 2 * (u - col * H);
     }
-    double2 v[NU];
+    double2 v[NB][NU];
     unsigned int spins = 0;  // a block that never arrives is a bug: stop the kernel instead of hanging the GPU
-    // the block's writer stores in this order too: when the last unit is there, the others mostly are
-    do {
-        v[NU - 1] = ld_relaxed_v2(gsrc + off[NU - 1]);
+    // The writers store their rows in ascending order as well: poll the LAST unit of every block (one round trip per
+    // poll for all blocks) and fetch the rest when it is there -- fetching everything up front was measured slower
+    // (the blocks are normally still on their way when the reader starts, and the stale reads load the L2).
+    for (;;) {
+        bool ok = true;
+#pragma unroll
+        for (int b = 0; b < NB; b++) v[b][NU - 1] = ld_relaxed_v2((b ? gsrc1 : gsrc0) + off[NU - 1]);
+#pragma unroll
+        for (int b = 0; b < NB; b++) ok = ok && tag_ok(v[b][NU - 1], bit);
+        if (ok) break;
         if (++spins > PL_SPIN_LIMIT) {
-            printf("k5_psd_hestenes: block (%d,%d) thread %d waited for version %u, last unit %016llx %016llx\n",
-                   (int)blockIdx.x, (int)NU - 1, (int)threadIdx.x, ver, (unsigned long long)__double_as_longlong(v[NU - 1].x),
-                   (unsigned long long)__double_as_longlong(v[NU - 1].y));
+            printf("k5_psd_hestenes: CTA %d thread %d waited for version %u: %016llx\n", (int)blockIdx.x, (int)threadIdx.x,
+                   ver, (unsigned long long)__double_as_longlong(v[0][NU - 1].x));
             __trap();
         }
-    } while (!tag_ok(v[NU - 1], bit));
-#pragma unroll
-    for (int k = 0; k < NU - 1; k++) v[k] = ld_relaxed_v2(gsrc + off[k]);
-#pragma unroll
-    for (int k = 0; k < NU; k++) {
-        while (!tag_ok(v[k], bit)) {
-            v[k] = ld_relaxed_v2(gsrc + off[k]);
-            if (++spins > PL_SPIN_LIMIT) {
-                printf("k5_psd_hestenes: block (%d,%d) thread %d waited for version %u, unit %016llx %016llx\n",
-                       (int)blockIdx.x, k, (int)threadIdx.x, ver, (unsigned long long)__double_as_longlong(v[k].x),
-                       (unsigned long long)__double_as_longlong(v[k].y));
-                __trap();
-            }
-        }
-        *reinterpret_cast<double2 *>(sdst + off[k]) = v[k];
     }
+#pragma unroll
+    for (int b = 0; b < NB; b++)
+#pragma unroll
+        for (int k = 0; k < NU - 1; k++) v[b][k] = ld_relaxed_v2((b ? gsrc1 : gsrc0) + off[k]);
+#pragma unroll
+    for (int b = 0; b < NB; b++)
+#pragma unroll
+        for (int k = 0; k < NU; k++) {
+            while (!tag_ok(v[b][k], bit)) {
+                v[b][k] = ld_relaxed_v2((b ? gsrc1 : gsrc0) + off[k]);
+                if (++spins > PL_SPIN_LIMIT) {
+                    printf("k5_psd_hestenes: CTA %d thread %d waited for version %u of block %d unit %d: %016llx %016llx\n",
+                           (int)blockIdx.x, (int)threadIdx.x, ver, b, k, (unsigned long long)__double_as_longlong(v[b][k].x),
+                           (unsigned long long)__double_as_longlong(v[b][k].y));
+                    __trap();
+                }
+            }
+            *reinterpret_cast<double2 *>(sdst + (size_t)b * BS * DS + off[k]) = v[b][k];
+        }
 }
 
 // acc[j] = sum_k M[i][k] * vc[j][k] for the BS columns vc (shared memory) and row i; M symmetric, column k
@@ -407,14 +419,19 @@ __global__ void __launch_bounds__(PLCfg<DK>::THREADS, 1) k5_psd_hestenes(const P
         for (int step = 0; step < NBk - 1; step++, gstep++) {
             int ba, bb;
             rr_pair_l(step, cta, NBk, ba, bb);
+            long long tp0 = 0, tp1 = 0, tp2 = 0, tp3 = 0, tp4 = 0;
+            if (a.prof) tp0 = clock64();
             {
                 const double *src = G + (gstep % PL_NBUF) * gbuf;
-                load_block_tagged<DK, BS, T>(cols, src + (size_t)ba * BS * DS, gstep);
-                load_block_tagged<DK, BS, T>(cols + BS * DS, src + (size_t)bb * BS * DS, gstep);
+                if constexpr (DK <= 8) {  // both blocks in flight at once while the registers allow it
+                    load_blocks_tagged<DK, BS, T, 2>(cols, src + (size_t)ba * BS * DS, src + (size_t)bb * BS * DS, gstep);
+                } else {
+                    load_blocks_tagged<DK, BS, T, 1>(cols, src + (size_t)ba * BS * DS, nullptr, gstep);
+                    load_blocks_tagged<DK, BS, T, 1>(cols + BS * DS, src + (size_t)bb * BS * DS, nullptr, gstep);
+                }
             }
             __syncthreads();
-            {
-
+            if (a.prof) tp1 = clock64();
             // S = X'X for the step's 2*BS columns on the FP64 tensor cores: warp w takes rows 8w..8w+7 of every
             // 64 (two k-steps, two accumulator sets); the partial tiles are summed across warps in a fixed order.
             {
@@ -456,61 +473,63 @@ __global__ void __launch_bounds__(PLCfg<DK>::THREADS, 1) k5_psd_hestenes(const P
                 s_J[0][ei_][ej_] = ei_ == ej_ ? 1.0 : 0.0;
             }
             __syncthreads();
+            if (a.prof) tp2 = clock64();
             // The rotations of the step on the Gram block: S <- R'SR, J <- JR per round of NC/2 disjoint pairs (in exact
-            // arithmetic what rotating the columns pair by pair does).  Every thread derives the rotations of its
-            // row pair and of its column pair itself, so a round costs one barrier.
+            // arithmetic what rotating the columns pair by pair does).  Every thread derives the rotation of its COLUMN
+            // pair itself; the rotation of its row pair is the one lane ei_ of the same warp derived (lanes 0..15 hold
+            // the column indices 0..15), so a round costs one barrier and one rotation per thread.
             int cur = 0;
-            for (int r = (step == 0 ? 0 : BS - 1); r < 2 * BS - 1; r++) {
-                const int ip = s_partner[r][ei_], jp = s_partner[r][ej_];
-                double ci, ei, cj, ej, cos2i, cos2j;
-                jacobi_cs<NC + 1>(s_S[cur], ei_, ip, tiny2, ci, ei, cos2i);
+            auto jacobi_round = [&](int ip, int jp) {
+                double cj, ej, cos2j;
                 jacobi_cs<NC + 1>(s_S[cur], ej_, jp, tiny2, cj, ej, cos2j);
-                if (ej_ == ip && ei_ < ip) lmax = fmax(lmax, cos2i);
+                const double ci = __shfl_sync(0xffffffffu, cj, ei_);
+                const double ei = __shfl_sync(0xffffffffu, ej, ei_);
+                if (ei_ == jp && ej_ < jp) lmax = fmax(lmax, cos2j);  // one thread per pair
                 const double sij = s_S[cur][ei_][ej_], sijp = s_S[cur][ei_][jp];
                 const double sipj = s_S[cur][ip][ej_], sipjp = s_S[cur][ip][jp];
                 s_S[cur ^ 1][ei_][ej_] = ci * fma(ej, sijp, cj * sij) + ei * fma(ej, sipjp, cj * sipj);
                 s_J[cur ^ 1][ei_][ej_] = fma(ej, s_J[cur][ei_][jp], cj * s_J[cur][ei_][ej_]);
                 cur ^= 1;
                 __syncthreads();
+            };
+            if (step == 0)  // pairs inside each of the two blocks, once per sweep
+                for (int r = 0; r < BS - 1; r++) jacobi_round(s_partner[r][ei_], s_partner[r][ej_]);
+#pragma unroll
+            for (int rc = 0; rc < BS; rc++) {  // cross pairs: column w of the first block meets column (w + rc) % BS of the second
+                const int ip = ei_ < BS ? BS + ((ei_ + rc) & (BS - 1)) : ((ei_ - BS - rc) & (BS - 1));
+                const int jp = ej_ < BS ? BS + ((ej_ + rc) & (BS - 1)) : ((ej_ - BS - rc) & (BS - 1));
+                jacobi_round(ip, jp);
             }
-            // X <- X J, rows 2u and 2u+1 per thread and trip (the J entries are read once for both), straight into the
-            // next version's location with the version bit set: fire and forget
+            if (a.prof) tp3 = clock64();
+            // X <- X J as Y' = J'X' on the FP64 tensor cores (the J fragments stay in registers, every element of X is
+            // read once), straight into the next version's location with the version bit set: fire and forget.
+            // Warp w takes rows 8w..8w+7 of every 64.
             {
-                const double2 *J2 = reinterpret_cast<const double2 *>(&s_J[cur][0][0]);
+                const int g = lane >> 2, k4 = lane & 3;
+                double ja[2][4];  // A fragments: J'[8 mt + g][4 ks + k4]
+#pragma unroll
+                for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                    for (int ks = 0; ks < 4; ks++) ja[mt][ks] = s_J[cur][4 * ks + k4][8 * mt + g];
                 double *dst = G + ((gstep + 1u) % PL_NBUF) * gbuf;
-                double *da = dst + (size_t)ba * BS * DS, *db = dst + (size_t)bb * BS * DS;
+                double *da = dst + (size_t)ba * BS * DS + (size_t)g * DS + 2 * k4;
+                double *db = dst + (size_t)bb * BS * DS + (size_t)g * DS + 2 * k4;
                 const unsigned long long bit = version_bit(gstep + 1u);
-#pragma unroll 1
-                for (int u = threadIdx.x; u < ROWS / 2; u += T) {
-                    asm volatile("" ::: "memory");  // keep the 128 J loads inside the trip (hoisted, they spill)
-                    double xa[NC], xb[NC], ya[NC], yb[NC];
+                const double *xb = cols + (size_t)k4 * DS + g;  // B fragments: X[n0 + g][4 ks + k4]
+#pragma unroll 2
+                for (int n0 = 8 * warp; n0 < ROWS; n0 += 8 * NW) {
+                    double ya[2] = {0.0, 0.0}, yb[2] = {0.0, 0.0};
 #pragma unroll
-                    for (int k = 0; k < NC; k++) {
-                        const double2 x2 = *reinterpret_cast<const double2 *>(cols + (size_t)k * DS + 2 * u);
-                        xa[k] = x2.x;
-                        xb[k] = x2.y;
-                        ya[k] = 0.0;
-                        yb[k] = 0.0;
+                    for (int ks = 0; ks < 4; ks++) {
+                        const double xv = xb[(size_t)(4 * ks) * DS + n0];
+                        dmma884(ya, ja[0][ks], xv);
+                        dmma884(yb, ja[1][ks], xv);
                     }
-#pragma unroll
-                    for (int k = 0; k < NC; k++) {
-#pragma unroll
-                        for (int j2 = 0; j2 < NC / 2; j2++) {
-                            const double2 jj = J2[k * (NC / 2) + j2];
-                            ya[2 * j2] = fma(xa[k], jj.x, ya[2 * j2]);
-                            ya[2 * j2 + 1] = fma(xa[k], jj.y, ya[2 * j2 + 1]);
-                            yb[2 * j2] = fma(xb[k], jj.x, yb[2 * j2]);
-                            yb[2 * j2 + 1] = fma(xb[k], jj.y, yb[2 * j2 + 1]);
-                        }
-                    }
-#pragma unroll
-                    for (int k = 0; k < BS; k++) {
-                        st_relaxed_v2(da + (size_t)k * DS + 2 * u, tag_word(ya[k], bit), tag_word(yb[k], bit));
-                        st_relaxed_v2(db + (size_t)k * DS + 2 * u, tag_word(ya[BS + k], bit), tag_word(yb[BS + k], bit));
-                    }
+                    st_relaxed_v2(da + n0, tag_word(ya[0], bit), tag_word(ya[1], bit));  // rows n0 + 2 k4, + 1 of column g
+                    st_relaxed_v2(db + n0, tag_word(yb[0], bit), tag_word(yb[1], bit));
                 }
             }
-            }
+            if (a.prof) tp4 = clock64();
             if (step == NBk - 2) {
                 // publish this CTA's largest |cos| of the sweep (non-negative doubles order like integers)
 #pragma unroll
@@ -529,6 +548,14 @@ __global__ void __launch_bounds__(PLCfg<DK>::THREADS, 1) k5_psd_hestenes(const P
             } else {
                 __syncthreads();  // everybody has read the columns before the next step's loads replace them
             }
+            if (a.prof && threadIdx.x == 0) {
+                atomicAdd(a.prof + 0, (unsigned long long)(tp1 - tp0));  // wait for + load the two blocks
+                atomicAdd(a.prof + 1, (unsigned long long)(tp2 - tp1));  // Gram block
+                atomicAdd(a.prof + 2, (unsigned long long)(tp3 - tp2));  // rotations
+                atomicAdd(a.prof + 3, (unsigned long long)(tp4 - tp3));  // X J + stores
+                atomicAdd(a.prof + 4, (unsigned long long)(clock64() - tp4));  // end-of-step barrier
+                atomicAdd(a.prof + 5, 1ull);
+            }
         }
         sweeps_done = sweep + 1;
         const double mx = __longlong_as_double((long long)*((volatile unsigned long long *)&ctl->maxcos[sweep]));
@@ -542,8 +569,8 @@ __global__ void __launch_bounds__(PLCfg<DK>::THREADS, 1) k5_psd_hestenes(const P
         double *g0 = G + (size_t)(2 * cta) * BS * DS;
         {   // the final version of this CTA's own two blocks (validated like every other block load)
             const double *src = G + (gstep % PL_NBUF) * gbuf + (size_t)(2 * cta) * BS * DS;
-            load_block_tagged<DK, BS, T>(cols, src, gstep);
-            load_block_tagged<DK, BS, T>(cols + BS * DS, src + (size_t)BS * DS, gstep);
+            load_blocks_tagged<DK, BS, T, 1>(cols, src, nullptr, gstep);
+            load_blocks_tagged<DK, BS, T, 1>(cols + BS * DS, src + (size_t)BS * DS, nullptr, gstep);
         }
         __syncthreads();
         for (int cidx = warp; cidx < 2 * BS; cidx += T / 32) {
@@ -740,6 +767,11 @@ void psd_project_large(Handle *h, ConeSet &K, const double *in, double *projbuf)
         K.psd_warm = true;  // V = I is a valid basis: the first projection is the cold start
     }
     a.vstore_stride = (int64_t)a.d_pad * dS;
+    static const bool want_prof = getenv("FOS_PSD_PROF") != nullptr;
+    static unsigned long long *d_prof = nullptr;
+    if (want_prof && !d_prof) FOS_CUDA(cudaMalloc((void **)&d_prof, 8 * sizeof(unsigned long long)));
+    if (want_prof) FOS_CUDA(cudaMemsetAsync(d_prof, 0, 8 * sizeof(unsigned long long), h->stream));
+    a.prof = want_prof ? d_prof : nullptr;
     a.in = in;
     a.proj = projbuf;
     a.work = K.psd_work.p;
@@ -765,6 +797,14 @@ void psd_project_large(Handle *h, ConeSet &K, const double *in, double *projbuf)
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess)
         throw Error(FOS_ERR_CUDA, std::string("large PSD projection launch failed: ") + cudaGetErrorString(e));
+    if (want_prof) {
+        unsigned long long hp[8];
+        FOS_CUDA(cudaStreamSynchronize(h->stream));
+        FOS_CUDA(cudaMemcpy(hp, d_prof, sizeof(hp), cudaMemcpyDeviceToHost));
+        const double n = (double)std::max<unsigned long long>(hp[5], 1);
+        fprintf(stderr, "psd_large d<=%d: %llu CTA-steps, cycles per step: load %.0f gram %.0f rotations %.0f apply %.0f sync %.0f\n",
+                64 * DK, hp[5], hp[0] / n, hp[1] / n, hp[2] / n, hp[3] / n, hp[4] / n);
+    }
 }
 
 // number of Jacobi sweeps the last large projection needed for cone 0 of its last chunk (diagnostics)

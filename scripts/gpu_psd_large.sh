@@ -13,3 +13,4 @@ for l in open("gpurun_out/psd_probe_large.jsonl"):
     print(d["d"], d["ncones"], "fos %.3f ms" % d["fos_cold_ms"], "sweeps", d["sweeps"], "lib %.3f" % d["cusolver_eigh_ms"], "speedup %.2f" % d["speedup_vs_best_library"], "diff %.1e" % d["max_rel_diff_vs_lib"])
 PY
 timeout 200 python scripts/config_runs.py c4 --iters 200 --warmup 30 2>&1 | tail -1 | tee gpurun_out/c4_new.jsonl | cut -c1-500
+FOS_PSD_PROF=1 timeout 100 python scripts/probes/psd_large_debug.py 512:1 1024:1 256:1 2>&1 | grep -E "psd_large" | awk 'NR%8==1'
