@@ -7,12 +7,20 @@
 //   1. G = M + sigma*I  (positive definite: its singular vectors ARE M's eigenvectors, also when M
 //      has eigenvalues +lambda and -lambda, where a one-sided method on M itself is ill-posed).
 //   2. One-sided (Hestenes) block Jacobi on the columns of G: G <- G J until the columns are mutually
-//      orthogonal.  Columns are grouped in 2*CT blocks of bs; a round-robin tournament over blocks
-//      gives each CTA one pair of blocks per step.  The CTA pulls its 2*bs columns into shared
-//      memory with bulk copies (TMA engine, cp.async.bulk), one warp rotates one column pair per
-//      round (bs rounds cover the bs^2 cross pairs), pushes the columns back, and the group meets at
-//      a global-memory barrier.  Rotations only touch the two columns involved, so the bs pairs of a
-//      round and the CT block pairs of a step are independent.
+//      orthogonal.  Columns are grouped in 2*CT blocks of 8; a round-robin tournament over blocks gives each CTA
+//      one pair of blocks per step.  Per step the CTA
+//        a. reads its 16 columns from global memory, recognising the other CTAs' output by a version bit in the
+//           data itself (no flags, no fences: see "block exchange" below),
+//        b. forms their 16 x 16 Gram block S = X'X on the FP64 tensor cores (DMMA m8n8k4),
+//        c. runs the step's 8 rounds of 8 disjoint rotations ON S (S <- R'SR, J <- JR: the same rotations, in
+//           exact arithmetic, as rotating the length-d columns pair by pair, without the length-d dot product
+//           and warp reduction in every round's dependency chain; G is well conditioned by construction, so
+//           working from the Gram block costs no accuracy),
+//        d. applies X <- X J on the tensor cores and stores the result straight to the next version's location.
+//      Rotations only touch the two columns involved, so the 8 pairs of a round and the CT block pairs of a
+//      step are independent.  Measured per step at d = 512 (SM cycles): exchange 2950, Gram 2500, rotations
+//      4000, X J 3650 (profiles/r2_psd_large.md); the kernel-per-pair version this replaces spent 4.8 us of an
+//      11.3 us step on the flag-based exchange alone.
 //   3. v_j = g_j/||g_j||, lambda_j = v_j' M v_j (Rayleigh quotient with the ORIGINAL matrix: the
 //      shift costs ||M||_F/|lambda| in relative accuracy of ||g_j|| - sigma, the quotient does not),
 //      w_j = sqrt(max(lambda_j,0)) v_j.
