@@ -401,6 +401,31 @@ def test_psd_large_batched_cones(fos, d, nc):
     assert np.abs(Y - Yn - X).max() <= 1e-12 * np.abs(X).max()
 
 
+@pytest.mark.parametrize("d", [640, 1024])
+def test_psd_large_block_exchange_is_reproducible(fos, d):
+    """The CTAs of a large cone exchange column blocks without flags: a reader recognises a block version by a bit in
+    the data (csrc/psd_large.cu, "block exchange").  Accepting a stale version would not crash, it would change the
+    result from run to run (it did, with two version buffers and 64 CTAs): repeated cold projections of the same
+    matrix -- random, then rank-deficient, where sweeps are few and the CTAs drift apart most -- must agree bit for
+    bit, take the same number of sweeps, and match LAPACK."""
+    from oracle import np_oracle as npo
+    rng = np.random.default_rng(7 * d)
+    X = rng.standard_normal((1, d * (d + 1) // 2))
+    ref = npo.prox_cone("SDP", X[0])
+    first = None
+    for rep in range(4):
+        H = fos.Handle(0)
+        Y, _, sw = H.time_psd(X, reps=2)
+        Y2, _, sw2 = H.time_psd(Y, reps=2)
+        if first is None:
+            first = (Y.copy(), sw, Y2.copy(), sw2)
+            assert np.abs(Y[0] - ref).max() <= 1e-12 * np.abs(ref).max()
+            assert np.abs(Y2 - Y).max() <= 1e-12 * np.abs(Y).max()
+        else:
+            assert sw == first[1] and sw2 == first[3], (rep, sw, sw2, first[1], first[3])
+            assert np.array_equal(Y, first[0]) and np.array_equal(Y2, first[2]), rep
+
+
 def test_dual_cone_product_prox(fos, oracle):
     """cones.jl:122-142 on a mixed product: Zero + NonNeg + SOC + SOC + SDP rows, Free + NonNeg vars."""
     from fos_b200 import problems
