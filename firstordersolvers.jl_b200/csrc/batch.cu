@@ -143,15 +143,23 @@ __device__ __forceinline__ void bt_pass(BK &k, const double *X0, const double *X
         __syncwarp();
         if (k.lane == 0) mbar_arrive(&k.empty[k.stage]);  // the tile is in registers: hand the stage back early
         warp_transpose_reduce<V>(rs, k.lane);
-        double *part = k.s_part + (tile & 1) * (16 * V);
+        // The warps' partial row sums wait in shared memory; the consumers meet once per BT_GROUP tiles (the per-tile
+        // barrier was 17 % of the kernel's stall samples, profiles/r2_c5_notes.md).  2 * BT_GROUP buffers: a buffer is
+        // written again two groups later, and the barrier of the group in between separates that from its readers.
+        double *part = k.s_part + (tile & (2 * BT_GROUP - 1)) * (CW * V);
         constexpr int LPV = 32 / V;  // lanes that end up holding the same value
         if ((k.lane & (LPV - 1)) == 0) part[k.warp * V + (k.lane / LPV)] = rs[0];
-        cbar(k.NT);
-        if (k.ct < V) {
-            double sum = 0.0;
-            for (int w = 0; w < CW; w++) sum += part[w * V + k.ct];
-            const int v = k.ct / BT_TR, r = k.ct - v * BT_TR;
-            k.s_ax[v * mr + __ldg(k.drow + row0 + r)] = sum;
+        if ((tile & (BT_GROUP - 1)) == BT_GROUP - 1 || tile == a.ntiles - 1) {
+            cbar(k.NT);
+            const int t0 = tile & ~(BT_GROUP - 1), nt = tile - t0 + 1;
+            if (k.ct < V * nt) {
+                const int tt = k.ct / V, idx = k.ct - tt * V;
+                const double *pt = k.s_part + ((t0 + tt) & (2 * BT_GROUP - 1)) * (CW * V);
+                double sum = 0.0;
+                for (int w = 0; w < CW; w++) sum += pt[w * V + idx];  // same order as ever: bitwise the per-tile result
+                const int v = idx / BT_TR, r = idx - v * BT_TR;
+                k.s_ax[v * mr + __ldg(k.drow + (t0 + tt) * BT_TR + r)] = sum;
+            }
         }
         k.t++;
         if (++k.stage == S) {
@@ -609,8 +617,8 @@ __global__ void __launch_bounds__(MAXT, MINB) k_batch_solve(const BatchArgs a)
     double *s_ax = tiles + (size_t)a.S * tile_elems;
     double *s_atw = s_ax + 2 * a.mr;
     double *s_wv = s_atw + 2 * a.L.n_pad;
-    double *s_part = s_wv + 2 * a.mr;           // [2 tile parities][16 warps][2 * BT_TR] row-sum partials
-    double *s_red = s_part + 2 * 16 * 2 * BT_TR;
+    double *s_part = s_wv + 2 * a.mr;           // [2 * BT_GROUP tiles][CW warps][2 * BT_TR] row-sum partials
+    double *s_red = s_part + 2 * BT_GROUP * a.CW * 2 * BT_TR;
     SocScale *s_soc = reinterpret_cast<SocScale *>(s_red + 8 * 16);
     uint64_t *full = reinterpret_cast<uint64_t *>(s_soc + BT_MAX_SOC);
     uint64_t *empty = full + BT_MAX_STAGES;
@@ -911,7 +919,7 @@ BatchGeom batch_geometry(int64_t m, int64_t n)
     if ((int64_t)g.KP * 32 * BT_MAX_CW < npairs) throw Error(FOS_ERR_UNSUPPORTED, "batch mode: n too large");
     g.CW = std::max(4, (npairs + g.KP * 32 - 1) / (g.KP * 32));
     const size_t tile_bytes = (size_t)BT_TR * g.lda * 8;
-    const size_t fixed = (size_t)(4 * (m_pad + 16) + 2 * n_pad + 2 * 16 * 2 * BT_TR + 8 * 16) * 8 +
+    const size_t fixed = (size_t)(4 * (m_pad + 16) + 2 * n_pad + 2 * BT_GROUP * g.CW * 2 * BT_TR + 8 * 16) * 8 +
                          BT_MAX_SOC * sizeof(SocScale) + 2 * BT_MAX_STAGES * 8 + 64;
     // two CTAs (= two problems) per SM when they fit: one CTA's vector phases overlap the other's pass
     g.ctas_per_sm = 1;

@@ -14,6 +14,7 @@ namespace fos {
 
 constexpr int BT_TR = 8;            // rows per A tile (NV * TR = 16 row sums per tile).  4-row tiles (four 17 KB stages at
                                     // config 5) were measured 12 % SLOWER: the per-tile barrier + reduce dominates (profiles/r2_c5_notes.md)
+constexpr int BT_GROUP = 4;         // tiles between two meetings of the consumer warps (power of two)
 constexpr int BT_MAX_STAGES = 4;
 constexpr int BT_MAX_CW = 15;       // consumer warps
 constexpr int BT_MAX_KP = 4;        // column pairs per consumer thread
