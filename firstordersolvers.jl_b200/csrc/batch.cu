@@ -648,6 +648,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_batch_solve(const BatchArgs a)
             int tix = 0;
             int s = 0;
             uint32_t eph = 0;  // parity to wait for on empty[s] (first used by tiles S..2S-1); flips every S tiles
+            const uint64_t stream_once = l2_evict_first_policy();  // the active problems' tiles (296 x 1 MB) never fit L2
             for (uint32_t T = 0;; T++) {
                 if (T >= (uint32_t)a.S) mbar_wait(&empty[s], eph);
                 while (base == nullptr && *s_switch_at == 0xffffffffu) {
@@ -659,7 +660,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_batch_solve(const BatchArgs a)
                     tix = 0;
                 }
                 mbar_expect_tx(&full[s], tile_bytes);
-                bulk_load_1d(tiles + (size_t)s * tile_elems, base + (size_t)tix * tile_elems, tile_bytes, &full[s]);
+                bulk_load_1d_hint(tiles + (size_t)s * tile_elems, base + (size_t)tix * tile_elems, tile_bytes, &full[s], stream_once);
                 tix = tix + 1 == a.ntiles ? 0 : tix + 1;
                 if (++s == a.S) {
                     s = 0;
