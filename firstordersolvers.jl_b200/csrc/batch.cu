@@ -648,7 +648,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_batch_solve(const BatchArgs a)
             int tix = 0;
             int s = 0;
             uint32_t eph = 0;  // parity to wait for on empty[s] (first used by tiles S..2S-1); flips every S tiles
-            const uint64_t stream_once = l2_evict_first_policy();  // the active problems' tiles (296 x 1 MB) never fit L2
+            const uint64_t stream_once = l2_policy_evict_first();  // the active problems' tiles (296 x 1 MB) never fit L2
             for (uint32_t T = 0;; T++) {
                 if (T >= (uint32_t)a.S) mbar_wait(&empty[s], eph);
                 while (base == nullptr && *s_switch_at == 0xffffffffu) {

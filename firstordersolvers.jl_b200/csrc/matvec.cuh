@@ -170,14 +170,9 @@ __device__ __forceinline__ void bulk_load_1d(void *dst, const void *src, uint32_
                  : "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
-// The same copy for data that is read once per pass (the batch kernel's A tiles): evict-first in L2, so that the stream
-// does not push out what IS reused (the problems' iteration vectors; ncu: DRAM traffic was 1.3x the tile bytes).
-__device__ __forceinline__ uint64_t l2_evict_first_policy()
-{
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
+// The same copy for data that is read once per pass (the batch kernel's A tiles), with the evict-first policy K1 uses for
+// its tiles: the stream must not push out what IS reused (the problems' iteration vectors; ncu: DRAM traffic was 1.3x
+// the tile bytes).
 __device__ __forceinline__ void bulk_load_1d_hint(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t policy)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
