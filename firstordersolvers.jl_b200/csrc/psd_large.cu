@@ -84,13 +84,6 @@ __device__ __forceinline__ void rr_pair_l(int s, int k, int D, int &a, int &b)
     }
 }
 
-__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p)
-{
-    unsigned int v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-
 // barrier among the CT CTAs of one cone: one atomic per CTA on the arrival counter; the last arriver
 // publishes the target on a separate cache line, which the others poll with relaxed loads
 __device__ __forceinline__ void group_barrier(PsdLargeCtl *ctl, unsigned int &epoch, unsigned int CT)
